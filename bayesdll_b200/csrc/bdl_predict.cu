@@ -1,0 +1,325 @@
+// bdl_predict.cu -- posterior-predictive ensemble and calibration reductions
+// (north star (c)).
+//
+//   bdl_ensemble          log-mean-softmax over S samples     methods/sgld.py:299-300, csgld.py:416-431
+//   bdl_ce_err            CE sum + error count                methods/sgld.py:302-306,314-315
+//   bdl_probsum_*         sample-sharded variant (one all-reduce of [B,K] probability sums, section 8e)
+//   bdl_calibrate         reliability bins + NLL              calibration.py:43-65, 246-249
+//
+// These tensors are tiny ([B,K,S] <= 64*37*40, [N,K] = 3669*37): the kernels are latency-bound, one
+// warp per row with shuffle reductions; shared-memory bin counters for the histogram.
+#include <math_constants.h>
+
+#include "bdl_common.cuh"
+
+namespace bdl {
+
+__device__ __forceinline__ float warp_max(float x) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) x = fmaxf(x, __shfl_xor_sync(0xffffffffu, x, o));
+    return x;
+}
+__device__ __forceinline__ float warp_sum(float x) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+    return x;
+}
+__device__ __forceinline__ double warp_sum(double x) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+    return x;
+}
+__device__ __forceinline__ double warp_max(double x) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) x = fmax(x, __shfl_xor_sync(0xffffffffu, x, o));
+    return x;
+}
+
+constexpr int kPredThreads = 256;
+constexpr int kPredWarps = kPredThreads / 32;
+
+__device__ __forceinline__ float mix(float comp, float w, float prev, int mode) {
+    if (mode == 0) return comp;
+    const float t = __fmul_rn(w, comp);                  // weight * component_out
+    return mode == 1 ? t : __fadd_rn(prev, t);           // batch_logits += ...
+}
+
+// One warp per batch row b.  lse_s = logsumexp_K(L[b,:,s]) is kept in shared memory (S floats per warp).
+__global__ void __launch_bounds__(kPredThreads)
+ensemble_kernel(const float* __restrict__ L, uint32_t B, uint32_t K, uint32_t S, float log_S, float weight, int mode,
+                float* __restrict__ out) {
+    extern __shared__ float s_lse[];                     // [kPredWarps][2*S]: max_s, log-sum_s
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    float* mx_s = s_lse + static_cast<size_t>(warp) * 2 * S;
+    float* ls_s = mx_s + S;
+    for (uint32_t b = blockIdx.x * kPredWarps + warp; b < B; b += gridDim.x * kPredWarps) {
+        const float* row = L + static_cast<size_t>(b) * K * S;
+        // log_softmax over K for every sample s:  (x - max) - log(sum exp(x - max))
+        for (uint32_t s = 0; s < S; ++s) {
+            float mx = -CUDART_INF_F;
+            for (uint32_t k = lane; k < K; k += 32) mx = fmaxf(mx, row[k * S + s]);
+            mx = warp_max(mx);
+            float sum = 0.f;
+            for (uint32_t k = lane; k < K; k += 32) sum += expf(row[k * S + s] - mx);
+            sum = warp_sum(sum);
+            if (lane == 0) {
+                mx_s[s] = mx;
+                ls_s[s] = logf(sum);
+            }
+        }
+        __syncwarp();
+        // logsumexp over S of the log-probabilities, minus log S
+        for (uint32_t k = lane; k < K; k += 32) {
+            float m2 = -CUDART_INF_F;
+            for (uint32_t s = 0; s < S; ++s) m2 = fmaxf(m2, (row[k * S + s] - mx_s[s]) - ls_s[s]);
+            float sum = 0.f;
+            for (uint32_t s = 0; s < S; ++s) sum += expf(((row[k * S + s] - mx_s[s]) - ls_s[s]) - m2);
+            const float comp = (logf(sum) + m2) - log_S;
+            float* o = out + static_cast<size_t>(b) * K + k;
+            *o = mix(comp, weight, mode == 2 ? *o : 0.f, mode);
+        }
+        __syncwarp();
+    }
+}
+
+// prob_sum[b,k] += softmax_K(logits[b,:])[k]
+__global__ void __launch_bounds__(kPredThreads)
+probsum_accum_kernel(const float* __restrict__ logits, uint32_t B, uint32_t K, float* __restrict__ prob_sum) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (uint32_t b = blockIdx.x * kPredWarps + warp; b < B; b += gridDim.x * kPredWarps) {
+        const float* row = logits + static_cast<size_t>(b) * K;
+        float mx = -CUDART_INF_F;
+        for (uint32_t k = lane; k < K; k += 32) mx = fmaxf(mx, row[k]);
+        mx = warp_max(mx);
+        float sum = 0.f;
+        for (uint32_t k = lane; k < K; k += 32) sum += expf(row[k] - mx);
+        sum = warp_sum(sum);
+        for (uint32_t k = lane; k < K; k += 32) prob_sum[static_cast<size_t>(b) * K + k] += expf(row[k] - mx) / sum;
+    }
+}
+
+__global__ void __launch_bounds__(kPredThreads)
+probsum_finalize_kernel(const float* __restrict__ prob_sum, uint32_t total, float log_S, float weight, int mode,
+                        float* __restrict__ out) {
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+        const float comp = logf(prob_sum[i]) - log_S;
+        out[i] = mix(comp, weight, mode == 2 ? out[i] : 0.f, mode);
+    }
+}
+
+// Single CTA (B is a batch: tens to hundreds of rows) so that the accumulation order is fixed.
+__global__ void __launch_bounds__(kPredThreads)
+ce_err_kernel(const float* __restrict__ logits, const int64_t* __restrict__ y, uint32_t B, uint32_t K,
+              double* __restrict__ loss_sum, int32_t* __restrict__ err_count) {
+    __shared__ float s_loss[kPredWarps];
+    __shared__ int s_err[kPredWarps];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    float loss = 0.f;
+    int err = 0;
+    for (uint32_t b = warp; b < B; b += kPredWarps) {
+        const float* row = logits + static_cast<size_t>(b) * K;
+        float mx = -CUDART_INF_F;
+        int arg = 0x7fffffff;
+        for (uint32_t k = lane; k < K; k += 32) {
+            const float x = row[k];
+            if (x > mx) { mx = x; arg = static_cast<int>(k); }       // first max within the lane's stride
+        }
+        // warp arg-max with lowest-index tie-break (torch.max returns the first maximal index on CUDA ties unspecified;
+        // ties have probability ~0 for real logits)
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const float omx = __shfl_xor_sync(0xffffffffu, mx, o);
+            const int oarg = __shfl_xor_sync(0xffffffffu, arg, o);
+            if (omx > mx || (omx == mx && oarg < arg)) { mx = omx; arg = oarg; }
+        }
+        float sum = 0.f;
+        for (uint32_t k = lane; k < K; k += 32) sum += expf(row[k] - mx);
+        sum = warp_sum(sum);
+        if (lane == 0) {
+            const int64_t t = y[b];
+            loss += -((row[t] - mx) - logf(sum));                    // -log_softmax[y]
+            err += (arg != static_cast<int>(t));
+        }
+    }
+    if (lane == 0) { s_loss[warp] = loss; s_err[warp] = err; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float tl = 0.f;
+        int te = 0;
+        for (int w = 0; w < kPredWarps; ++w) { tl += s_loss[w]; te += s_err[w]; }
+        *loss_sum += static_cast<double>(tl);
+        *err_count += te;
+    }
+}
+
+// -------------------------------------------------------------------------------------------
+// calibration: one warp per row; per-CTA shared-memory bin counters; fp64 compare against the
+// host-computed numpy edges (np.linspace(0, 1+1e-8, M+1)[1:]); np.digitize == #edges <= p.
+// -------------------------------------------------------------------------------------------
+constexpr int kMaxBins = 128;
+
+template <typename T>
+__device__ __forceinline__ T t_exp(T x);
+template <> __device__ __forceinline__ float t_exp<float>(float x) { return expf(x); }
+template <> __device__ __forceinline__ double t_exp<double>(double x) { return exp(x); }
+template <typename T>
+__device__ __forceinline__ T t_log(T x);
+template <> __device__ __forceinline__ float t_log<float>(float x) { return logf(x); }
+template <> __device__ __forceinline__ double t_log<double>(double x) { return log(x); }
+
+template <typename T>
+__global__ void __launch_bounds__(kPredThreads)
+calibrate_kernel(const float* __restrict__ logits, const int64_t* __restrict__ labels, uint32_t N, uint32_t K, T temp,
+                 const double* __restrict__ edges, uint32_t M, double* __restrict__ bin_size,
+                 double* __restrict__ acc_sum, double* __restrict__ conf_sum, double* __restrict__ nll_sum,
+                 unsigned long long* __restrict__ near_edge, int32_t* __restrict__ binned) {
+    __shared__ double s_edges[kMaxBins];
+    __shared__ unsigned int s_size[kMaxBins];
+    __shared__ unsigned int s_acc[kMaxBins];
+    __shared__ double s_conf[kMaxBins];
+    __shared__ double s_nll;
+    __shared__ unsigned int s_near;
+    for (uint32_t i = threadIdx.x; i < M; i += blockDim.x) {
+        s_edges[i] = edges[i];
+        s_size[i] = 0; s_acc[i] = 0; s_conf[i] = 0.0;
+    }
+    if (threadIdx.x == 0) { s_nll = 0.0; s_near = 0; }
+    __syncthreads();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const double guess_scale = static_cast<double>(M) / (1.0 + 1e-8);
+    const bool scaled = !(temp == T(1));
+    for (uint32_t r = blockIdx.x * kPredWarps + warp; r < N; r += gridDim.x * kPredWarps) {
+        const float* row = logits + static_cast<size_t>(r) * K;
+        const int64_t lab = labels[r];
+        T mx = -CUDART_INF;
+        for (uint32_t k = lane; k < K; k += 32) {
+            const T x = scaled ? static_cast<T>(row[k]) / temp : static_cast<T>(row[k]);
+            mx = x > mx ? x : mx;
+        }
+        mx = warp_max(mx);
+        T sum = 0;
+        for (uint32_t k = lane; k < K; k += 32) {
+            const T x = scaled ? static_cast<T>(row[k]) / temp : static_cast<T>(row[k]);
+            sum += t_exp<T>(x - mx);
+        }
+        sum = warp_sum(sum);
+        for (uint32_t k = lane; k < K; k += 32) {
+            const T x = scaled ? static_cast<T>(row[k]) / temp : static_cast<T>(row[k]);
+            const T pt = t_exp<T>(x - mx) / sum;
+            const double p = static_cast<double>(pt);
+            int b = static_cast<int>(p * guess_scale);
+            b = b < 0 ? 0 : (b > static_cast<int>(M) ? static_cast<int>(M) : b);
+            while (b < static_cast<int>(M) && s_edges[b] <= p) ++b;          // digitize: #edges <= p
+            while (b > 0 && s_edges[b - 1] > p) --b;
+            // certification: is p within 16 ulp(T) of the nearest edge?  (a different-but-valid softmax
+            // rounding could then land in the neighbouring bin)
+            const double tol = p * (sizeof(T) == 4 ? 16.0 * 5.9604644775390625e-08 : 16.0 * 1.1102230246251565e-16);
+            const double dl = b > 0 ? p - s_edges[b - 1] : 1.0;
+            const double dr = b < static_cast<int>(M) ? s_edges[b] - p : 1.0;
+            if (dl <= tol || dr <= tol) atomicAdd(&s_near, 1u);
+            if (binned) binned[static_cast<size_t>(r) * K + k] = b;
+            if (b < static_cast<int>(M)) {
+                atomicAdd(&s_size[b], 1u);
+                if (static_cast<int64_t>(k) == lab) atomicAdd(&s_acc[b], 1u);
+                atomicAdd(&s_conf[b], p);
+            }
+        }
+        if (lane == 0) {
+            const T xl = scaled ? static_cast<T>(row[lab]) / temp : static_cast<T>(row[lab]);
+            const T nll = (t_log<T>(sum) + mx) - xl;                          // logsumexp - logit[y]
+            atomicAdd(&s_nll, static_cast<double>(nll));
+        }
+    }
+    __syncthreads();
+    for (uint32_t i = threadIdx.x; i < M; i += blockDim.x) {
+        if (s_size[i]) {
+            atomicAdd(&bin_size[i], static_cast<double>(s_size[i]));
+            atomicAdd(&acc_sum[i], static_cast<double>(s_acc[i]));
+            atomicAdd(&conf_sum[i], s_conf[i]);
+        }
+    }
+    if (threadIdx.x == 0) {
+        atomicAdd(nll_sum, s_nll);
+        if (near_edge && s_near) atomicAdd(near_edge, static_cast<unsigned long long>(s_near));
+    }
+}
+
+static uint32_t rows_grid(uint32_t rows) {
+    uint32_t need = (rows + kPredWarps - 1) / kPredWarps;
+    uint32_t cap = static_cast<uint32_t>(num_sms() * 4);
+    return need < cap ? (need ? need : 1) : cap;
+}
+
+}  // namespace bdl
+
+extern "C" int bdl_ensemble(const float* logits_all, uint32_t B, uint32_t K, uint32_t S, float log_S, float weight,
+                            int mode, float* out, void* stream) {
+    using namespace bdl;
+    BDL_REQUIRE(logits_all && out, BDL_ERR_INVALID, "bdl_ensemble: null pointer");
+    BDL_REQUIRE(K >= 1 && S >= 1, BDL_ERR_INVALID, "bdl_ensemble: K and S must be >= 1");
+    BDL_REQUIRE(mode >= 0 && mode <= 2, BDL_ERR_INVALID, "bdl_ensemble: mode must be 0,1,2");
+    if (B == 0) return BDL_OK;
+    const size_t smem = static_cast<size_t>(kPredWarps) * 2 * S * sizeof(float);
+    BDL_REQUIRE(smem <= 48 * 1024, BDL_ERR_UNSUPPORTED, "bdl_ensemble: S=%u too large", S);
+    ensemble_kernel<<<rows_grid(B), kPredThreads, smem, static_cast<cudaStream_t>(stream)>>>(logits_all, B, K, S, log_S,
+                                                                                           weight, mode, out);
+    return check_cuda(cudaGetLastError(), "ensemble_kernel launch");
+}
+
+extern "C" int bdl_ce_err(const float* logits, const int64_t* y, uint32_t B, uint32_t K, double* loss_sum,
+                          int32_t* err_count, void* stream) {
+    using namespace bdl;
+    BDL_REQUIRE(logits && y && loss_sum && err_count, BDL_ERR_INVALID, "bdl_ce_err: null pointer");
+    BDL_REQUIRE(K >= 1, BDL_ERR_INVALID, "bdl_ce_err: K must be >= 1");
+    if (B == 0) return BDL_OK;
+    ce_err_kernel<<<1, kPredThreads, 0, static_cast<cudaStream_t>(stream)>>>(logits, y, B, K, loss_sum, err_count);
+    return check_cuda(cudaGetLastError(), "ce_err_kernel launch");
+}
+
+extern "C" int bdl_probsum_accum(const float* logits, uint32_t B, uint32_t K, float* prob_sum, void* stream) {
+    using namespace bdl;
+    BDL_REQUIRE(logits && prob_sum, BDL_ERR_INVALID, "bdl_probsum_accum: null pointer");
+    BDL_REQUIRE(K >= 1, BDL_ERR_INVALID, "bdl_probsum_accum: K must be >= 1");
+    if (B == 0) return BDL_OK;
+    probsum_accum_kernel<<<rows_grid(B), kPredThreads, 0, static_cast<cudaStream_t>(stream)>>>(logits, B, K, prob_sum);
+    return check_cuda(cudaGetLastError(), "probsum_accum_kernel launch");
+}
+
+extern "C" int bdl_probsum_finalize(const float* prob_sum, uint32_t B, uint32_t K, float log_S, float weight, int mode,
+                                    float* out, void* stream) {
+    using namespace bdl;
+    BDL_REQUIRE(prob_sum && out, BDL_ERR_INVALID, "bdl_probsum_finalize: null pointer");
+    BDL_REQUIRE(mode >= 0 && mode <= 2, BDL_ERR_INVALID, "bdl_probsum_finalize: mode must be 0,1,2");
+    const uint64_t total = static_cast<uint64_t>(B) * K;
+    BDL_REQUIRE(total < 0xFFFFFFFFull, BDL_ERR_INVALID, "bdl_probsum_finalize: B*K too large");
+    if (total == 0) return BDL_OK;
+    uint32_t grid = static_cast<uint32_t>((total + kPredThreads - 1) / kPredThreads);
+    const uint32_t cap = static_cast<uint32_t>(num_sms() * 4);
+    if (grid > cap) grid = cap;
+    probsum_finalize_kernel<<<grid, kPredThreads, 0, static_cast<cudaStream_t>(stream)>>>(
+        prob_sum, static_cast<uint32_t>(total), log_S, weight, mode, out);
+    return check_cuda(cudaGetLastError(), "probsum_finalize_kernel launch");
+}
+
+extern "C" int bdl_calibrate(const float* logits, const int64_t* labels, uint64_t N, uint32_t K, double temperature,
+                             int use_f64, const double* edges, uint32_t M, double* bin_size, double* acc_sum,
+                             double* conf_sum, double* nll_sum, unsigned long long* near_edge, int32_t* binned,
+                             void* stream) {
+    using namespace bdl;
+    BDL_REQUIRE(logits && labels && edges && bin_size && acc_sum && conf_sum && nll_sum, BDL_ERR_INVALID,
+                "bdl_calibrate: null pointer");
+    BDL_REQUIRE(M >= 1 && M <= static_cast<uint32_t>(kMaxBins), BDL_ERR_UNSUPPORTED, "bdl_calibrate: num_bins=%u not in [1,%d]", M, kMaxBins);
+    BDL_REQUIRE(K >= 1 && N < 0xFFFFFFFFull, BDL_ERR_INVALID, "bdl_calibrate: bad N/K");
+    BDL_REQUIRE(temperature > 0.0, BDL_ERR_INVALID, "bdl_calibrate: temperature must be > 0");
+    if (N == 0) return BDL_OK;
+    const uint32_t grid = rows_grid(static_cast<uint32_t>(N));
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (use_f64)
+        calibrate_kernel<double><<<grid, kPredThreads, 0, st>>>(logits, labels, static_cast<uint32_t>(N), K, temperature,
+                                                                edges, M, bin_size, acc_sum, conf_sum, nll_sum, near_edge, binned);
+    else
+        calibrate_kernel<float><<<grid, kPredThreads, 0, st>>>(logits, labels, static_cast<uint32_t>(N), K,
+                                                               static_cast<float>(temperature), edges, M, bin_size,
+                                                               acc_sum, conf_sum, nll_sum, near_edge, binned);
+    return check_cuda(cudaGetLastError(), "calibrate_kernel launch");
+}

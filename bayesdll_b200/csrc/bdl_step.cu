@@ -1,0 +1,331 @@
+// bdl_step.cu -- the fused SG-MCMC sampler update.
+//
+// One pass over the padded flat state replaces the reference's per-tensor Python loop
+// (methods/sghmc.py:482-510 etc.) *and* the torch.optim.SGD step that follows it
+// (methods/sghmc.py:229): prior pull, friction/momentum, Adam moments, Gaussian noise (injected
+// or in-kernel Philox), SGD momentum buffer and the parameter write, with every element read
+// once and written once.
+//
+// Roofline: HBM bandwidth.  Algorithmic bytes per element (fp32):
+//   SGLD mu!=0 24 (R theta,g,theta0,b; W b,theta) | SGLD mu=0 16 | SGHMC 24 | cSGHMC 20
+//   Adam-SGHMC mu!=0 48 / mu=0 40 | Adam-cSGHMC 40 | +4 with injected noise.
+//
+// Arithmetic: every operation is an explicitly rounded fp32 intrinsic in the reference's
+// operation order so that, with injected noise, results are bit-identical
+// to oracle/ (and hence to the reference's eager ops).  The only fused multiply-add is the one
+// torch's `add_(x, alpha=-lr)` performs.
+//
+// Mapping: persistent grid-stride CTAs (grid = #SM * ctas_per_sm), 256 threads, each thread owns
+// kU float4 groups per tile, consecutive threads touch consecutive 16-byte groups (512 B per warp
+// per stream), all loads of a tile are issued before the first dependent instruction.
+#include "bdl_common.cuh"
+
+namespace bdl {
+
+struct StepParams {
+    float* theta;
+    const float* g;
+    const float* theta0;
+    float* v;
+    float* m;
+    float* s;
+    float* buf;
+    const float* xi;
+    const bdl_run* runs;
+    uint32_t nruns;
+    uint32_t n4;  // number of float4 groups
+    // scalars (already rounded to fp32 by the host)
+    float lr[2], neg_lr[2], c[2];
+    float oma, sig2, inv_sig2, N, inv_N, mu;
+    float b1, omb1, b2, omb2, bc1, inv_bc1, bc2, inv_bc2, eps, two_alpha, nd, T, inv_T;
+    int first_step, add_noise;
+    NoiseKey key;
+};
+
+struct RunCursor {
+    uint32_t idx;
+    uint32_t end4;        // end / 4 of the current run
+    uint32_t cls;
+    const float* gbase;   // address of gradient element for flat index i is gbase + i
+    uint64_t valid_end;
+    bool own_g;
+};
+
+__device__ __forceinline__ void cursor_load(RunCursor& c, const StepParams& p, uint32_t idx) {
+    const bdl_run* r = p.runs + idx;
+    c.idx = idx;
+    c.end4 = static_cast<uint32_t>(__ldg(&r->end) >> 2);
+    c.cls = __ldg(&r->cls);
+    const float* gr = reinterpret_cast<const float*>(__ldg(reinterpret_cast<const unsigned long long*>(&r->g_dev)));
+    c.own_g = gr != nullptr;
+    c.valid_end = __ldg(&r->valid_end);
+    c.gbase = c.own_g ? gr - __ldg(&r->begin) : p.g;
+}
+
+__device__ __forceinline__ void cursor_seek(RunCursor& c, const StepParams& p, uint32_t q) {
+    // runs are sorted and contiguous; q only ever increases within a thread
+    while (q >= c.end4 && c.idx + 1 < p.nruns) cursor_load(c, p, c.idx + 1);
+}
+
+// -------------------------------------------------------------------------------------------
+// per-element update rules
+// -------------------------------------------------------------------------------------------
+template <int kDiv>
+__device__ __forceinline__ float prior_term(const StepParams& p, float th, float th0) {
+    float d = __fsub_rn(th, th0);                       // (p - p0)
+    d = div_scalar<kDiv>(d, p.sig2, p.inv_sig2);        //   / prior_sig**2
+    d = div_scalar<kDiv>(d, p.N, p.inv_N);              //   / N
+    return d;
+}
+
+template <bool kHasBuf>
+__device__ __forceinline__ float sgd_apply(const StepParams& p, float th, float gp, float neg_lr, float& b) {
+    float d = gp;
+    if constexpr (kHasBuf) {
+        b = p.first_step ? gp : __fadd_rn(__fmul_rn(b, p.mu), gp);
+        d = b;
+    }
+    return __fmaf_rn(d, neg_lr, th);                    // param.add_(d, alpha=-lr)
+}
+
+template <int kVariant, bool kHasBuf, int kDiv>
+__device__ __forceinline__ void update_one(const StepParams& p, uint32_t cls, float& th, float g, float th0,
+                                           float& v, float& m, float& s, float& b, float xi) {
+    const int h = cls & BDL_CLS_HEAD;
+    const bool prior = (cls & BDL_CLS_PRIOR) != 0;
+    const float lr = p.lr[h], neg_lr = p.neg_lr[h];
+    if constexpr (kVariant == BDL_SGLD) {
+        const float noise = __fmul_rn(p.c[h], xi);
+        const float add = prior ? __fadd_rn(prior_term<kDiv>(p, th, th0), noise) : noise;
+        const float gp = __fadd_rn(g, add);
+        th = sgd_apply<kHasBuf>(p, th, gp, neg_lr, b);
+    } else if constexpr (kVariant == BDL_SGHMC) {
+        const float gU = prior ? __fadd_rn(g, prior_term<kDiv>(p, th, th0)) : g;
+        const float noise = __fmul_rn(p.c[h], xi);
+        v = __fadd_rn(__fadd_rn(__fmul_rn(v, p.oma), __fmul_rn(lr, gU)), noise);
+        const float gp = __fadd_rn(g, v);               // p.grad = p.grad + v
+        th = __fmaf_rn(gp, neg_lr, th);                 // SGD(momentum=0)
+    } else if constexpr (kVariant == BDL_CSGHMC) {
+        const float gU = __fadd_rn(g, __fmul_rn(p.sig2, th));     // g + prior_sig * theta
+        float vn = __fsub_rn(__fmul_rn(v, p.oma), __fmul_rn(lr, gU));
+        if (p.add_noise) vn = __fadd_rn(vn, __fmul_rn(p.c[h], xi));
+        v = vn;
+        th = __fadd_rn(th, vn);                         // p.data.add_(v)
+    } else {
+        constexpr bool kCyc = (kVariant == BDL_ADAM_CSGHMC);
+        const float gl = kCyc ? div_scalar<kDiv>(g, p.T, p.inv_T) : g;
+        const float gU = prior ? __fadd_rn(gl, prior_term<kDiv>(p, th, th0)) : gl;
+        m = __fadd_rn(__fmul_rn(p.b1, m), __fmul_rn(p.omb1, gU));
+        s = __fadd_rn(__fmul_rn(p.b2, s), __fmul_rn(p.omb2, __fmul_rn(gU, gU)));
+        const float mh = div_scalar<kDiv>(m, p.bc1, p.inv_bc1);
+        const float sh = div_scalar<kDiv>(s, p.bc2, p.inv_bc2);
+        const float den = __fadd_rn(__fsqrt_rn(sh), p.eps);
+        const float pg = __fdiv_rn(mh, den);
+        const float pre = __frcp_rn(den);               // 1.0 / den
+        const float ns = __fmul_rn(p.nd, __fsqrt_rn(div_scalar<kDiv>(__fmul_rn(p.two_alpha, pre), p.N, p.inv_N)));
+        const float noise = __fmul_rn(ns, xi);
+        v = __fadd_rn(__fadd_rn(__fmul_rn(v, p.oma), __fmul_rn(lr, pg)), noise);
+        if constexpr (kCyc) {
+            th = __fmaf_rn(v, neg_lr, th);              // p.grad = v ; SGD(momentum=0)
+        } else {
+            const float gp = __fadd_rn(g, v);           // p.grad = p.grad + v
+            th = sgd_apply<kHasBuf>(p, th, gp, neg_lr, b);
+        }
+    }
+}
+
+template <int kVariant>
+struct Uses {
+    static constexpr bool theta0 = (kVariant != BDL_CSGHMC);
+    static constexpr bool v = (kVariant != BDL_SGLD);
+    static constexpr bool adam = (kVariant == BDL_ADAM_SGHMC || kVariant == BDL_ADAM_CSGHMC);
+};
+
+constexpr int kThreads = 256;
+
+// Resident CTAs per SM the kernel is compiled for: 16 data registers per stream per unroll step plus
+// ~28 registers of addressing / Philox state, rounded to the allocation granule, against the 64K-entry RF.
+template <int kVariant, bool kHasBuf, bool kPhilox, int kU>
+constexpr int min_blocks() {
+    int streams = (kVariant == BDL_SGLD) ? 3 : (kVariant == BDL_SGHMC) ? 4 : (kVariant == BDL_CSGHMC) ? 3 : 6;
+    streams += (kHasBuf ? 1 : 0) + (kPhilox ? 0 : 1);
+    int regs = 4 * kU * streams + 28;
+    regs = (regs + 7) / 8 * 8;
+    int blocks = 65536 / (kThreads * regs);
+    return blocks < 1 ? 1 : (blocks > 8 ? 8 : blocks);
+}
+
+template <int kVariant, bool kHasBuf, bool kPhilox, int kDiv, int kU>
+__global__ void __launch_bounds__(kThreads, (min_blocks<kVariant, kHasBuf, kPhilox, kU>()))
+step_kernel(const StepParams p) {
+    using U = Uses<kVariant>;
+    const uint32_t tile_groups = kThreads * kU;
+    const uint32_t ntiles = (p.n4 + tile_groups - 1) / tile_groups;
+    RunCursor cur;
+    cursor_load(cur, p, 0);
+
+    for (uint32_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const uint32_t q0 = tile * tile_groups + threadIdx.x;
+        float4 th[kU], g[kU], th0[kU], v[kU], m[kU], s[kU], b[kU], xi[kU];
+        uint32_t cls[kU];
+        // ---- issue every load of the tile first (kU * #streams independent 128-bit requests) ----
+#pragma unroll
+        for (int u = 0; u < kU; ++u) {
+            const uint32_t q = q0 + u * kThreads;
+            if (q < p.n4) {
+                const uint64_t i = static_cast<uint64_t>(q) << 2;
+                cursor_seek(cur, p, q);
+                cls[u] = cur.cls;
+                th[u] = ld_stream(p.theta + i);
+                g[u] = ld_stream(cur.gbase + i);
+                if (cur.own_g && i + 4 > cur.valid_end) {  // tail group of a per-run gradient: zero the padding lanes
+                    if (i + 0 >= cur.valid_end) g[u].x = 0.f;
+                    if (i + 1 >= cur.valid_end) g[u].y = 0.f;
+                    if (i + 2 >= cur.valid_end) g[u].z = 0.f;
+                    if (i + 3 >= cur.valid_end) g[u].w = 0.f;
+                }
+                if constexpr (U::theta0) th0[u] = ld_stream(p.theta0 + i);
+                if constexpr (U::v) v[u] = ld_stream(p.v + i);
+                if constexpr (U::adam) {
+                    m[u] = ld_stream(p.m + i);
+                    s[u] = ld_stream(p.s + i);
+                }
+                if constexpr (kHasBuf) b[u] = ld_stream(p.buf + i);
+                if constexpr (!kPhilox) xi[u] = ld_stream(p.xi + i);
+            }
+        }
+        // ---- compute + store ----
+#pragma unroll
+        for (int u = 0; u < kU; ++u) {
+            const uint32_t q = q0 + u * kThreads;
+            if (q < p.n4) {
+                const uint64_t i = static_cast<uint64_t>(q) << 2;
+                if constexpr (kPhilox) xi[u] = philox_normal4(p.key, q);
+                update_one<kVariant, kHasBuf, kDiv>(p, cls[u], th[u].x, g[u].x, th0[u].x, v[u].x, m[u].x, s[u].x, b[u].x, xi[u].x);
+                update_one<kVariant, kHasBuf, kDiv>(p, cls[u], th[u].y, g[u].y, th0[u].y, v[u].y, m[u].y, s[u].y, b[u].y, xi[u].y);
+                update_one<kVariant, kHasBuf, kDiv>(p, cls[u], th[u].z, g[u].z, th0[u].z, v[u].z, m[u].z, s[u].z, b[u].z, xi[u].z);
+                update_one<kVariant, kHasBuf, kDiv>(p, cls[u], th[u].w, g[u].w, th0[u].w, v[u].w, m[u].w, s[u].w, b[u].w, xi[u].w);
+                if constexpr (U::v) st_stream(p.v + i, v[u]);
+                if constexpr (U::adam) {
+                    st_stream(p.m + i, m[u]);
+                    st_stream(p.s + i, s[u]);
+                }
+                if constexpr (kHasBuf) st_stream(p.buf + i, b[u]);
+                st_stream(p.theta + i, th[u]);
+            }
+        }
+    }
+}
+
+// -------------------------------------------------------------------------------------------
+// host side
+// -------------------------------------------------------------------------------------------
+static int g_ctas_per_sm = 0;   // 0 = default
+static int g_unroll = 0;
+
+template <int kVariant, bool kHasBuf, bool kPhilox, int kDiv>
+static int launch_u(const StepParams& p, cudaStream_t st) {
+    constexpr bool kAdam = (kVariant == BDL_ADAM_SGHMC || kVariant == BDL_ADAM_CSGHMC);
+    const int unroll = g_unroll ? g_unroll : (kAdam ? 1 : 2);
+    int per_sm = g_ctas_per_sm;
+    if (per_sm == 0) {
+        per_sm = unroll == 1 ? min_blocks<kVariant, kHasBuf, kPhilox, 1>()
+               : unroll == 2 ? min_blocks<kVariant, kHasBuf, kPhilox, 2>()
+                             : min_blocks<kVariant, kHasBuf, kPhilox, 4>();
+    }
+    const uint32_t tile_groups = kThreads * unroll;
+    const uint32_t ntiles = (p.n4 + tile_groups - 1) / tile_groups;
+    uint32_t grid = static_cast<uint32_t>(num_sms() * per_sm);
+    if (grid > ntiles) grid = ntiles;
+    if (grid == 0) return BDL_OK;
+    switch (unroll) {
+        case 1: step_kernel<kVariant, kHasBuf, kPhilox, kDiv, 1><<<grid, kThreads, 0, st>>>(p); break;
+        case 2: step_kernel<kVariant, kHasBuf, kPhilox, kDiv, 2><<<grid, kThreads, 0, st>>>(p); break;
+        case 4: step_kernel<kVariant, kHasBuf, kPhilox, kDiv, 4><<<grid, kThreads, 0, st>>>(p); break;
+        default:
+            set_error("bdl_step: unsupported unroll %d (1, 2 or 4)", unroll);
+            return BDL_ERR_INVALID;
+    }
+    return check_cuda(cudaGetLastError(), "step_kernel launch");
+}
+
+template <int kVariant, bool kHasBuf>
+static int launch_nd(const StepParams& p, bool philox, int div, cudaStream_t st) {
+    if (philox) {
+        return div == BDL_DIV_IEEE ? launch_u<kVariant, kHasBuf, true, BDL_DIV_IEEE>(p, st)
+                                   : launch_u<kVariant, kHasBuf, true, BDL_DIV_RECIP>(p, st);
+    }
+    return div == BDL_DIV_IEEE ? launch_u<kVariant, kHasBuf, false, BDL_DIV_IEEE>(p, st)
+                               : launch_u<kVariant, kHasBuf, false, BDL_DIV_RECIP>(p, st);
+}
+
+}  // namespace bdl
+
+extern "C" int bdl_set_launch_config(int ctas_per_sm, int unroll) {
+    using namespace bdl;
+    BDL_REQUIRE(ctas_per_sm >= 0 && ctas_per_sm <= 32, BDL_ERR_INVALID, "ctas_per_sm out of range");
+    BDL_REQUIRE(unroll == 0 || unroll == 1 || unroll == 2 || unroll == 4, BDL_ERR_INVALID, "unroll must be 0,1,2,4");
+    g_ctas_per_sm = ctas_per_sm;
+    g_unroll = unroll;
+    return BDL_OK;
+}
+
+extern "C" int bdl_step(int variant, float* theta, const float* g, const float* theta0, float* v, float* m,
+                        float* s, float* buf, uint64_t n, const bdl_run* runs, uint32_t nruns,
+                        const bdl_scalars* sc, const bdl_noise* nz, void* stream) {
+    using namespace bdl;
+    BDL_REQUIRE(variant >= BDL_SGLD && variant <= BDL_ADAM_CSGHMC, BDL_ERR_INVALID, "bdl_step: unknown variant %d", variant);
+    BDL_REQUIRE(theta && runs && sc && nz, BDL_ERR_INVALID, "bdl_step: null theta/runs/scalars/noise");
+    BDL_REQUIRE(n % 4 == 0, BDL_ERR_INVALID, "bdl_step: n=%llu is not a multiple of 4", (unsigned long long)n);
+    BDL_REQUIRE((n >> 2) < 0xFFFFFFFFull, BDL_ERR_INVALID, "bdl_step: n too large for 32-bit group index");
+    BDL_REQUIRE(nruns >= 1 && nruns <= BDL_MAX_RUNS, BDL_ERR_INVALID, "bdl_step: nruns=%u out of range", nruns);
+    const bool adam = variant == BDL_ADAM_SGHMC || variant == BDL_ADAM_CSGHMC;
+    const bool has_buf = (variant == BDL_SGLD || variant == BDL_ADAM_SGHMC) && sc->mu != 0.0f;
+    BDL_REQUIRE(variant == BDL_CSGHMC || theta0, BDL_ERR_INVALID, "bdl_step: theta0 required");
+    BDL_REQUIRE(variant == BDL_SGLD || v, BDL_ERR_INVALID, "bdl_step: momentum buffer v required");
+    BDL_REQUIRE(!adam || (m && s), BDL_ERR_INVALID, "bdl_step: Adam moments m,s required");
+    BDL_REQUIRE(!has_buf || buf, BDL_ERR_INVALID, "bdl_step: SGD momentum buffer required when mu != 0");
+    BDL_REQUIRE(sc->div_mode == BDL_DIV_IEEE || sc->div_mode == BDL_DIV_RECIP, BDL_ERR_INVALID, "bdl_step: bad div_mode");
+    const void* ptrs[] = {theta, g, theta0, v, m, s, buf, nz->xi_dev};
+    for (const void* q : ptrs) BDL_REQUIRE(aligned16(q), BDL_ERR_ALIGN, "bdl_step: pointer %p is not 16-byte aligned", q);
+    if (n == 0) return BDL_OK;
+
+    StepParams p{};
+    p.theta = theta; p.g = g; p.theta0 = theta0; p.v = v; p.m = m; p.s = s; p.buf = buf;
+    p.xi = nz->xi_dev; p.runs = runs; p.nruns = nruns; p.n4 = static_cast<uint32_t>(n >> 2);
+    for (int h = 0; h < 2; ++h) {
+        p.lr[h] = sc->lr[h];
+        p.neg_lr[h] = -sc->lr[h];
+        p.c[h] = sc->noise_scale[h];
+    }
+    p.oma = sc->one_minus_alpha;
+    p.sig2 = sc->sig2; p.inv_sig2 = 1.0f / sc->sig2;
+    p.N = sc->N; p.inv_N = 1.0f / sc->N;
+    p.mu = sc->mu;
+    p.b1 = sc->beta1; p.omb1 = sc->one_minus_beta1; p.b2 = sc->beta2; p.omb2 = sc->one_minus_beta2;
+    p.bc1 = sc->bias_corr1; p.inv_bc1 = 1.0f / sc->bias_corr1;
+    p.bc2 = sc->bias_corr2; p.inv_bc2 = 1.0f / sc->bias_corr2;
+    p.eps = sc->eps; p.two_alpha = sc->two_alpha; p.nd = sc->nd;
+    p.T = sc->temperature; p.inv_T = 1.0f / sc->temperature;
+    p.first_step = sc->first_step; p.add_noise = sc->add_noise;
+    p.key.k0 = static_cast<uint32_t>(nz->seed); p.key.k1 = static_cast<uint32_t>(nz->seed >> 32);
+    p.key.stream_id = nz->stream_id;
+    p.key.sub_lo = static_cast<uint32_t>(nz->subseq); p.key.sub_hi = static_cast<uint32_t>(nz->subseq >> 32);
+
+    const bool philox = nz->xi_dev == nullptr;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const int d = sc->div_mode;
+    switch (variant) {
+        case BDL_SGLD:
+            return has_buf ? launch_nd<BDL_SGLD, true>(p, philox, d, st) : launch_nd<BDL_SGLD, false>(p, philox, d, st);
+        case BDL_SGHMC:
+            return launch_nd<BDL_SGHMC, false>(p, philox, d, st);
+        case BDL_CSGHMC:
+            return launch_nd<BDL_CSGHMC, false>(p, philox, d, st);
+        case BDL_ADAM_SGHMC:
+            return has_buf ? launch_nd<BDL_ADAM_SGHMC, true>(p, philox, d, st)
+                           : launch_nd<BDL_ADAM_SGHMC, false>(p, philox, d, st);
+        default:
+            return launch_nd<BDL_ADAM_CSGHMC, false>(p, philox, d, st);
+    }
+}

@@ -1,0 +1,211 @@
+"""Torch-tensor front end of the C ABI (include/bdl.h).  PyTorch is plumbing here: it owns the device
+memory and the stream; every numerical operation is a hand-written sm_100a kernel in libbdl.so.
+
+Every function validates device / dtype / contiguity on the Python side ("Error
+conventions"), launches asynchronously on the caller's current CUDA stream and raises ``BdlError`` on
+a non-zero status.  There is no CPU implementation: CPU tensors are rejected.
+"""
+import ctypes as C
+import math
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import (ADAM_CSGHMC, ADAM_SGHMC, CSGHMC, DIV_IEEE, DIV_RECIP, SGHMC, SGLD, STREAM_DRAW, STREAM_STEP,
+                   STREAM_USER, BdlError, Noise, Run, Scalars)
+
+__all__ = ["make_scalars", "upload_runs", "step", "philox_normal", "moments_avg", "moments_welford",
+           "capture_ring", "draw", "ensemble", "ce_err", "probsum_accum", "probsum_finalize", "calibrate",
+           "set_launch_config"]
+
+
+def _ptr(t, name, dtype=torch.float32, allow_none=False):
+    if t is None:
+        if allow_none:
+            return None
+        raise BdlError(f"{name}: tensor required")
+    if not isinstance(t, torch.Tensor) or not t.is_cuda:
+        raise BdlError(f"{name}: expected a CUDA tensor (bayesdll_b200 has no CPU path)")
+    if t.dtype != dtype:
+        raise BdlError(f"{name}: expected dtype {dtype}, got {t.dtype}")
+    if not t.is_contiguous():
+        raise BdlError(f"{name}: tensor must be contiguous")
+    return t.data_ptr()
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def set_launch_config(ctas_per_sm=0, unroll=0):
+    _lib.check(_lib.load().bdl_set_launch_config(ctas_per_sm, unroll), "bdl_set_launch_config")
+
+
+# ----------------------------------------------------------------------------------------------
+# host scalar preparation: Python doubles -> the fp32 values the reference's eager ops would use
+# ----------------------------------------------------------------------------------------------
+def make_scalars(variant, *, lr_body, lr_head, ND, Ninflate=1.0, prior_sig=1.0, nd=1.0, alpha=0.05, mu=0.0,
+                 beta1=0.9, beta2=0.999, eps=1e-8, temperature=1.0, t=1, first_step=False, add_noise=True,
+                 div_mode=DIV_RECIP):
+    """All arithmetic below is host fp64 exactly as written in the reference; ctypes' c_float performs the
+    double -> fp32 rounding torch applies when a Python scalar meets an fp32 tensor.
+
+    noise scale  SGLD   nd*np.sqrt(2/(N*lr))        methods/sgld.py:478,483
+                 SGHMC  nd*np.sqrt(2*a/(N*lr))      methods/sghmc.py:500
+                 cSGHMC nd*np.sqrt(2*a*lr)/N        methods/csghmc.py:765
+    """
+    N = ND * Ninflate
+    sc = Scalars()
+    lrs = (float(lr_body), float(lr_head))
+    for h, lr in enumerate(lrs):
+        sc.lr[h] = lr
+        if variant == SGLD:
+            c = nd * np.sqrt(2 / (N * lr))
+        elif variant == SGHMC:
+            c = nd * np.sqrt(2 * alpha / (N * lr))
+        elif variant == CSGHMC:
+            c = nd * np.sqrt((2 * alpha * lr)) / N
+        else:
+            c = 0.0
+        sc.noise_scale[h] = c
+    sc.one_minus_alpha = 1 - alpha
+    sc.sig2 = prior_sig if variant == CSGHMC else prior_sig ** 2
+    sc.N = N
+    sc.mu = mu if variant in (SGLD, ADAM_SGHMC) else 0.0
+    sc.beta1, sc.one_minus_beta1 = beta1, 1 - beta1
+    sc.beta2, sc.one_minus_beta2 = beta2, 1 - beta2
+    sc.bias_corr1 = 1 - beta1 ** t
+    sc.bias_corr2 = 1 - beta2 ** t
+    sc.eps = eps
+    sc.two_alpha = 2 * alpha
+    sc.nd = nd
+    sc.temperature = temperature
+    sc.first_step = int(bool(first_step))
+    sc.add_noise = int(bool(add_noise))
+    sc.div_mode = div_mode
+    return sc
+
+
+def upload_runs(run_array, device, out=None):
+    """Copy a ctypes bdl_run array to the device (uint8 tensor).  Returns (tensor, nruns)."""
+    nbytes = C.sizeof(run_array)
+    host = torch.frombuffer(bytearray(bytes(run_array)), dtype=torch.uint8)
+    if out is None or out.numel() < nbytes:
+        out = torch.empty(nbytes, dtype=torch.uint8, device=device)
+    out[:nbytes].copy_(host, non_blocking=False)
+    return out, len(run_array)
+
+
+def make_noise(xi=None, seed=0, subseq=0, stream_id=STREAM_STEP):
+    nz = Noise()
+    nz.xi_dev = 0 if xi is None else _ptr(xi, "xi")
+    nz.seed = int(seed) & 0xFFFFFFFFFFFFFFFF
+    nz.subseq = int(subseq) & 0xFFFFFFFFFFFFFFFF
+    nz.stream_id = int(stream_id)
+    return nz
+
+
+# ----------------------------------------------------------------------------------------------
+# kernels
+# ----------------------------------------------------------------------------------------------
+def step(variant, theta, g, theta0, v, m, s, buf, runs_dev, nruns, scalars, noise):
+    """One fused sampler update (bdl_step).  Tensors are padded-flat fp32 CUDA buffers; unused state may be
+    None.  ``noise`` from make_noise(); ``runs_dev`` from upload_runs()."""
+    n = theta.numel()
+    for name, t in (("g", g), ("theta0", theta0), ("v", v), ("m", m), ("s", s), ("buf", buf)):
+        if t is not None and t.numel() != n:
+            raise BdlError(f"{name}: length {t.numel()} != theta length {n}")
+    rc = _lib.load().bdl_step(
+        int(variant), _ptr(theta, "theta"), _ptr(g, "g", allow_none=True), _ptr(theta0, "theta0", allow_none=True),
+        _ptr(v, "v", allow_none=True), _ptr(m, "m", allow_none=True), _ptr(s, "s", allow_none=True),
+        _ptr(buf, "buf", allow_none=True), n, _ptr(runs_dev, "runs", torch.uint8), nruns,
+        C.byref(scalars), C.byref(noise), _stream())
+    _lib.check(rc, "bdl_step")
+
+
+def philox_normal(out, seed, stream_id=STREAM_USER, subseq=0):
+    rc = _lib.load().bdl_philox_normal(_ptr(out, "out"), out.numel(), int(seed) & 0xFFFFFFFFFFFFFFFF, int(stream_id),
+                                       int(subseq) & 0xFFFFFFFFFFFFFFFF, _stream())
+    _lib.check(rc, "bdl_philox_normal")
+    return out
+
+
+def moments_avg(theta, mom1, mom2, cnt, init=False, div_mode=DIV_RECIP):
+    """init: mom1 = theta*1.0, mom2 = theta**2.  else mom <- (theta^k + cnt*mom)/(cnt+1)."""
+    rc = _lib.load().bdl_moments_avg(_ptr(theta, "theta"), _ptr(mom1, "mom1"), _ptr(mom2, "mom2", allow_none=True),
+                                     theta.numel(), float(cnt), float(cnt + 1), int(init), div_mode, _stream())
+    _lib.check(rc, "bdl_moments_avg")
+
+
+def moments_welford(theta, mean, M2, n, init=False, div_mode=DIV_RECIP):
+    rc = _lib.load().bdl_moments_welford(_ptr(theta, "theta"), _ptr(mean, "mean"), _ptr(M2, "M2"), theta.numel(),
+                                         float(n), int(init), div_mode, _stream())
+    _lib.check(rc, "bdl_moments_welford")
+
+
+def capture_ring(theta, ring, slot):
+    n = theta.numel()
+    if ring.dim() != 2 or ring.shape[1] != n or not (0 <= slot < ring.shape[0]):
+        raise BdlError("ring must be [slots, n] and slot in range")
+    rc = _lib.load().bdl_capture_ring(_ptr(theta, "theta"), _ptr(ring, "ring"), int(slot), n, _stream())
+    _lib.check(rc, "bdl_capture_ring")
+
+
+VAR_FROM_MOMENTS, VAR_FROM_WELFORD, VAR_TINY, VAR_GIVEN = 0, 1, 2, 3
+
+
+def draw(mean, second, out, var_mode, scale, noise, div_mode=DIV_RECIP):
+    rc = _lib.load().bdl_draw(_ptr(mean, "mean"), _ptr(second, "second", allow_none=True), _ptr(out, "out"),
+                              mean.numel(), int(var_mode), float(scale), div_mode, C.byref(noise), _stream())
+    _lib.check(rc, "bdl_draw")
+
+
+def ensemble(logits_all, out, nst, weight=1.0, mode=0):
+    """logits_all [B,K,S] -> out [B,K] (see bdl_ensemble).  nst == 0 -> no '- log S'."""
+    B, K, S = logits_all.shape
+    log_S = float(np.float32(np.log(nst))) if nst > 0 else 0.0
+    rc = _lib.load().bdl_ensemble(_ptr(logits_all, "logits_all"), B, K, S, log_S, float(weight), int(mode),
+                                  _ptr(out, "out"), _stream())
+    _lib.check(rc, "bdl_ensemble")
+    return out
+
+
+def ce_err(logits, y, loss_sum, err_count):
+    B, K = logits.shape
+    rc = _lib.load().bdl_ce_err(_ptr(logits, "logits"), _ptr(y, "y", torch.int64), B, K,
+                                _ptr(loss_sum, "loss_sum", torch.float64), _ptr(err_count, "err_count", torch.int32),
+                                _stream())
+    _lib.check(rc, "bdl_ce_err")
+
+
+def probsum_accum(logits, prob_sum):
+    B, K = logits.shape
+    rc = _lib.load().bdl_probsum_accum(_ptr(logits, "logits"), B, K, _ptr(prob_sum, "prob_sum"), _stream())
+    _lib.check(rc, "bdl_probsum_accum")
+
+
+def probsum_finalize(prob_sum, out, n_samples, weight=1.0, mode=0):
+    B, K = prob_sum.shape
+    log_S = float(np.float32(np.log(n_samples))) if n_samples > 0 else 0.0
+    rc = _lib.load().bdl_probsum_finalize(_ptr(prob_sum, "prob_sum"), B, K, log_S, float(weight), int(mode),
+                                          _ptr(out, "out"), _stream())
+    _lib.check(rc, "bdl_probsum_finalize")
+    return out
+
+
+def calibrate(logits, labels, edges, temperature=1.0, use_f64=False, want_binned=False):
+    """Returns device tensors (bin_size[M], acc_sum[M], conf_sum[M], nll_sum[1], near_edge[1], binned|None)."""
+    N, K = logits.shape
+    M = edges.numel()
+    dev = logits.device
+    stats = torch.zeros(3 * M + 1, dtype=torch.float64, device=dev)
+    near = torch.zeros(1, dtype=torch.int64, device=dev)
+    binned = torch.empty(N * K, dtype=torch.int32, device=dev) if want_binned else None
+    base = stats.data_ptr()
+    rc = _lib.load().bdl_calibrate(
+        _ptr(logits, "logits"), _ptr(labels, "labels", torch.int64), N, K, float(temperature), int(use_f64),
+        _ptr(edges, "edges", torch.float64), M, base, base + 8 * M, base + 16 * M, base + 24 * M,
+        near.data_ptr(), None if binned is None else binned.data_ptr(), _stream())
+    _lib.check(rc, "bdl_calibrate")
+    return stats[:M], stats[M:2 * M], stats[2 * M:3 * M], stats[3 * M:], near, binned

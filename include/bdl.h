@@ -1,0 +1,200 @@
+/*
+ * bdl.h -- C ABI of libbdl: B200 (sm_100a) kernels for the SG-MCMC sampler hot path of
+ * BayesDLL (omarezz46/BayesDLL).  This is the drop-in boundary.
+ *
+ * The reference has no FFI today: its hot path is per-tensor Python loops over torch eager ops.
+ * Each entry point below names the reference call site (file:line, relative to the reference
+ * checkout) whose arithmetic it replaces.  INTEGRATION.md shows the ctypes binding a maintainer
+ * of the reference would add.
+ *
+ * Conventions
+ *   - plain C types only; no torch / C++ types cross the boundary.
+ *   - every pointer named *_dev is DEVICE memory owned by the caller (torch CUDA tensors in the
+ *     Python host).  The library never allocates, frees or retains caller memory.
+ *   - `stream` is a cudaStream_t passed as void*; all launches are asynchronous on it; no
+ *     hidden synchronisation.
+ *   - return value: 0 (BDL_OK) or a negative bdl_status; bdl_last_error() returns a
+ *     thread-local human-readable message.  No C++ exception crosses the boundary.
+ *   - flat buffers: fp32, base 16-byte aligned, length `n` a multiple of 4 elements.  Tensors
+ *     are laid out in named_parameters() order, every tensor start rounded up to a multiple of
+ *     4 elements ("padded flat layout"); padding elements are ordinary elements with g = 0.
+ *   - Python doubles are rounded to fp32 by the host exactly where the reference's eager ops
+ *     round them; bdl_scalars carries the already-rounded values.
+ */
+#ifndef BDL_H_
+#define BDL_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define BDL_ABI_VERSION 1
+
+typedef enum {
+    BDL_OK = 0,
+    BDL_ERR_INVALID = -1,   /* bad argument (null pointer, n not multiple of 4, unknown variant ...) */
+    BDL_ERR_ALIGN = -2,     /* a pointer is not 16-byte aligned */
+    BDL_ERR_CUDA = -3,      /* a CUDA runtime call failed; see bdl_last_error() */
+    BDL_ERR_UNSUPPORTED = -4
+} bdl_status;
+
+/* Sampler update rules. */
+typedef enum {
+    BDL_SGLD = 0,          /* methods/sgld.py:469-484 + SGD.step :226 ; methods/csgld.py:665-680 + :253 */
+    BDL_SGHMC = 1,         /* methods/sghmc.py:482-510 + SGD(momentum=0).step :229                      */
+    BDL_CSGHMC = 2,        /* methods/csghmc.py:747-778 (writes p.data, no optimizer step :304)         */
+    BDL_ADAM_SGHMC = 3,    /* methods/adam_sghmc.py:507-553 + SGD(momentum).step :233                   */
+    BDL_ADAM_CSGHMC = 4    /* methods/adam_csghmc.py:814-861 + SGD(momentum=0).step :322                */
+} bdl_variant;
+
+/* Element class bits (per run). */
+#define BDL_CLS_HEAD 1u    /* readout_name in pname  -> lr_head / head noise scale (methods/sghmc.py:485-488) */
+#define BDL_CLS_PRIOR 2u   /* prior pull enabled; cleared for 'bias' in pname && bias=='uninformative' (:494) */
+
+/* A run = a contiguous range of the padded flat layout whose elements share one class
+ * (and, optionally, one gradient tensor).  Runs are sorted, contiguous and cover [0, n). */
+typedef struct {
+    uint64_t begin;        /* first element, multiple of 4                                         */
+    uint64_t end;          /* one past the last element incl. padding, multiple of 4               */
+    uint64_t valid_end;    /* begin + number of real elements; [valid_end, end) is padding         */
+    const float* g_dev;    /* optional per-run gradient tensor (element 0 <-> flat index `begin`,   */
+                           /* 16-byte aligned, readable up to the next 16-byte boundary past its    */
+                           /* end); NULL -> read the flat gradient buffer                           */
+    uint32_t cls;          /* BDL_CLS_* bits                                                       */
+    uint32_t reserved;
+} bdl_run;
+
+#define BDL_MAX_RUNS 2048
+
+/* Division semantics for `tensor / python_scalar` (last row of the table):
+ * the reference on CPU divides (IEEE); the reference on CUDA multiplies by the fp32 reciprocal. */
+#define BDL_DIV_IEEE 0
+#define BDL_DIV_RECIP 1
+
+typedef struct {
+    float lr[2];             /* [body, head]   fp32(lr_e)                                              */
+    float noise_scale[2];    /* [body, head]   SGLD: nd*sqrt(2/(N lr)); SGHMC: nd*sqrt(2 a/(N lr));     */
+                             /*                cSGHMC: nd*sqrt(2 a lr)/N   (host fp64 -> fp32)          */
+    float one_minus_alpha;   /* fp32(1 - momentum_decay)                                               */
+    float sig2;              /* fp32(prior_sig**2);  cSGHMC: fp32(prior_sig) used as an L2 coefficient  */
+    float N;                 /* fp32(ND * Ninflate)                                                    */
+    float mu;                /* torch SGD momentum (args.momentum); 0 -> no momentum buffer            */
+    float beta1, one_minus_beta1, beta2, one_minus_beta2;
+    float bias_corr1;        /* fp32(1 - beta1**t), t after the increment (adam_sghmc.py:494,533)      */
+    float bias_corr2;        /* fp32(1 - beta2**t)                                                     */
+    float eps;               /* Adam epsilon                                                           */
+    float two_alpha;         /* fp32(2 * momentum_decay)   (adam_sghmc.py:541)                         */
+    float nd;                /* noise discount (Adam variants multiply it in-kernel, :541)             */
+    float temperature;       /* Adam-cSGHMC: g / T (adam_csghmc.py:829-831)                            */
+    int32_t first_step;      /* 1: SGD momentum buffer is initialised to g' (torch sgd.py)             */
+    int32_t add_noise;       /* cSGHMC: should_sample (csghmc.py:769); other variants ignore it        */
+    int32_t div_mode;        /* BDL_DIV_IEEE | BDL_DIV_RECIP                                           */
+    int32_t reserved;
+} bdl_scalars;
+
+/* Gaussian noise source.  xi_dev != NULL: externally injected N(0,1) draws in the padded flat
+ * layout (parity mode: replaces torch.randn_like, methods/sghmc.py:501).  xi_dev == NULL:
+ * in-kernel counter-based Philox4x32-10 + Box-Muller keyed by (seed; element/4, stream, subseq):
+ * results do not depend on grid shape or on how work is sharded. */
+typedef struct {
+    const float* xi_dev;
+    uint64_t seed;
+    uint64_t subseq;         /* step counter (sampler) or packed (batch, cycle, sample) id (draw) */
+    uint32_t stream_id;      /* BDL_STREAM_* : separates uses of the same seed                    */
+    uint32_t reserved;
+} bdl_noise;
+
+#define BDL_STREAM_STEP 0u
+#define BDL_STREAM_DRAW 1u
+#define BDL_STREAM_USER 2u
+
+int bdl_abi_version(void);
+const char* bdl_last_error(void);
+
+/* Optional launch tuning (0 = library default).  Used by bench sweeps; not needed for correctness. */
+int bdl_set_launch_config(int ctas_per_sm, int unroll);
+
+/* (a1..a5) One fused sampler update over the whole flat state: prior pull, friction/momentum,
+ * Adam moments, noise, SGD momentum and the parameter update in a single pass.
+ *   theta, v, m, s, buf: updated in place.  g / theta0: read only.
+ *   Unused state for a variant may be NULL (v: SGLD; m,s: non-Adam; buf: mu == 0; theta0: cSGHMC).
+ *   g_dev may be NULL iff every run carries its own g_dev.
+ *   runs_dev: DEVICE array of nruns bdl_run (<= BDL_MAX_RUNS). */
+int bdl_step(int variant, float* theta_dev, const float* g_dev, const float* theta0_dev,
+             float* v_dev, float* m_dev, float* s_dev, float* buf_dev, uint64_t n,
+             const bdl_run* runs_dev, uint32_t nruns, const bdl_scalars* scalars,
+             const bdl_noise* noise, void* stream);
+
+/* Fill out[0..n) with exactly the N(0,1) stream the step / draw kernels use for (seed, stream_id,
+ * subseq).  Test and diagnostics entry (KS / moment tests; external-vs-in-kernel equivalence). */
+int bdl_philox_normal(float* out_dev, uint64_t n, uint64_t seed, uint32_t stream_id, uint64_t subseq,
+                      void* stream);
+
+/* (a7, a8) Running first/second moments of theta.
+ *   init != 0 : mom1 = theta*1.0 ; mom2 = theta**2            (methods/sgld.py:95-102, csgld.py:282-284)
+ *   else      : mom <- (theta^k + cnt*mom) / (cnt+1)          (methods/sgld.py:243-245, csgld.py:286-290)
+ *   mom2_dev may be NULL (nst == 0). cnt is passed as fp32(cnt) and fp32(cnt+1). */
+int bdl_moments_avg(const float* theta_dev, float* mom1_dev, float* mom2_dev, uint64_t n, float cnt,
+                    float cnt_plus_1, int init, int div_mode, void* stream);
+
+/* (a8) cSGHMC Welford update (methods/csghmc.py:333-345).
+ *   init != 0 : mean = theta ; M2 = 0
+ *   else      : d = theta-mean ; mean += d/n_f ; M2 += d*(theta-mean)          (n_f = fp32(n)) */
+int bdl_moments_welford(const float* theta_dev, float* mean_dev, float* m2_dev, uint64_t n, float n_f,
+                        int init, int div_mode, void* stream);
+
+/* (north star b) Copy theta into slot `slot` of a preallocated sample ring [slots][n] using TMA
+ * bulk copies (cp.async.bulk global->shared->global).  Replaces theta_vec.clone() into a dict
+ * (methods/csgld.py:278-279). */
+int bdl_capture_ring(const float* theta_dev, float* ring_dev, uint64_t slot, uint64_t n, void* stream);
+
+/* (a9) Posterior draw theta_s = mean + sqrt(var) * eps (methods/sgld.py:292-297, csgld.py:404-413).
+ *   var_mode 0: var = max(scale * (second - mean^2), 1e-12)   scale = fp32(ratio)  (sgld.py:338-348)
+ *   var_mode 1: var = max(second / scale, 1e-12)              scale = fp32(n-1)    (csghmc.py:451-459)
+ *   var_mode 2: var = 1e-12                                   (csghmc.py:458)
+ *   var_mode 3: second already holds the variance */
+int bdl_draw(const float* mean_dev, const float* second_dev, float* theta_out_dev, uint64_t n, int var_mode,
+             float scale, int div_mode, const bdl_noise* noise, void* stream);
+
+/* (a10) Ensemble average for one test batch (methods/sgld.py:283-305):
+ *   logits_all [B,K,S] fp32 (contiguous, S fastest, i.e. torch.stack(outs, 2)) ->
+ *   comp[B,K] = logsumexp_S(log_softmax_K(logits_all)) - log_S     (log_S = 0 when nst == 0)
+ *   mode 0: out = comp                       (non-cyclical runners)
+ *   mode 1: out = weight * comp              (first GMM component, methods/csgld.py:428-429)
+ *   mode 2: out += weight * comp             (further components, :430-431; log-space mixture) */
+int bdl_ensemble(const float* logits_all_dev, uint32_t B, uint32_t K, uint32_t S, float log_S, float weight,
+                 int mode, float* out_logits_dev, void* stream);
+
+/* CE loss sum and error count of [B,K] logits against int64 labels (methods/sgld.py:302-306,314-315):
+ *   *loss_sum += sum_b -log_softmax(logits[b])[y[b]] ;  *err_count += sum_b (argmax_k logits[b,k] != y[b]).
+ * Accumulating on the device removes the reference's two host syncs per batch. */
+int bdl_ce_err(const float* logits_dev, const int64_t* y_dev, uint32_t B, uint32_t K, double* loss_sum_dev,
+               int32_t* err_count_dev, void* stream);
+
+/* Sample-sharded ensembles (section 8e): prob_sum[B,K] += softmax_K(logits[B,K]) for one sample; after the
+ * (NCCL) all-reduce of prob_sum, bdl_probsum_finalize forms comp = log(prob_sum) - log_S and applies the
+ * same mode / weight rule as bdl_ensemble. */
+int bdl_probsum_accum(const float* logits_dev, uint32_t B, uint32_t K, float* prob_sum_dev, void* stream);
+int bdl_probsum_finalize(const float* prob_sum_dev, uint32_t B, uint32_t K, float log_S, float weight, int mode,
+                         float* out_logits_dev, void* stream);
+
+/* (a11) Calibration bins (calibration.py:24-67) and NLL (calibration.py:246-249).
+ *   logits [N,K] fp32, labels [N] int64, edges [M] fp64 right bin boundaries (host: np.linspace(0,1+1e-8,M+1)[1:]).
+ *   use_f64 == 0: logits/T and softmax in fp32 (temperature is the int 1 or a Python float in the reference)
+ *   use_f64 != 0: logits/T and softmax in fp64 (temperature is an fp64 ndarray in the reference: Topt)
+ *   Outputs (device, accumulated into -- caller zeroes): bin_size[M], acc_sum[M], conf_sum[M], nll_sum[1] (fp64)
+ *   and near_edge[1] (optional, may be NULL): number of probabilities within 16 ulp of a bin edge; 0 certifies
+ *   that any correctly-implemented softmax yields the same bin counts.
+ *   binned[N*K] (optional int32, may be NULL): per-probability bin index, np.digitize's return value.
+ *   Class-wise over all N*K probabilities; bin index = #edges <= p (np.digitize). */
+int bdl_calibrate(const float* logits_dev, const int64_t* labels_dev, uint64_t N, uint32_t K, double temperature,
+                  int use_f64, const double* edges_dev, uint32_t M, double* bin_size_dev, double* acc_sum_dev,
+                  double* conf_sum_dev, double* nll_sum_dev, unsigned long long* near_edge_dev,
+                  int32_t* binned_dev, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BDL_H_ */

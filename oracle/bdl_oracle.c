@@ -1,0 +1,238 @@
+/*
+ * bdl_oracle.c -- plain-C CPU restatement of BayesDLL's sampler update rules and of the
+ * Philox4x32-10 + Box-Muller noise stream.
+ *
+ * TEST INFRASTRUCTURE ONLY (see oracle/README.md).  Used by tests/ as a checker at sizes where
+ * the numpy oracle is slow, and by bench.py's cpu_baseline / --impl reference leg as the timed
+ * CPU port of the reference path (OpenMP over all host cores).  The product (bayesdll_b200)
+ * never links or calls this file.
+ *
+ * Same struct layouts as include/bdl.h so tests can drive both sides with identical arguments;
+ * all pointers here are HOST pointers.
+ *
+ * Reference sites restated (relative to the reference checkout):
+ *   SGLD        methods/sgld.py:469-484 + torch SGD step :226
+ *   SGHMC       methods/sghmc.py:482-510 + SGD(momentum=0) :229
+ *   cSGHMC      methods/csghmc.py:747-778
+ *   Adam-SGHMC  methods/adam_sghmc.py:507-553 + SGD(momentum) :233
+ *   Adam-cSGHMC methods/adam_csghmc.py:814-861 + SGD(momentum=0) :322
+ * Philox4x32-10: Salmon et al., SC'11 (Random123 v1.14 philox.h); pinned by the Random123
+ * known-answer vectors in tests/test_philox_cpu.py.
+ *
+ * Compile with -ffp-contract=off: every fp32 op must round once, the only fused op is the
+ * explicit fmaf() that restates torch's add_(x, alpha=-lr).
+ */
+#include <math.h>
+#include <stdint.h>
+#include <string.h>
+
+#include "bdl.h"
+
+/* ------------------------------------------------------------------------------------------ */
+static inline void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1,
+                                 uint32_t out[4]) {
+    for (int r = 0; r < 10; ++r) {
+        const uint64_t p0 = (uint64_t)0xD2511F53u * c0;
+        const uint64_t p1 = (uint64_t)0xCD9E8D57u * c2;
+        const uint32_t hi0 = (uint32_t)(p0 >> 32), lo0 = (uint32_t)p0;
+        const uint32_t hi1 = (uint32_t)(p1 >> 32), lo1 = (uint32_t)p1;
+        const uint32_t n0 = hi1 ^ c1 ^ k0, n2 = hi0 ^ c3 ^ k1;
+        c0 = n0; c1 = lo1; c2 = n2; c3 = lo0;
+        k0 += 0x9E3779B9u;
+        k1 += 0xBB67AE85u;
+    }
+    out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+
+void bdl_oracle_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]) {
+    philox4x32_10(ctr[0], ctr[1], ctr[2], ctr[3], key[0], key[1], out);
+}
+
+static inline void box_muller(uint32_t ra, uint32_t rb, float* z0, float* z1) {
+    const float u = fmaf((float)ra, 2.3283064365386963e-10f, 1.1641532182693481e-10f);
+    const float a = (float)rb * 2.3283064365386963e-10f;
+    const float r = sqrtf(-1.3862943611198906f * log2f(u));
+    const float ang = 6.2831853071795865f * a;
+    *z0 = r * cosf(ang);
+    *z1 = r * sinf(ang);
+}
+
+static inline void normal4(uint64_t seed, uint32_t stream_id, uint64_t subseq, uint64_t q, float z[4]) {
+    uint32_t r[4];
+    philox4x32_10((uint32_t)q, stream_id, (uint32_t)subseq, (uint32_t)(subseq >> 32), (uint32_t)seed,
+                  (uint32_t)(seed >> 32), r);
+    box_muller(r[0], r[1], &z[0], &z[1]);
+    box_muller(r[2], r[3], &z[2], &z[3]);
+}
+
+int bdl_oracle_philox_normal(float* out, uint64_t n, uint64_t seed, uint32_t stream_id, uint64_t subseq) {
+    if (n % 4) return BDL_ERR_INVALID;
+#pragma omp parallel for schedule(static)
+    for (int64_t q = 0; q < (int64_t)(n / 4); ++q) normal4(seed, stream_id, subseq, (uint64_t)q, out + 4 * q);
+    return BDL_OK;
+}
+
+/* ------------------------------------------------------------------------------------------ */
+static inline float div_s(float x, float s, float inv_s, int mode) { return mode == BDL_DIV_IEEE ? x / s : x * inv_s; }
+
+typedef struct {
+    float lr[2], c[2];
+    float oma, sig2, inv_sig2, N, inv_N, mu, b1, omb1, b2, omb2, bc1, inv_bc1, bc2, inv_bc2, eps, two_alpha, nd, T, inv_T;
+    int first_step, add_noise, div;
+} sc_t;
+
+static inline float prior_term(const sc_t* p, float th, float th0) {
+    float d = th - th0;
+    d = div_s(d, p->sig2, p->inv_sig2, p->div);
+    d = div_s(d, p->N, p->inv_N, p->div);
+    return d;
+}
+
+static inline float sgd_apply(const sc_t* p, int has_buf, float th, float gp, float lr, float* b) {
+    float d = gp;
+    if (has_buf) {
+        *b = p->first_step ? gp : (*b * p->mu) + gp;
+        d = *b;
+    }
+    return fmaf(d, -lr, th);
+}
+
+static inline void update_one(int variant, int has_buf, const sc_t* p, uint32_t cls, float* th, float g, float th0,
+                              float* v, float* m, float* s, float* b, float xi) {
+    const int h = cls & BDL_CLS_HEAD;
+    const int prior = (cls & BDL_CLS_PRIOR) != 0;
+    const float lr = p->lr[h];
+    if (variant == BDL_SGLD) {
+        const float noise = p->c[h] * xi;
+        const float add = prior ? prior_term(p, *th, th0) + noise : noise;
+        const float gp = g + add;
+        *th = sgd_apply(p, has_buf, *th, gp, lr, b);
+    } else if (variant == BDL_SGHMC) {
+        const float gU = prior ? g + prior_term(p, *th, th0) : g;
+        const float noise = p->c[h] * xi;
+        *v = ((*v * p->oma) + (lr * gU)) + noise;
+        const float gp = g + *v;
+        *th = fmaf(gp, -lr, *th);
+    } else if (variant == BDL_CSGHMC) {
+        const float gU = g + (p->sig2 * *th);
+        float vn = (*v * p->oma) - (lr * gU);
+        if (p->add_noise) vn = vn + (p->c[h] * xi);
+        *v = vn;
+        *th = *th + vn;
+    } else {
+        const int cyc = variant == BDL_ADAM_CSGHMC;
+        const float gl = cyc ? div_s(g, p->T, p->inv_T, p->div) : g;
+        const float gU = prior ? gl + prior_term(p, *th, th0) : gl;
+        *m = (p->b1 * *m) + (p->omb1 * gU);
+        *s = (p->b2 * *s) + (p->omb2 * (gU * gU));
+        const float mh = div_s(*m, p->bc1, p->inv_bc1, p->div);
+        const float sh = div_s(*s, p->bc2, p->inv_bc2, p->div);
+        const float den = sqrtf(sh) + p->eps;
+        const float pg = mh / den;
+        const float pre = 1.0f / den;
+        const float ns = p->nd * sqrtf(div_s(p->two_alpha * pre, p->N, p->inv_N, p->div));
+        const float noise = ns * xi;
+        *v = ((*v * p->oma) + (lr * pg)) + noise;
+        if (cyc) {
+            *th = fmaf(*v, -lr, *th);
+        } else {
+            const float gp = g + *v;
+            *th = sgd_apply(p, has_buf, *th, gp, lr, b);
+        }
+    }
+}
+
+/* Same contract as bdl_step() in include/bdl.h with HOST pointers (stream ignored). */
+int bdl_oracle_step(int variant, float* theta, const float* g, const float* theta0, float* v, float* m, float* s,
+                    float* buf, uint64_t n, const bdl_run* runs, uint32_t nruns, const bdl_scalars* sc,
+                    const bdl_noise* nz) {
+    if (variant < BDL_SGLD || variant > BDL_ADAM_CSGHMC || !theta || !runs || !sc || !nz || n % 4) return BDL_ERR_INVALID;
+    sc_t p;
+    for (int h = 0; h < 2; ++h) { p.lr[h] = sc->lr[h]; p.c[h] = sc->noise_scale[h]; }
+    p.oma = sc->one_minus_alpha; p.sig2 = sc->sig2; p.inv_sig2 = 1.0f / sc->sig2; p.N = sc->N; p.inv_N = 1.0f / sc->N;
+    p.mu = sc->mu; p.b1 = sc->beta1; p.omb1 = sc->one_minus_beta1; p.b2 = sc->beta2; p.omb2 = sc->one_minus_beta2;
+    p.bc1 = sc->bias_corr1; p.inv_bc1 = 1.0f / sc->bias_corr1; p.bc2 = sc->bias_corr2; p.inv_bc2 = 1.0f / sc->bias_corr2;
+    p.eps = sc->eps; p.two_alpha = sc->two_alpha; p.nd = sc->nd; p.T = sc->temperature; p.inv_T = 1.0f / sc->temperature;
+    p.first_step = sc->first_step; p.add_noise = sc->add_noise; p.div = sc->div_mode;
+    const int has_buf = (variant == BDL_SGLD || variant == BDL_ADAM_SGHMC) && sc->mu != 0.0f;
+    const float* xi = (const float*)(uintptr_t)nz->xi_dev;
+    const uint64_t seed = nz->seed, subseq = nz->subseq;
+    const uint32_t sid = nz->stream_id;
+    for (uint32_t r = 0; r < nruns; ++r) {
+        const bdl_run run = runs[r];
+        const int64_t q0 = (int64_t)(run.begin / 4), q1 = (int64_t)(run.end / 4);
+#pragma omp parallel for schedule(static)
+        for (int64_t q = q0; q < q1; ++q) {
+            float z[4];
+            if (xi) memcpy(z, xi + 4 * q, sizeof z);
+            else normal4(seed, sid, subseq, (uint64_t)q, z);
+            for (int k = 0; k < 4; ++k) {
+                const uint64_t i = 4 * (uint64_t)q + k;
+                float gi;
+                if (run.g_dev) gi = i < run.valid_end ? run.g_dev[i - run.begin] : 0.0f;
+                else gi = g[i];
+                float dv = 0, dm = 0, ds = 0, db = 0;
+                update_one(variant, has_buf, &p, run.cls, &theta[i], gi, theta0 ? theta0[i] : 0.0f, v ? &v[i] : &dv,
+                           m ? &m[i] : &dm, s ? &s[i] : &ds, buf ? &buf[i] : &db, z[k]);
+            }
+        }
+    }
+    return BDL_OK;
+}
+
+/* posterior draw, same contract as bdl_draw() */
+int bdl_oracle_draw(const float* mean, const float* second, float* out, uint64_t n, int var_mode, float scale,
+                    int div_mode, const bdl_noise* nz) {
+    if (n % 4) return BDL_ERR_INVALID;
+    const float* xi = (const float*)(uintptr_t)nz->xi_dev;
+    const float inv = 1.0f / scale;
+#pragma omp parallel for schedule(static)
+    for (int64_t q = 0; q < (int64_t)(n / 4); ++q) {
+        float z[4];
+        if (xi) memcpy(z, xi + 4 * q, sizeof z);
+        else normal4(nz->seed, nz->stream_id, nz->subseq, (uint64_t)q, z);
+        for (int k = 0; k < 4; ++k) {
+            const uint64_t i = 4 * (uint64_t)q + k;
+            float var;
+            if (var_mode == 0) { var = scale * (second[i] - (mean[i] * mean[i])); var = fmaxf(var, 1e-12f); }
+            else if (var_mode == 1) var = fmaxf(div_s(second[i], scale, inv, div_mode), 1e-12f);
+            else if (var_mode == 2) var = 1e-12f;
+            else var = second[i];
+            out[i] = mean[i] + (sqrtf(var) * z[k]);
+        }
+    }
+    return BDL_OK;
+}
+
+int bdl_oracle_moments_avg(const float* theta, float* mom1, float* mom2, uint64_t n, float cnt, float cntp1, int init,
+                           int div_mode) {
+    const float inv = 1.0f / cntp1;
+#pragma omp parallel for schedule(static)
+    for (int64_t i = 0; i < (int64_t)n; ++i) {
+        const float t = theta[i];
+        if (init) {
+            mom1[i] = t * 1.0f;
+            if (mom2) mom2[i] = t * t;
+        } else {
+            mom1[i] = div_s(t + (cnt * mom1[i]), cntp1, inv, div_mode);
+            if (mom2) mom2[i] = div_s((t * t) + (cnt * mom2[i]), cntp1, inv, div_mode);
+        }
+    }
+    return BDL_OK;
+}
+
+int bdl_oracle_moments_welford(const float* theta, float* mean, float* M2, uint64_t n, float nf, int init, int div_mode) {
+    const float inv = 1.0f / nf;
+#pragma omp parallel for schedule(static)
+    for (int64_t i = 0; i < (int64_t)n; ++i) {
+        const float t = theta[i];
+        if (init) { mean[i] = t; M2[i] = 0.0f; }
+        else {
+            const float d = t - mean[i];
+            mean[i] = mean[i] + div_s(d, nf, inv, div_mode);
+            const float d2 = t - mean[i];
+            M2[i] = M2[i] + (d * d2);
+        }
+    }
+    return BDL_OK;
+}

@@ -1,0 +1,76 @@
+"""ctypes front end of oracle/bdl_oracle.c (TEST INFRASTRUCTURE ONLY -- see module docstring of
+oracle/sampler_oracle.py for who may import this).  Builds the shared object with `make` on first use."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+SO = os.path.join(HERE, "_build", "libbdl_oracle.so")
+
+_lib = None
+
+
+def build(force=False):
+    src = os.path.join(HERE, "bdl_oracle.c")
+    hdr = os.path.join(HERE, "..", "include", "bdl.h")
+    stale = (not os.path.exists(SO)) or any(os.path.getmtime(f) > os.path.getmtime(SO) for f in (src, hdr))
+    if force or stale:
+        subprocess.check_call(["make", "-s", "-C", HERE] + (["-B"] if force else []))
+    return SO
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        build()
+        _lib = C.CDLL(SO)
+    return _lib
+
+
+def _fp(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+def philox4x32_10(ctr, key):
+    c = (C.c_uint32 * 4)(*ctr)
+    k = (C.c_uint32 * 2)(*key)
+    out = (C.c_uint32 * 4)()
+    lib().bdl_oracle_philox4x32_10(c, k, out)
+    return tuple(out)
+
+
+def philox_normal(n, seed, stream_id, subseq):
+    out = np.empty(n, np.float32)
+    rc = lib().bdl_oracle_philox_normal(_fp(out), C.c_uint64(n), C.c_uint64(seed & (2**64 - 1)), C.c_uint32(stream_id),
+                                        C.c_uint64(subseq & (2**64 - 1)))
+    assert rc == 0
+    return out
+
+
+def step(variant, theta, g, theta0, v, m, s, buf, runs, scalars, noise):
+    """In-place on the numpy arrays.  runs: ctypes array of bayesdll_b200._lib.Run with HOST g pointers;
+    scalars / noise: the same ctypes structs the CUDA path receives (noise.xi_dev = host address or 0)."""
+    n = theta.size
+    rc = lib().bdl_oracle_step(C.c_int(variant), _fp(theta), _fp(g), _fp(theta0), _fp(v), _fp(m), _fp(s), _fp(buf),
+                               C.c_uint64(n), runs, C.c_uint32(len(runs)), C.byref(scalars), C.byref(noise))
+    assert rc == 0, rc
+
+
+def draw(mean, second, out, var_mode, scale, div_mode, noise):
+    rc = lib().bdl_oracle_draw(_fp(mean), _fp(second), _fp(out), C.c_uint64(mean.size), C.c_int(var_mode),
+                               C.c_float(scale), C.c_int(div_mode), C.byref(noise))
+    assert rc == 0
+
+
+def moments_avg(theta, mom1, mom2, cnt, init, div_mode):
+    rc = lib().bdl_oracle_moments_avg(_fp(theta), _fp(mom1), _fp(mom2), C.c_uint64(theta.size), C.c_float(cnt),
+                                      C.c_float(cnt + 1), C.c_int(init), C.c_int(div_mode))
+    assert rc == 0
+
+
+def moments_welford(theta, mean, M2, n, init, div_mode):
+    rc = lib().bdl_oracle_moments_welford(_fp(theta), _fp(mean), _fp(M2), C.c_uint64(theta.size), C.c_float(n),
+                                          C.c_int(init), C.c_int(div_mode))
+    assert rc == 0

@@ -1,0 +1,171 @@
+"""Loader + injection harness for the *real* reference (omarezz46/BayesDLL).
+
+TEST INFRASTRUCTURE ONLY.  Nothing under ``bayesdll_b200/`` may import this.
+It is used in the build container (where ``/root/reference`` is mounted) by
+``oracle/make_golden.py`` to run the reference's own PyTorch code on injected
+gradients / injected noise and record golden vectors under ``tests/golden/``.
+The reference does not exist on the GPU box, so nothing in ``tests -m gpu``,
+``smoke()`` or ``bench.py`` imports this module.
+
+Two shims are needed to import the reference unmodified:
+  * a stub ``matplotlib`` (imported at calibration.py:14-15, only used by the plots)
+  * ``<ref>/src`` on sys.path so ``from bayesdll import calibration``
+    (methods/cyclical.py:10) resolves.
+"""
+import contextlib
+import importlib
+import os
+import sys
+import types
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+
+def find_reference():
+    for cand in (os.environ.get("BDL_REF"), "/root/reference"):
+        if cand and os.path.isfile(os.path.join(cand, "methods", "sghmc.py")):
+            return cand
+    raise FileNotFoundError("reference checkout not found (set $BDL_REF or mount /root/reference)")
+
+
+def _install_matplotlib_stub():
+    if "matplotlib" in sys.modules:
+        return
+    mpl = types.ModuleType("matplotlib")
+    pyplot = types.ModuleType("matplotlib.pyplot")
+    patches = types.ModuleType("matplotlib.patches")
+
+    class _Anything:
+        def __getattr__(self, name):
+            return _Anything()
+
+        def __call__(self, *a, **k):
+            return _Anything()
+
+        def __getitem__(self, k):
+            return _Anything()
+
+        def __iter__(self):
+            return iter(())
+
+    def _mod_getattr(name):
+        if name.startswith("__"):
+            raise AttributeError(name)
+        return _Anything()
+
+    pyplot.__getattr__ = _mod_getattr
+    patches.__getattr__ = _mod_getattr
+    mpl.pyplot = pyplot
+    mpl.patches = patches
+    sys.modules["matplotlib"] = mpl
+    sys.modules["matplotlib.pyplot"] = pyplot
+    sys.modules["matplotlib.patches"] = patches
+
+
+_REF_MODULE_NAMES = ("calibration", "methods", "networks", "bayesdll", "utils", "datasets")
+
+
+@contextlib.contextmanager
+def reference_imports():
+    """Context manager: inside it ``import methods.sghmc`` etc. resolve to the reference.
+
+    On exit the reference's top-level module names are removed from ``sys.modules``
+    and ``sys.path`` so they cannot shadow ``bayesdll_b200``'s own modules.
+    """
+    ref = find_reference()
+    _install_matplotlib_stub()
+    added = [ref, os.path.join(ref, "src")]
+    saved = {k: v for k, v in sys.modules.items()
+             if k.split(".")[0] in _REF_MODULE_NAMES}
+    for k in saved:
+        del sys.modules[k]
+    sys.path[:0] = added
+    try:
+        yield ref
+    finally:
+        for p in added:
+            with contextlib.suppress(ValueError):
+                sys.path.remove(p)
+        for k in list(sys.modules):
+            if k.split(".")[0] in _REF_MODULE_NAMES:
+                del sys.modules[k]
+        sys.modules.update(saved)
+
+
+def load(modname):
+    """Import one reference module (e.g. 'methods.sghmc', 'calibration') and return it.
+
+    The module object stays usable after the context exits."""
+    with reference_imports():
+        return importlib.import_module(modname)
+
+
+class NoiseTape:
+    """Replacement for ``torch.randn_like`` that hands out consecutive slices of a
+    pre-generated flat fp32 noise vector ('Noise injection')."""
+
+    def __init__(self, flat_noise):
+        self.flat = torch.as_tensor(flat_noise, dtype=torch.float32)
+        self.pos = 0
+        self.calls = 0
+
+    def __call__(self, like, **kw):
+        n = like.numel()
+        out = self.flat[self.pos:self.pos + n].reshape(like.shape).clone()
+        assert out.numel() == n, "noise tape exhausted"
+        self.pos += n
+        self.calls += 1
+        return out.to(like.device)
+
+
+@contextlib.contextmanager
+def injected_noise(flat_noise):
+    tape = NoiseTape(flat_noise)
+    orig = torch.randn_like
+    torch.randn_like = tape
+    try:
+        yield tape
+    finally:
+        torch.randn_like = orig
+
+
+class GradInjectNet(nn.Module):
+    """A 'network' whose parameters have reference-style names and whose forward
+    returns sum_t (p_t * G_t).sum(), so that after ``loss.backward()`` with
+    ``criterion = lambda out, y: out`` every ``p.grad == G_t`` exactly
+    ('Gradient injection without touching reference code').
+
+    ``shapes``: ordered dict name -> shape; names may contain dots
+    (``layers.0.bias``, ``classifier.weight``) – they are registered through nested
+    ModuleDicts so ``named_parameters()`` yields exactly those names.
+    """
+
+    def __init__(self, shapes, readout_name, init_std=0.1, seed=0):
+        super().__init__()
+        gen = torch.Generator().manual_seed(seed)
+        self._names = list(shapes)
+        for name, shape in shapes.items():
+            parts = name.split(".")
+            mod = self
+            for part in parts[:-1]:
+                if not hasattr(mod, part):
+                    mod.add_module(part, nn.Module())
+                mod = getattr(mod, part)
+            mod.register_parameter(parts[-1], nn.Parameter(torch.randn(shape, generator=gen) * init_std))
+        self.readout_name = readout_name
+        self._G = None
+
+    def set_grads(self, grads):
+        self._G = [torch.as_tensor(g, dtype=torch.float32) for g in grads]
+
+    def forward(self, x):
+        tot = 0.0
+        for p, g in zip(self.parameters(), self._G):
+            tot = tot + (p * g).sum()
+        return tot
+
+
+def identity_criterion(out, y):
+    return out

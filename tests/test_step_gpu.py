@@ -1,0 +1,160 @@
+"""GPU parity: the fused CUDA step (through the C ABI) against the oracle and the reference goldens."""
+import numpy as np
+import pytest
+import torch
+
+import golden_util as gu
+from oracle import sampler_oracle as so
+
+pytestmark = pytest.mark.gpu
+
+EXACT = ("sgld", "csgld", "sghmc", "csghmc")
+
+
+def bits_equal(a, b):
+    return np.array_equal(np.asarray(a, np.float32).view(np.uint32), np.asarray(b, np.float32).view(np.uint32))
+
+
+def _stepper(name, device, per_tensor_runs=False):
+    from gpu_impl import GpuStepper
+    z, hp, method = gu.load_step_case(name)
+    return GpuStepper(z["names"].tolist(), z["sizes"].tolist(), "classifier", hp["bias"], device,
+                      per_tensor_runs=per_tensor_runs)
+
+
+@pytest.mark.parametrize("name", gu.step_cases())
+@pytest.mark.parametrize("chained", [False, True])
+def test_step_matches_reference_golden(cuda_device, name, chained):
+    """IEEE-division mode, injected noise: bit-exact vs the reference for SGLD/cSGLD/SGHMC/cSGHMC, within the
+    north-star fp32 rel 1e-6 for the Adam variants (whose CPU reference has a 1-ulp sqrt, see test_oracle_golden)."""
+    _, _, method = gu.load_step_case(name)
+    pairs = gu.replay_step_case(name, _stepper(name, cuda_device), chained=chained, div_mode="true")
+    for key, lst in pairs.items():
+        for t, (got, want) in enumerate(lst):
+            if method in EXACT or key in ("m", "s"):
+                assert bits_equal(got, want), f"{name} {key} step {t}"
+            else:
+                assert gu.max_rel(got, want) <= 1e-6, f"{name} {key} step {t}: {gu.max_rel(got, want):.2e}"
+
+
+@pytest.mark.parametrize("name", gu.step_cases())
+@pytest.mark.parametrize("div_mode", ["true", "recip"])
+@pytest.mark.parametrize("per_tensor_runs", [False, True])
+def test_step_bit_exact_vs_oracle(cuda_device, name, div_mode, per_tensor_runs):
+    """Both division semantics, merged and per-tensor run tables: CUDA == oracle bit for bit (all variants)."""
+    gpu = gu.replay_step_case(name, _stepper(name, cuda_device, per_tensor_runs), chained=True, div_mode=div_mode)
+    ora = gu.replay_step_case(name, so, chained=True, div_mode=div_mode)
+    for key in gpu:
+        for t, ((got, _), (want, _)) in enumerate(zip(gpu[key], ora[key])):
+            assert bits_equal(got, want), f"{name} {key} step {t} ({div_mode})"
+
+
+def _random_layout(rng, ntensors, max_numel):
+    from bayesdll_b200.flat import FlatLayout
+    shapes = []
+    for i in range(ntensors):
+        numel = int(rng.integers(1, max_numel))
+        kind = ("weight", "bias")[i % 2]
+        prefix = "classifier" if i >= ntensors - 2 else f"layers.{i // 2}"
+        shapes.append((f"{prefix}.{kind}", (numel,)))
+    return FlatLayout(shapes, "classifier")
+
+
+@pytest.mark.parametrize("variant_name", ["sgld", "sghmc", "csghmc", "adam_sghmc", "adam_csghmc"])
+@pytest.mark.parametrize("bias_mode", ["informative", "uninformative"])
+@pytest.mark.parametrize("own_g", [False, True])
+def test_step_ragged_layout_vs_oracle(cuda_device, variant_name, bias_mode, own_g):
+    """Ragged tensors (numel 1..5000, many not multiples of 4), multi-tile grids, optional per-run gradient
+    pointers with tail masking.  Oracle runs on the same padded buffers."""
+    from bayesdll_b200 import _lib, ops
+    rng = np.random.default_rng(hash((variant_name, bias_mode, own_g)) % 2**32)
+    lay = _random_layout(rng, 41, 5000)
+    n = lay.n_padded
+    is_head, P = lay.per_element(bias_mode)
+    hp = so.HParams(ND=1840, Ninflate=3.0, prior_sig=0.9, nd=0.7, alpha=0.18, beta1=0.9, beta2=0.999, eps=1e-8,
+                    temperature=1.3, mu=0.5 if variant_name in ("sgld", "adam_sghmc") else 0.0)
+    lrb, lrh = 1e-3, 1e-2
+    f = lambda scale=1.0: (rng.standard_normal(n) * scale).astype(np.float32)
+    theta, theta0, v, m, xi = f(0.1), f(0.1), f(0.01), f(0.01), f()
+    s = np.abs(f(1e-3)).astype(np.float32) + np.float32(1e-6)
+    buf = f(0.01)
+    g_dense = [rng.standard_normal(sg.numel).astype(np.float32) * 0.05 for sg in lay.segments]
+    g = np.zeros(n, np.float32)
+    for sg, gd in zip(lay.segments, g_dense):
+        g[sg.begin:sg.begin + sg.numel] = gd
+    variant = dict(sgld=_lib.SGLD, sghmc=_lib.SGHMC, csghmc=_lib.CSGHMC, adam_sghmc=_lib.ADAM_SGHMC,
+                   adam_csghmc=_lib.ADAM_CSGHMC)[variant_name]
+    dev = cuda_device
+    T = {k: torch.from_numpy(a.copy()).to(dev) for k, a in
+         dict(theta=theta, theta0=theta0, v=v, m=m, s=s, buf=buf, xi=xi, g=g).items()}
+    keep = []
+    if own_g:
+        ptrs = []
+        for gd in g_dense:
+            # allocate each gradient separately, poison what follows its end to prove the tail mask works
+            t = torch.full((gd.size + 8,), float("nan"), device=dev)
+            t[:gd.size] = torch.from_numpy(gd).to(dev)
+            keep.append(t)
+            ptrs.append(t.data_ptr())
+        tab = lay.run_table(bias_mode, grad_ptrs=ptrs)
+        g_arg = None
+    else:
+        tab = lay.run_table(bias_mode)
+        g_arg = T["g"]
+    runs_dev, nruns = ops.upload_runs(tab, dev)
+    for div_name, div in (("true", _lib.DIV_IEEE), ("recip", _lib.DIV_RECIP)):
+        for k, a in dict(theta=theta, v=v, m=m, s=s, buf=buf).items():
+            T[k].copy_(torch.from_numpy(a))
+        sc = ops.make_scalars(variant, lr_body=lrb, lr_head=lrh, ND=hp.ND, Ninflate=hp.Ninflate, prior_sig=hp.prior_sig,
+                              nd=hp.nd, alpha=hp.alpha, mu=hp.mu, beta1=hp.beta1, beta2=hp.beta2, eps=hp.eps,
+                              temperature=hp.temperature, t=3, first_step=False, add_noise=True, div_mode=div)
+        adam = variant_name.startswith("adam")
+        ops.step(variant, T["theta"], g_arg, None if variant_name == "csghmc" else T["theta0"],
+                 None if variant_name == "sgld" else T["v"], T["m"] if adam else None, T["s"] if adam else None,
+                 T["buf"] if hp.mu != 0 else None, runs_dev, nruns, sc, ops.make_noise(xi=T["xi"]))
+        torch.cuda.synchronize()
+        kw = dict(is_head=is_head, lr_body=lrb, lr_head=lrh, hp=hp)
+        if variant_name == "sgld":
+            want = dict(zip(("theta", "buf"), so.step_sgld(theta, g, theta0, buf, xi, P=P, first_step=False,
+                                                            div_mode=div_name, **kw)))
+        elif variant_name == "sghmc":
+            want = dict(zip(("theta", "v"), so.step_sghmc(theta, g, theta0, v, xi, P=P, div_mode=div_name, **kw)))
+        elif variant_name == "csghmc":
+            want = dict(zip(("theta", "v"), so.step_csghmc(theta, g, v, xi, should_sample=True, **kw)))
+        elif variant_name == "adam_sghmc":
+            want = dict(zip(("theta", "v", "m", "s", "buf"),
+                            so.step_adam_sghmc(theta, g, theta0, v, m, s, buf, xi, P=P, t=3, first_step=False,
+                                               div_mode=div_name, **kw)))
+        else:
+            want = dict(zip(("theta", "v", "m", "s"),
+                            so.step_adam_csghmc(theta, g, theta0, v, m, s, xi, P=P, t=3, div_mode=div_name, **kw)))
+        for k, w in want.items():
+            got = T[k].cpu().numpy()
+            assert not np.isnan(got).any(), f"{k}: NaN leaked from gradient padding"
+            assert bits_equal(got, w), f"{variant_name} {k} ({div_name}, own_g={own_g}): " \
+                                       f"{(got.view(np.uint32) != w.view(np.uint32)).sum()} mismatches"
+
+
+def test_step_empty_and_argument_errors(cuda_device):
+    from bayesdll_b200 import _lib, ops
+    from bayesdll_b200.flat import FlatLayout
+    lay = FlatLayout([("a.weight", (8,))], "classifier")
+    runs_dev, nruns = ops.upload_runs(lay.run_table("informative"), cuda_device)
+    sc = ops.make_scalars(_lib.SGHMC, lr_body=1e-3, lr_head=1e-3, ND=10)
+    z = lambda n: torch.zeros(n, device=cuda_device)
+    # n == 0 is a no-op
+    e = torch.zeros(0, device=cuda_device)
+    ops.step(_lib.SGHMC, e, e, e, e, None, None, None, runs_dev, nruns, sc, ops.make_noise(seed=1))
+    # n not a multiple of 4
+    with pytest.raises(_lib.BdlError, match="multiple of 4"):
+        ops.step(_lib.SGHMC, z(6), z(6), z(6), z(6), None, None, None, runs_dev, nruns, sc, ops.make_noise(seed=1))
+    # missing momentum buffer
+    with pytest.raises(_lib.BdlError, match="momentum"):
+        ops.step(_lib.SGHMC, z(8), z(8), z(8), None, None, None, None, runs_dev, nruns, sc, ops.make_noise(seed=1))
+    # unaligned pointer
+    with pytest.raises(_lib.BdlError, match="aligned"):
+        ops.step(_lib.SGHMC, z(9)[1:], z(8), z(8), z(8), None, None, None, runs_dev, nruns, sc, ops.make_noise(seed=1))
+    # CPU tensors are rejected: there is no CPU path
+    with pytest.raises(_lib.BdlError, match="CUDA tensor"):
+        ops.step(_lib.SGHMC, torch.zeros(8), z(8), z(8), z(8), None, None, None, runs_dev, nruns, sc,
+                 ops.make_noise(seed=1))
