@@ -15,7 +15,7 @@ BDL_ABI_VERSION = 1
 SGLD, SGHMC, CSGHMC, ADAM_SGHMC, ADAM_CSGHMC = range(5)
 VARIANT_NAMES = {SGLD: "sgld", SGHMC: "sghmc", CSGHMC: "csghmc", ADAM_SGHMC: "adam_sghmc",
                  ADAM_CSGHMC: "adam_csghmc"}
-CLS_HEAD, CLS_PRIOR = 1, 2
+CLS_HEAD, CLS_PRIOR, CLS_SKIP = 1, 2, 4
 DIV_IEEE, DIV_RECIP = 0, 1
 STREAM_STEP, STREAM_DRAW, STREAM_USER = 0, 1, 2
 MAX_RUNS = 2048

@@ -1,0 +1,151 @@
+"""Flat HBM state of one SG-MCMC chain and the host logic that feeds the fused kernels.
+
+``ChainState`` owns the padded flat buffers (theta / theta0 / v / m / s / SGD momentum / optional flat
+gradient / injected-noise scratch), re-points the network's parameters at views of ``theta`` and builds
+the per-step run table.  It is the host-side mirror of what the reference keeps as per-tensor Python
+objects: ``net.parameters()``, ``net0.parameters()``, ``Model.momentum_buffer`` / ``.m`` / ``.v`` dicts
+and the torch SGD ``momentum_buffer`` state (methods/sghmc.py:462-465, methods/adam_sghmc.py:484-491).
+"""
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _lib, ops
+from .flat import FlatLayout, adopt_parameters, alloc_flat
+
+_RUN_DTYPE = np.dtype([("begin", "<u8"), ("end", "<u8"), ("valid_end", "<u8"), ("g_dev", "<u8"), ("cls", "<u4"),
+                       ("reserved", "<u4")])
+assert _RUN_DTYPE.itemsize == C.sizeof(_lib.Run)
+
+
+class ChainState:
+    def __init__(self, net, net0, *, variant, bias_mode, mu=0.0, device=None, noise="philox", seed=0,
+                 grad_mode="table", div_mode=_lib.DIV_RECIP):
+        params = [p for _, p in net.named_parameters()]
+        device = device or params[0].device
+        if device.type != "cuda":
+            raise _lib.BdlError("bayesdll_b200 runs on CUDA devices only (no CPU fallback); got " + str(device))
+        if any(p.dtype != torch.float32 for p in params):
+            raise _lib.BdlError("all parameters must be fp32 (the reference is fp32 throughout)")
+        _lib.load()
+        self.variant, self.bias_mode, self.mu = variant, bias_mode, float(mu)
+        self.device, self.noise_mode, self.seed = device, noise, int(seed)
+        self.grad_mode, self.div_mode = grad_mode, div_mode
+        self.layout = L = FlatLayout.from_module(net)
+        self.params = params
+        self.names = [n for n, _ in net.named_parameters()]
+        n = L.n_padded
+
+        self.theta = alloc_flat(n, device)
+        adopt_parameters(net, L, self.theta)
+        self.theta0 = None
+        if variant != _lib.CSGHMC:                       # cSGHMC ignores net0 (Appendix B.1)
+            self.theta0 = alloc_flat(n, device)
+            with torch.no_grad():
+                torch._foreach_copy_(L.views(self.theta0), [p.detach().to(device) for p in net0.parameters()])
+        self.v = alloc_flat(n, device) if variant != _lib.SGLD else None
+        adam = variant in (_lib.ADAM_SGHMC, _lib.ADAM_CSGHMC)
+        self.m = alloc_flat(n, device) if adam else None
+        self.s = alloc_flat(n, device) if adam else None
+        self.buf = alloc_flat(n, device) if (self.mu != 0.0 and variant in (_lib.SGLD, _lib.ADAM_SGHMC)) else None
+        self.g_flat = None
+        self.xi = None
+        self.step_count = 0            # Philox sub-sequence = number of updates applied so far
+        self.sgd_steps = 0             # torch SGD creates its momentum buffer on the first step
+
+        # static merged run table (flat gradient buffer mode) and per-tensor template (pointer-table mode)
+        self._runs_merged = ops.upload_runs(L.run_table(bias_mode), device)
+        tmpl = L.run_table(bias_mode, grad_ptrs=[0] * len(L.segments))
+        self._run_np = np.frombuffer(bytes(tmpl), dtype=_RUN_DTYPE).copy()
+        # two pinned staging buffers + events: the host may run ahead of the stream by one step
+        self._run_pinned = [torch.empty(self._run_np.nbytes, dtype=torch.uint8).pin_memory() for _ in range(2)]
+        self._run_dev = [torch.empty(self._run_np.nbytes, dtype=torch.uint8, device=device) for _ in range(2)]
+        self._run_evt = [None, None]
+        self._run_slot = 0
+
+    # ---- views handed to reference-style code ------------------------------------------------
+    def named_views(self, flat):
+        return dict(zip(self.names, self.layout.views(flat)))
+
+    def _ensure_g_flat(self):
+        if self.g_flat is None:
+            self.g_flat = alloc_flat(self.layout.n_padded, self.device)
+            self._g_views = self.layout.views(self.g_flat)
+        return self.g_flat
+
+    # ---- gradients ---------------------------------------------------------------------------
+    def _gradient_table(self):
+        """Run table whose rows point straight at autograd's gradient tensors: the kernel reads each p.grad in
+        place, so no gather / flatten pass (8 B/param) precedes the update.  Tensors whose gradient cannot be
+        read in place (non-contiguous, mis-aligned, wrong dtype) are copied into the flat gradient buffer; a
+        tensor without gradient is skipped like the reference does (``if p.grad is not None``)."""
+        rows = self._run_np
+        base_cls = rows["cls"] & ~np.uint32(_lib.CLS_SKIP)
+        ptrs = np.zeros(len(rows), np.uint64)
+        skip = np.zeros(len(rows), bool)
+        for i, p in enumerate(self.params):
+            g = p.grad
+            if g is None:
+                skip[i] = True
+            elif g.dtype == torch.float32 and g.is_contiguous() and g.data_ptr() % 16 == 0 and g.device == self.device:
+                ptrs[i] = g.data_ptr()
+            else:
+                self._ensure_g_flat()
+                self._g_views[i].copy_(g)
+        rows["g_dev"] = ptrs
+        rows["cls"] = np.where(skip, base_cls | np.uint32(_lib.CLS_SKIP), base_cls)
+        k = self._run_slot = self._run_slot ^ 1
+        if self._run_evt[k] is not None:
+            self._run_evt[k].synchronize()               # the copy that last used this staging buffer has run
+        self._run_pinned[k].numpy()[:] = rows.view(np.uint8)
+        self._run_dev[k].copy_(self._run_pinned[k], non_blocking=True)
+        self._run_evt[k] = torch.cuda.Event()
+        self._run_evt[k].record()
+        return self._run_dev[k], len(rows)
+
+    def _gradient_flat(self):
+        self._ensure_g_flat()
+        grads = [p.grad for p in self.params]
+        if any(g is None for g in grads):
+            return self._gradient_table()
+        torch._foreach_copy_(self._g_views, grads)
+        return self._runs_merged
+
+    # ---- noise -------------------------------------------------------------------------------
+    def _noise(self):
+        if self.noise_mode == "philox":
+            return ops.make_noise(seed=self.seed, subseq=self.step_count, stream_id=_lib.STREAM_STEP)
+        if self.noise_mode == "torch":
+            # Parity / debugging mode: one torch.randn_like per tensor in named_parameters() order, exactly the
+            # calls the reference makes (methods/sghmc.py:501), so seeding or patching torch.randn_like drives both.
+            if self.xi is None:
+                self.xi = alloc_flat(self.layout.n_padded, self.device)
+                self._xi_views = self.layout.views(self.xi)
+            for view, p in zip(self._xi_views, self.params):
+                if p.grad is not None:
+                    view.copy_(torch.randn_like(view))
+            return ops.make_noise(xi=self.xi)
+        raise ValueError(f"unknown noise mode {self.noise_mode!r} (philox | torch)")
+
+    # ---- the fused update --------------------------------------------------------------------
+    def update(self, scalars):
+        """Apply one fused update using the gradients currently held in ``p.grad``."""
+        if self.grad_mode == "table":
+            runs_dev, nruns = self._gradient_table()
+            g = self.g_flat
+        else:
+            runs_dev, nruns = self._gradient_flat()
+            g = self.g_flat
+        scalars.div_mode = self.div_mode
+        if self.buf is not None:
+            scalars.first_step = int(self.sgd_steps == 0)
+        ops.step(self.variant, self.theta, g, self.theta0, self.v, self.m, self.s, self.buf, runs_dev, nruns,
+                 scalars, self._noise())
+        self.step_count += 1
+        self.sgd_steps += 1
+
+    def reset_momenta(self):
+        for t in (self.v, self.m, self.s):
+            if t is not None:
+                t.zero_()

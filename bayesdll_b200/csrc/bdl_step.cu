@@ -168,14 +168,19 @@ step_kernel(const StepParams p) {
         const uint32_t q0 = tile * tile_groups + threadIdx.x;
         float4 th[kU], g[kU], th0[kU], v[kU], m[kU], s[kU], b[kU], xi[kU];
         uint32_t cls[kU];
+        bool act[kU];
         // ---- issue every load of the tile first (kU * #streams independent 128-bit requests) ----
 #pragma unroll
         for (int u = 0; u < kU; ++u) {
             const uint32_t q = q0 + u * kThreads;
-            if (q < p.n4) {
-                const uint64_t i = static_cast<uint64_t>(q) << 2;
+            act[u] = q < p.n4;
+            if (act[u]) {
                 cursor_seek(cur, p, q);
                 cls[u] = cur.cls;
+                act[u] = (cur.cls & BDL_CLS_SKIP) == 0;     // p.grad is None -> tensor left untouched
+            }
+            if (act[u]) {
+                const uint64_t i = static_cast<uint64_t>(q) << 2;
                 th[u] = ld_stream(p.theta + i);
                 g[u] = ld_stream(cur.gbase + i);
                 if (cur.own_g && i + 4 > cur.valid_end) {  // tail group of a per-run gradient: zero the padding lanes
@@ -198,7 +203,7 @@ step_kernel(const StepParams p) {
 #pragma unroll
         for (int u = 0; u < kU; ++u) {
             const uint32_t q = q0 + u * kThreads;
-            if (q < p.n4) {
+            if (act[u]) {
                 const uint64_t i = static_cast<uint64_t>(q) << 2;
                 if constexpr (kPhilox) xi[u] = philox_normal4(p.key, q);
                 update_one<kVariant, kHasBuf, kDiv>(p, cls[u], th[u].x, g[u].x, th0[u].x, v[u].x, m[u].x, s[u].x, b[u].x, xi[u].x);
@@ -275,6 +280,7 @@ extern "C" int bdl_step(int variant, float* theta, const float* g, const float* 
                         const bdl_scalars* sc, const bdl_noise* nz, void* stream) {
     using namespace bdl;
     BDL_REQUIRE(variant >= BDL_SGLD && variant <= BDL_ADAM_CSGHMC, BDL_ERR_INVALID, "bdl_step: unknown variant %d", variant);
+    if (n == 0) return BDL_OK;                      // empty state: nothing to do (pointers may be null)
     BDL_REQUIRE(theta && runs && sc && nz, BDL_ERR_INVALID, "bdl_step: null theta/runs/scalars/noise");
     BDL_REQUIRE(n % 4 == 0, BDL_ERR_INVALID, "bdl_step: n=%llu is not a multiple of 4", (unsigned long long)n);
     BDL_REQUIRE((n >> 2) < 0xFFFFFFFFull, BDL_ERR_INVALID, "bdl_step: n too large for 32-bit group index");
@@ -288,7 +294,6 @@ extern "C" int bdl_step(int variant, float* theta, const float* g, const float* 
     BDL_REQUIRE(sc->div_mode == BDL_DIV_IEEE || sc->div_mode == BDL_DIV_RECIP, BDL_ERR_INVALID, "bdl_step: bad div_mode");
     const void* ptrs[] = {theta, g, theta0, v, m, s, buf, nz->xi_dev};
     for (const void* q : ptrs) BDL_REQUIRE(aligned16(q), BDL_ERR_ALIGN, "bdl_step: pointer %p is not 16-byte aligned", q);
-    if (n == 0) return BDL_OK;
 
     StepParams p{};
     p.theta = theta; p.g = g; p.theta0 = theta0; p.v = v; p.m = m; p.s = s; p.buf = buf;

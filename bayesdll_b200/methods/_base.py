@@ -1,0 +1,829 @@
+"""Shared machinery of the drop-in ``Runner`` / ``Model`` pairs.
+
+The reference has six near-identical 500-900 line files (methods/{sgld,sghmc,adam_sghmc,csgld,csghmc,
+adam_csghmc}.py).  Here the per-method modules are thin: they pick a kernel variant, the optimizer momentum
+and the capture scheme, and inherit everything else from the two runners below.
+
+What is kept identical to the reference: constructor signatures, ``train`` / ``evaluate`` /
+``train_one_epoch`` / ``save_logits`` / ``save_ckpt`` / ``load_ckpt`` names, arguments and return values, the
+attributes other code reads (``net, net0, model, optimizer, criterion, Ninflate, nd, burnin, thin, nst,
+post_theta_mom1/2/cnt, cycle_theta_mom1/2, samples_per_cycle, cycle_likelihoods, cycle_states,
+model.momentum_buffer/m/v/t``), the checkpoint keys and the dense ``parameters_to_vector`` layout of every
+stored vector, and the quirks listed in SURVEY.md Appendix B.
+
+What is different: one fused kernel per step instead of ~12-30 eager kernels per tensor, no per-sample
+``deepcopy(net)``, no host sync per batch in ``evaluate`` and none per step in ``train_one_epoch``.
+"""
+import copy
+import os
+import pickle
+import time
+
+import numpy as np
+import torch
+import torch.nn as nn
+from tqdm import tqdm
+
+from .. import _lib, calibration, ops
+from ..chain import ChainState
+from ..flat import adopt_parameters, alloc_flat
+from .cyclical import CyclicalSGMCMC
+
+
+# ================================================================================================
+# optimizer shim
+# ================================================================================================
+class FusedSGD(torch.optim.SGD):
+    """Holds ``param_groups`` (cyclical runners write ``param_groups[i]['lr']`` every step, methods/csgld.py:234-239)
+    and the ``momentum_buffer`` state for checkpoints.  The parameter update itself is applied by the fused kernel
+    launched from ``Model.forward``, so ``step()`` does nothing: calling it after ``Model.forward`` -- as the
+    reference's training loop does (methods/sghmc.py:229) -- is harmless."""
+
+    def step(self, closure=None):  # noqa: D401
+        return None if closure is None else closure()
+
+
+def make_optimizer(net, lr, lr_head, momentum):
+    """Body / head parameter groups exactly as methods/sghmc.py:53-57."""
+    body = [p for n, p in net.named_parameters() if net.readout_name not in n]
+    head = [p for n, p in net.named_parameters() if net.readout_name in n]
+    return FusedSGD([{"params": body, "lr": lr}, {"params": head, "lr": lr_head}], momentum=momentum, weight_decay=0)
+
+
+# ================================================================================================
+# Model: fwd + bwd in PyTorch, then ONE fused update kernel
+# ================================================================================================
+class FusedModel(nn.Module):
+    """Parameter-free module with the reference's ``Model`` interface (methods/sghmc.py:409-512)."""
+
+    VARIANT = None
+
+    def __init__(self, ND, prior_sig=1.0, bias="informative", momentum_decay=0.05, beta1=0.9, beta2=0.999,
+                 epsilon=1e-8, temperature=1.0):
+        super().__init__()
+        self.ND = ND
+        self.prior_sig = prior_sig
+        self.bias = bias
+        self.momentum_decay = momentum_decay
+        self.beta1, self.beta2, self.epsilon = beta1, beta2, epsilon
+        self.temperature = temperature
+        self.t = 0
+        self._chain = None
+        self._opts = dict(sgd_momentum=0.0, seed=None, noise="philox", grad_mode="table", div_mode=_lib.DIV_RECIP,
+                          optimizer=None)
+
+    def configure(self, **opts):
+        unknown = set(opts) - set(self._opts)
+        if unknown:
+            raise TypeError(f"unknown option(s) {sorted(unknown)}")
+        self._opts.update(opts)
+        return self
+
+    # ---- state exposed under the reference's attribute names (dict: param name -> tensor view) ------------
+    def _views(self, which):
+        if self._chain is None or getattr(self._chain, which) is None:
+            raise AttributeError(which)
+        return self._chain.named_views(getattr(self._chain, which))
+
+    def _assign(self, which, mapping):
+        views = self._views(which)
+        with torch.no_grad():
+            for k, t in mapping.items():
+                views[k].copy_(t)
+
+    momentum_buffer = property(lambda self: self._views("v"), lambda self, d: self._assign("v", d))
+
+    @property
+    def chain(self):
+        return self._chain
+
+    def _ensure_chain(self, net, net0):
+        ch = self._chain
+        if ch is not None and ch.params and ch.params[0] is next(iter(net.parameters())):
+            return ch
+        o = self._opts
+        seed = o["seed"] if o["seed"] is not None else torch.initial_seed()
+        ch = ChainState(net, net0, variant=self.VARIANT, bias_mode=self.bias, mu=o["sgd_momentum"], noise=o["noise"],
+                        seed=seed, grad_mode=o["grad_mode"], div_mode=o["div_mode"])
+        self._chain = ch
+        opt = o["optimizer"]
+        if opt is not None and ch.buf is not None:       # expose the SGD momentum buffer through optimizer.state
+            for p, view in zip(ch.params, ch.layout.views(ch.buf)):
+                opt.state[p]["momentum_buffer"] = view
+        return ch
+
+    def _scalars(self, lrs, Ninflate, nd, should_sample):
+        lr_body, lr_head = (lrs[0], lrs[0]) if len(lrs) == 1 else (lrs[0], lrs[1])
+        return ops.make_scalars(self.VARIANT, lr_body=lr_body, lr_head=lr_head, ND=self.ND, Ninflate=Ninflate,
+                                prior_sig=self.prior_sig, nd=nd, alpha=self.momentum_decay,
+                                mu=self._opts["sgd_momentum"], beta1=self.beta1, beta2=self.beta2, eps=self.epsilon,
+                                temperature=self.temperature, t=max(self.t, 1), add_noise=should_sample)
+
+    def step_async(self, x, y, net, net0, criterion, lrs, Ninflate=1.0, nd=1.0, should_sample=False):
+        """``forward`` without the host sync: returns (loss tensor, detached logits)."""
+        chain = self._ensure_chain(net, net0)
+        if self.VARIANT in (_lib.ADAM_SGHMC, _lib.ADAM_CSGHMC):
+            self.t += 1                                   # methods/adam_sghmc.py:494
+        out = net(x)
+        loss = criterion(out, y)
+        net.zero_grad()                                   # grads -> None; autograd hands us fresh tensors
+        loss.backward()
+        chain.update(self._scalars(lrs, Ninflate, nd, should_sample))
+        return loss.detach(), out.detach()
+
+    def forward(self, x, y, net, net0, criterion, lrs, Ninflate=1.0, nd=1.0, should_sample=False):
+        """Same contract as the reference: returns ``(loss: float, out: detached [B,K])``; side effect: ``net`` holds the
+        next sample (the SGD step the reference performs afterwards is already folded in)."""
+        loss, out = self.step_async(x, y, net, net0, criterion, lrs, Ninflate, nd, should_sample)
+        return loss.item(), out
+
+
+class AdamStateMixin:
+    """``Model.m`` / ``Model.v`` are the Adam first / second moment dicts (methods/adam_sghmc.py:486-491)."""
+    m = property(lambda self: self._views("m"), lambda self, d: self._assign("m", d))
+    v = property(lambda self: self._views("s"), lambda self, d: self._assign("s", d))
+
+
+# ================================================================================================
+# evaluation helpers shared by both runners
+# ================================================================================================
+class _EvalNet:
+    """A copy of the live network whose parameters are views of one flat buffer, so a posterior sample is
+    materialised by ONE kernel (bdl_draw) instead of ``deepcopy(net)`` + 5 eager kernels per tensor."""
+
+    def __init__(self, net, layout):
+        self.net = copy.deepcopy(net)                     # inherits BatchNorm running stats (Appendix B.12)
+        self.net.eval()
+        self.flat = alloc_flat(layout.n_padded, next(net.parameters()).device)
+        adopt_parameters(self.net, layout, self.flat)
+        self.layout = layout
+        self._xi = None
+
+    def load(self, flat_values):
+        self.flat.copy_(flat_values)
+
+    def draw(self, mean, second, var_mode, scale, noise_mode, seed, subseq, div_mode):
+        if noise_mode == "philox":
+            nz = ops.make_noise(seed=seed, subseq=subseq, stream_id=_lib.STREAM_DRAW)
+        else:                                             # parity mode: torch.randn_like per tensor (sgld.py:294)
+            if self._xi is None:
+                self._xi = alloc_flat(self.layout.n_padded, self.flat.device)
+                self._xi_views = self.layout.views(self._xi)
+            for view in self._xi_views:
+                view.copy_(torch.randn_like(view))
+            nz = ops.make_noise(xi=self._xi)
+        ops.draw(mean, second, self.flat, var_mode, scale, nz, div_mode)
+
+
+def _pack_subseq(eval_id, batch, cycle, sample):
+    """64-bit Philox sub-sequence of one posterior draw: independent of how samples are sharded over ranks."""
+    return ((eval_id & 0xFFFF) << 48) | ((batch & 0xFFFFFF) << 24) | ((cycle & 0xFF) << 16) | (sample & 0xFFFF)
+
+
+class _RunnerCommon:
+    """Construction, evaluation plumbing, logits / checkpoint writers common to all six runners."""
+
+    MODEL_CLS = None
+    SGD_MOMENTUM_FROM_ARGS = False     # SGD(momentum=args.momentum) vs SGD(momentum=0)
+
+    # ---- construction (methods/sghmc.py:18-67) ------------------------------------------------------------
+    def __init__(self, net, net0, args, logger):
+        self.args = args
+        self.logger = logger
+        if args.pretrained is None:                       # zero prior mean
+            self.net0 = copy.deepcopy(net)
+            with torch.no_grad():
+                for p in self.net0.parameters():
+                    p.zero_()
+        else:
+            self.net0 = net0
+        self.net0 = self.net0.to(args.device)
+        self.net = net.to(args.device)
+
+        hp = args.hparams
+        self.model = self._build_model(hp).to(args.device)
+        mu = float(args.momentum) if self.SGD_MOMENTUM_FROM_ARGS else 0.0
+        self.optimizer = make_optimizer(self.net, args.lr, args.lr_head, mu)
+        self.criterion = torch.nn.CrossEntropyLoss()
+
+        self.Ninflate = float(hp["Ninflate"])
+        self.nd = float(hp["nd"])
+        self.nst = int(hp["nst"])
+        self.thin = int(hp["thin"])
+
+        # extra, optional knobs of the B200 path (absent from the reference's hparams -> defaults)
+        self.noise_mode = str(hp.get("noise", "philox"))
+        self.div_mode = {"recip": _lib.DIV_RECIP, "ieee": _lib.DIV_IEEE}[str(hp.get("div", "recip"))]
+        seed = int(hp["seed"]) if "seed" in hp else getattr(args, "seed", None)
+        self.seed = int(seed) if seed is not None else torch.initial_seed()
+        self.model.configure(sgd_momentum=mu, seed=self.seed, noise=self.noise_mode,
+                             grad_mode=str(hp.get("grad", "table")), div_mode=self.div_mode, optimizer=self.optimizer)
+        self._eval_calls = 0
+
+    def _build_model(self, hp):
+        raise NotImplementedError
+
+    # ---- small helpers --------------------------------------------------------------------------------
+    def _chain(self):
+        return self.model._ensure_chain(self.net, self.net0)
+
+    def _lrs(self):
+        return [pg["lr"] for pg in self.optimizer.param_groups]
+
+    def _dense(self, flat):
+        return self._chain().layout.to_dense(flat)
+
+    def _finish_eval(self, loss_sum, err_cnt, nb, ys, lgs, lgalls):
+        targets = torch.cat(ys).cpu().numpy()
+        logits = torch.cat(lgs).cpu().numpy()
+        logits_all = torch.cat(lgalls).cpu().numpy()
+        return loss_sum.item() / nb, err_cnt.item() / nb, targets, logits, logits_all
+
+    # ---- writers (methods/sghmc.py:356-367) -----------------------------------------------------------
+    def save_logits(self, targets, logits, logits_all, suffix=None):
+        suffix = "" if suffix is None else f"_{suffix}"
+        fname = os.path.join(self.args.log_dir, f"logits{suffix}.pkl")
+        with open(fname, "wb") as ff:
+            pickle.dump({"targets": targets, "logits": logits, "logits_all": logits_all}, ff,
+                        protocol=pickle.HIGHEST_PROTOCOL)
+        return fname
+
+    def _state_dict_copy(self):
+        """Independent tensors (the live state_dict entries are views of the flat buffer)."""
+        return {k: v.detach().clone() for k, v in self.net.state_dict().items()}
+
+    def _calibrate_and_log(self, targets_test, logits_test, val, fmt_topt):
+        args, logger = self.args, self.logger
+        ece, mce, nll = calibration.analyze(targets_test, logits_test, num_bins=args.ece_num_bins,
+                                            plot_save_path=os.path.join(args.log_dir, "reliability_T1.png"),
+                                            temperature=1)
+        logger.info("[Calibration - Default T=1] ECE = %.4f, MCE = %.4f, NLL = %.4f" % (ece, mce, nll))
+        if val is not None:
+            targets_val, logits_val = val
+            Topt, ok = calibration.find_optimal_temperature(
+                targets_val, logits_val, plot_save_path=os.path.join(args.log_dir, "temp_scale_optim_curve.png"))
+            if ok:
+                ece, mce, nll = calibration.analyze(targets_test, logits_test, num_bins=args.ece_num_bins,
+                                                    plot_save_path=os.path.join(args.log_dir, "reliability_Topt.png"),
+                                                    temperature=Topt)
+                logger.info("[Calibration - Temp-scaled Topt=%.4f] ECE = %.4f, MCE = %.4f, NLL = %.4f" %
+                            (fmt_topt(Topt), ece, mce, nll))
+            else:
+                logger.info("!! Temperature scaling optimization failed !!")
+
+    def _eval_and_report(self, ep, val_loader, test_loader, losses_val, errors_val, losses_test, errors_test):
+        """Validation + test evaluation of one epoch with the reference's log lines; returns what train() needs."""
+        logger = self.logger
+        val = None
+        if val_loader is not None:
+            tic = time.time()
+            losses_val[ep], errors_val[ep], t_val, l_val, la_val = self.evaluate(val_loader)
+            logger.info(f"(Epoch {ep}) Validation summary: loss = {losses_val[ep]:.4f}, "
+                        f"prediction error = {errors_val[ep]:.4f} (time: {time.time() - tic:.4f} seconds)")
+            val = (t_val, l_val, la_val)
+        tic = time.time()
+        losses_test[ep], errors_test[ep], t_test, l_test, la_test = self.evaluate(test_loader)
+        logger.info(f"(Epoch {ep}) Test summary: loss = {losses_test[ep]:.4f}, "
+                    f"prediction error = {errors_test[ep]:.4f} (time: {time.time() - tic:.4f} seconds)")
+        return val, (t_test, l_test, la_test)
+
+    def _on_best(self, ep, loss_now, val, test, fmt_topt, save_ckpt):
+        logger = self.logger
+        logger.info(f"Best evaluation loss so far! @epoch {ep}: loss = {loss_now}")
+        if val is not None:
+            logger.info(f"Logits on val set saved at {self.save_logits(*val, suffix='val')}")
+        logger.info(f"Logits on test set saved at {self.save_logits(*test, suffix='test')}")
+        if save_ckpt:
+            logger.info(f"Checkpoint saved at {self.save_ckpt(ep)}")
+        self._calibrate_and_log(test[0], test[1], None if val is None else val[:2], fmt_topt)
+
+
+# ================================================================================================
+# burn-in / thinning runners: sgld, sghmc, adam_sghmc      (methods/sghmc.py:16-406)
+# ================================================================================================
+class BurninRunner(_RunnerCommon):
+
+    def __init__(self, net, net0, args, logger):
+        super().__init__(net, net0, args, logger)
+        self.burnin = int(args.hparams["burnin"])
+        self._mom1 = self._mom2 = None
+
+    # dense views under the reference's attribute names (checkpoint contract: parameters_to_vector order)
+    @property
+    def post_theta_mom1(self):
+        if self._mom1 is None:
+            raise AttributeError("post_theta_mom1")
+        return self._dense(self._mom1)
+
+    @post_theta_mom1.setter
+    def post_theta_mom1(self, dense):
+        ch = self._chain()
+        self._mom1 = ch.layout.from_dense(dense.to(ch.device, torch.float32), self._mom1)
+
+    @property
+    def post_theta_mom2(self):
+        if self._mom2 is None:
+            raise AttributeError("post_theta_mom2")
+        return self._dense(self._mom2)
+
+    @post_theta_mom2.setter
+    def post_theta_mom2(self, dense):
+        ch = self._chain()
+        self._mom2 = ch.layout.from_dense(dense.to(ch.device, torch.float32), self._mom2)
+
+    # ---- training loop (methods/sghmc.py:70-193) -----------------------------------------------------------
+    def train(self, train_loader, val_loader, test_loader):
+        args, logger = self.args, self.logger
+        logger.info("Start training...")
+        losses_train, errors_train = np.zeros(args.epochs), np.zeros(args.epochs)
+        losses_val = errors_val = None
+        if val_loader is not None:
+            losses_val, errors_val = np.zeros(args.epochs), np.zeros(args.epochs)
+        losses_test, errors_test = np.zeros(args.epochs), np.zeros(args.epochs)
+        best_loss = np.inf
+        tic0 = time.time()
+        bi = 0
+        for ep in range(args.epochs):
+            if ep == self.burnin:
+                logger.info("(leaving burnin period) start collecting posterior samples")
+                self._start_collecting()
+            tic = time.time()
+            losses_train[ep], errors_train[ep], bi = self.train_one_epoch(train_loader, collect=(ep >= self.burnin), bi=bi)
+            logger.info("[Epoch %d/%d] Training summary: loss = %.4f, prediction error = %.4f (time: %.4f seconds)" %
+                        (ep, args.epochs, losses_train[ep], errors_train[ep], time.time() - tic))
+            if ep % args.test_eval_freq == 0 and ep >= self.burnin:
+                val, test = self._eval_and_report(ep, val_loader, test_loader, losses_val, errors_val, losses_test,
+                                                  errors_test)
+                loss_now = losses_val[ep] if val_loader is not None else losses_test[ep]
+                if loss_now < best_loss:
+                    best_loss = loss_now
+                    self._on_best(ep, loss_now, val, test, fmt_topt=lambda T: float(np.asarray(T).reshape(-1)[0]), save_ckpt=True)
+        toc0 = time.time()
+        logger.info("Training done! Total time = %f (average per epoch = %f) seconds" %
+                    (toc0 - tic0, (toc0 - tic0) / args.epochs))
+
+    def _start_collecting(self):
+        """mom1 = theta*1.0 ; mom2 = theta**2 ; cnt = 1   (methods/sghmc.py:96-103)."""
+        ch = self._chain()
+        n = ch.layout.n_padded
+        self._mom1 = alloc_flat(n, ch.device, zero=False) if self._mom1 is None else self._mom1
+        if self.nst > 0 and self._mom2 is None:
+            self._mom2 = alloc_flat(n, ch.device, zero=False)
+        ops.moments_avg(ch.theta, self._mom1, self._mom2 if self.nst > 0 else None, 0, init=True)
+        self.post_theta_cnt = 1
+
+    def train_one_epoch(self, train_loader, collect, bi):
+        """One epoch of sampler steps; running moments every ``thin`` steps after burn-in (methods/sghmc.py:196-253)."""
+        args, logger = self.args, self.logger
+        self.net.train()
+        dev = args.device
+        loss_acc = torch.zeros((), dtype=torch.float64, device=dev)
+        err_acc = torch.zeros((), dtype=torch.int64, device=dev)
+        nb_samples = 0
+        with tqdm(train_loader, unit="batch") as tepoch:
+            for x, y in tepoch:
+                x, y = x.to(dev, non_blocking=True), y.to(dev, non_blocking=True)
+                loss_, out = self.model.step_async(x, y, self.net, self.net0, self.criterion, self._lrs(),
+                                                   self.Ninflate, self.nd)
+                self.optimizer.step()                     # no-op: the update is part of the fused kernel
+                loss_acc += loss_.double() * len(y)
+                err_acc += out.argmax(dim=1).ne(y).sum()
+                nb_samples += len(y)
+                bi += 1
+                if collect and bi % self.thin == 0:
+                    logger.info("(post-burnin) accumulate posterior samples")
+                    ch = self._chain()
+                    ops.moments_avg(ch.theta, self._mom1, self._mom2 if self.nst > 0 else None, self.post_theta_cnt,
+                                    div_mode=self.div_mode)
+                    self.post_theta_cnt += 1
+        loss, error = loss_acc.item(), err_acc.item()      # the only host sync of the epoch
+        return loss / nb_samples, error / nb_samples, bi
+
+    # ---- posterior-predictive ensemble (methods/sghmc.py:256-324) -------------------------------------------
+    def _variance_ratio(self):
+        return self.post_theta_cnt / (self.post_theta_cnt - 1) if self.post_theta_cnt > 1 else 1.0
+
+    def evaluate(self, test_loader):
+        args = self.args
+        dev = args.device
+        ch = self._chain()
+        ev = _EvalNet(self.net, ch.layout)
+        self._eval_calls += 1
+        ratio = self._variance_ratio()
+        loss_sum = torch.zeros(1, dtype=torch.float64, device=dev)
+        err_cnt = torch.zeros(1, dtype=torch.int32, device=dev)
+        nb, ys, lgs, lgalls = 0, [], [], []
+        with torch.no_grad(), tqdm(test_loader, unit="batch") as tepoch:
+            for b_idx, (x, y) in enumerate(tepoch):
+                x, y = x.to(dev, non_blocking=True), y.to(dev, non_blocking=True)
+                outs = []
+                if self.nst == 0:
+                    ev.load(self._mom1)
+                    outs.append(ev.net(x))
+                else:
+                    for ii in range(self.nst):             # fresh draw for every batch (Appendix B.6)
+                        ev.draw(self._mom1, self._mom2, ops.VAR_FROM_MOMENTS, ratio, self.noise_mode, self.seed,
+                                _pack_subseq(self._eval_calls, b_idx, 0, ii), self.div_mode)
+                        outs.append(ev.net(x))
+                logits_all_ = torch.stack(outs, 2).contiguous().float()
+                logits_ = torch.empty(logits_all_.shape[:2], dtype=torch.float32, device=dev)
+                ops.ensemble(logits_all_, logits_, self.nst)
+                ops.ce_err(logits_, y, loss_sum, err_cnt)
+                ys.append(y)
+                lgs.append(logits_)
+                lgalls.append(logits_all_)
+                nb += len(y)
+        return self._finish_eval(loss_sum, err_cnt, nb, ys, lgs, lgalls)
+
+    def get_mean_vars_from_moments(self):
+        """API compatibility (methods/sghmc.py:327-353): two ``net``-like modules holding mean and variance."""
+        ch = self._chain()
+        with torch.no_grad():
+            mean = copy.deepcopy(self.net)
+            nn.utils.vector_to_parameters(self.post_theta_mom1.clone(), mean.parameters())
+            var = None
+            if self.nst > 0:
+                vec = self._variance_ratio() * (self.post_theta_mom2 - self.post_theta_mom1 ** 2)
+                vec.clamp_(min=1e-12)
+                var = copy.deepcopy(self.net)
+                nn.utils.vector_to_parameters(vec, var.parameters())
+        return mean, var
+
+    # ---- checkpoints (methods/sghmc.py:370-406) --------------------------------------------------------------
+    CKPT_HAS_LAST_THETA = True
+
+    def _ckpt_extra(self):
+        return {}
+
+    def save_ckpt(self, epoch):
+        fname = os.path.join(self.args.log_dir, "ckpt.pt")
+        ck = {}
+        if self.CKPT_HAS_LAST_THETA:
+            ck["last_theta"] = self._state_dict_copy()
+        ck.update({
+            "post_theta_mom1": self.post_theta_mom1.clone(),
+            "post_theta_mom2": self.post_theta_mom2.clone() if self.nst > 0 else None,
+            "post_theta_cnt": self.post_theta_cnt,
+            "prior_sig": self.model.prior_sig,
+            "optimizer": self.optimizer.state_dict(),
+        })
+        ck.update(self._ckpt_extra())
+        ck["epoch"] = epoch
+        torch.save(ck, fname)
+        return fname
+
+    def load_ckpt(self, ckpt_path):
+        """Mirrors the reference incl. its quirk: theta is not restored and the sample count is overwritten with the
+        epoch number (Appendix B.11)."""
+        ckpt = torch.load(ckpt_path, map_location=self.args.device, weights_only=False)
+        self.post_theta_mom1 = ckpt["post_theta_mom1"]
+        if ckpt["post_theta_mom2"] is not None:
+            self.post_theta_mom2 = ckpt["post_theta_mom2"]
+        self.post_theta_cnt = ckpt["epoch"]
+        self.model.prior_sig = ckpt["prior_sig"]
+        self._load_ckpt_extra(ckpt)
+        self.optimizer.load_state_dict(ckpt["optimizer"])
+        ch = self._chain()
+        if ch.buf is not None:                           # re-attach the flat SGD momentum buffer
+            for p, view in zip(ch.params, ch.layout.views(ch.buf)):
+                st = self.optimizer.state[p]
+                if "momentum_buffer" in st and st["momentum_buffer"] is not None:
+                    view.copy_(st["momentum_buffer"])
+                    ch.sgd_steps = max(ch.sgd_steps, 1)
+                st["momentum_buffer"] = view
+        return ckpt["epoch"]
+
+    def _load_ckpt_extra(self, ckpt):
+        pass
+
+
+# ================================================================================================
+# cyclical runners: csgld, csghmc, adam_csghmc       (methods/csgld.py:17-594, csghmc.py, adam_csghmc.py)
+# ================================================================================================
+class CyclicalRunner(_RunnerCommon):
+    CAPTURE = "avg"                  # 'avg' (csgld.py:282-290, adam_csghmc.py:349-357) | 'welford' (csghmc.py:333-345)
+    LIKELIHOOD_MEAN = "theta"        # 'theta' (csgld.py:518) | 'cycle_mean' (csghmc.py:578, adam_csghmc.py:639)
+    LAST_THETA_AS_VECTOR = False     # csghmc / adam_csghmc store a flat vector (csghmc.py:534)
+    PASS_SHOULD_SAMPLE = False       # only csghmc's Model takes should_sample (csghmc.py:296-300)
+    RESET_ADAM_AT_CYCLE_END = False  # adam_csghmc.py:370-378, 405
+    STORE_ALL_SAMPLES = False        # csgld.py:278-279 (args.full_sample)
+    TITLE = "Cyclical SGLD"
+
+    def __init__(self, net, net0, args, logger):
+        super().__init__(net, net0, args, logger)
+        self.cyclical_scheduler = CyclicalSGMCMC(
+            base_lr=args.lr,
+            nbr_of_cycles=args.num_cycles if hasattr(args, "num_cycles") else 10,
+            epochs=args.epochs,
+            proportion_exploration=args.proportion_exploration if hasattr(args, "proportion_exploration") else 0.5)
+        if "burnin" in args.hparams:
+            self.burnin = int(args.hparams["burnin"])
+        self.samples_collected = 0
+        self.current_cycle = 0
+        self.samples_per_cycle = {}
+        self._cyc1, self._cyc2 = {}, {}      # cycle -> padded flat moment buffers
+        self.cycle_likelihoods = {}
+        self.cycle_states = {}
+        self.all_samples = {}
+
+    # dict views under the reference's names: cycle -> dense vector
+    @property
+    def cycle_theta_mom1(self):
+        return {c: self._dense(t) for c, t in self._cyc1.items()}
+
+    @cycle_theta_mom1.setter
+    def cycle_theta_mom1(self, d):
+        ch = self._chain()
+        self._cyc1 = {c: ch.layout.from_dense(t.to(ch.device, torch.float32)) for c, t in d.items()}
+
+    @property
+    def cycle_theta_mom2(self):
+        return {c: self._dense(t) for c, t in self._cyc2.items()}
+
+    @cycle_theta_mom2.setter
+    def cycle_theta_mom2(self, d):
+        ch = self._chain()
+        self._cyc2 = {c: ch.layout.from_dense(t.to(ch.device, torch.float32)) for c, t in d.items()}
+
+    # ---- training loop (methods/csgld.py:81-193) ---------------------------------------------------------------
+    def train(self, train_loader, val_loader, test_loader):
+        args, logger = self.args, self.logger
+        logger.info(f"Start training with {self.TITLE}...")
+        losses_train, errors_train = np.zeros(args.epochs), np.zeros(args.epochs)
+        losses_val = errors_val = None
+        if val_loader is not None:
+            losses_val, errors_val = np.zeros(args.epochs), np.zeros(args.epochs)
+        losses_test, errors_test = np.zeros(args.epochs), np.zeros(args.epochs)
+        best_loss = np.inf
+        tic0 = time.time()
+        for ep in range(args.epochs):
+            self.cyclical_scheduler.current_epoch = ep
+            tic = time.time()
+            losses_train[ep], errors_train[ep], cycle_updated = self.train_one_epoch(train_loader)
+            logger.info(f"[Epoch {ep}/{args.epochs}] Training summary: loss = {losses_train[ep]:.4f}, "
+                        f"prediction error = {errors_train[ep]:.4f} (time: {time.time() - tic:.4f} seconds)")
+            self._after_epoch(ep, val_loader)
+            if cycle_updated:
+                self._before_cycle_eval(val_loader)
+                val, test = self._eval_and_report(ep, val_loader, test_loader, losses_val, errors_val, losses_test,
+                                                  errors_test)
+                loss_now = losses_val[ep] if val_loader is not None else losses_test[ep]
+                if loss_now < best_loss:
+                    best_loss = loss_now
+                    self._on_best(ep, loss_now, val, test, fmt_topt=lambda T: T[0], save_ckpt=False)
+        toc0 = time.time()
+        logger.info(f"Training done! Total time = {toc0 - tic0:.4f} (average per epoch = "
+                    f"{(toc0 - tic0) / args.epochs:.4f}) seconds")
+        logger.info(f"Total samples collected: {self.samples_collected} across {self.current_cycle} cycles")
+        return {"losses_train": losses_train, "errors_train": errors_train,
+                "losses_val": losses_val if val_loader is not None else None,
+                "errors_val": errors_val if val_loader is not None else None,
+                "losses_test": losses_test, "errors_test": errors_test, "samples_per_cycle": self.samples_per_cycle}
+
+    def _after_epoch(self, ep, val_loader):
+        pass
+
+    def _before_cycle_eval(self, val_loader):
+        pass
+
+    def _point_estimate(self, loader, net):
+        """Deterministic pass of ``net`` over ``loader``: (mean CE, error rate)."""
+        dev = self.args.device
+        was_training = net.training
+        net.eval()
+        loss_sum = torch.zeros(1, dtype=torch.float64, device=dev)
+        err_cnt = torch.zeros(1, dtype=torch.int32, device=dev)
+        nb = 0
+        with torch.no_grad():
+            for x, y in loader:
+                x, y = x.to(dev, non_blocking=True), y.to(dev, non_blocking=True)
+                ops.ce_err(net(x).float().contiguous(), y, loss_sum, err_cnt)
+                nb += len(y)
+        net.train(was_training)
+        if nb == 0:
+            return 0.0, 0.0
+        return loss_sum.item() / nb, err_cnt.item() / nb
+
+    def train_one_epoch(self, train_loader):
+        """One epoch with the cyclical step size; per-cycle capture; end-of-cycle bookkeeping (methods/csgld.py:195-331)."""
+        args, logger = self.args, self.logger
+        sched = self.cyclical_scheduler
+        self.net.train()
+        dev = args.device
+        loss_acc = torch.zeros((), dtype=torch.float64, device=dev)
+        err_acc = torch.zeros((), dtype=torch.int64, device=dev)
+        nb_samples = 0
+        cycle_updated = False
+        B = len(train_loader)
+        with tqdm(train_loader, unit="batch") as tepoch:
+            for batch_idx, (x, y) in enumerate(tepoch):
+                pos = dict(epoch=sched.current_epoch, batch=batch_idx, batches_per_epoch=B)
+                current_lr = sched.calculate_lr(**pos)
+                should_sample = sched.should_sample(**pos) and batch_idx % self.thin == 0
+                last_in_cycle = sched.last_in_cycle(**pos)
+                for i, group in enumerate(self.optimizer.param_groups):
+                    group["lr"] = current_lr * (args.lr_head / args.lr) if i == 1 else current_lr
+
+                x, y = x.to(dev, non_blocking=True), y.to(dev, non_blocking=True)
+                kw = dict(should_sample=should_sample) if self.PASS_SHOULD_SAMPLE else {}
+                loss_, out = self.model.step_async(x, y, self.net, self.net0, self.criterion, self._lrs(),
+                                                   self.Ninflate, self.nd, **kw)
+                self.optimizer.step()                     # no-op (see FusedSGD)
+                loss_acc += loss_.double() * len(y)
+                err_acc += out.argmax(dim=1).ne(y).sum()
+                nb_samples += len(y)
+
+                if should_sample:
+                    cycle_number = sched.get_cycle_number(**pos)
+                    if batch_idx % 50 == 0:
+                        logger.info(f"Sampling phase: collecting posterior sample at lr={current_lr:.6f}")
+                    self._capture(cycle_number, sched.current_epoch, batch_idx)
+                    self.samples_collected += 1
+                    self.samples_per_cycle[cycle_number] = self.samples_per_cycle.get(cycle_number, 0) + 1
+                elif batch_idx % 50 == 0:
+                    logger.info(f"Exploration phase: lr={current_lr:.6f}")
+
+                if last_in_cycle:
+                    cycle_number = sched.get_cycle_number(**pos)
+                    self.cycle_states[cycle_number] = self._state_dict_copy()
+                    if self.RESET_ADAM_AT_CYCLE_END:
+                        logger.info(f"Resetting momentum states for new cycle {cycle_number}")
+                        self._reset_optimizer_states(log=False)
+                    if cycle_number > self.current_cycle:
+                        cycle_updated = True
+                        self.current_cycle = cycle_number
+                        logger.info(f"Completed cycle {cycle_number}")
+                        likelihood = np.array(self.full_batch_likelihoods(train_loader))
+                        self.cycle_likelihoods[cycle_number] = likelihood
+                        logger.info(f"Cycle {cycle_number} full batch likelihood: {likelihood.mean():.6e}")
+                        self.save_ckpt(epoch=sched.current_epoch)
+                        if self.STORE_ALL_SAMPLES and getattr(args, "full_sample", False):
+                            torch.save(self.all_samples, "all_samples_TEST.ckpt")   # csgld.py:328-329
+                        self._after_cycle_completed(cycle_number)
+        loss, error = loss_acc.item(), err_acc.item()
+        return loss / nb_samples, error / nb_samples, cycle_updated
+
+    def _after_cycle_completed(self, cycle_number):
+        pass
+
+    def _reset_optimizer_states(self, log=True):
+        pass
+
+    # ---- per-cycle capture ------------------------------------------------------------------------------------
+    def _capture(self, cycle, epoch, batch_idx):
+        ch = self._chain()
+        n = ch.layout.n_padded
+        first = cycle not in self._cyc1
+        if first:
+            self._cyc1[cycle] = alloc_flat(n, ch.device, zero=False)
+            self._cyc2[cycle] = alloc_flat(n, ch.device, zero=False)
+        if self.CAPTURE == "avg":
+            if self.STORE_ALL_SAMPLES and getattr(self.args, "full_sample", False):
+                self.all_samples[f"{epoch}_{batch_idx}"] = self._dense(ch.theta).clone()      # csgld.py:278-279
+            if first:
+                ops.moments_avg(ch.theta, self._cyc1[cycle], self._cyc2[cycle], 0, init=True)
+            else:
+                cycle_count = self.samples_per_cycle.get(cycle, 0) + 1
+                ops.moments_avg(ch.theta, self._cyc1[cycle], self._cyc2[cycle], cycle_count - 1, div_mode=self.div_mode)
+        else:   # Welford with the reference's double-counted n (Appendix B.3): n runs 3, 5, 7, ...
+            if first:
+                ops.moments_welford(ch.theta, self._cyc1[cycle], self._cyc2[cycle], 1, init=True)
+                self.samples_per_cycle[cycle] = 1
+            else:
+                n_w = self.samples_per_cycle.get(cycle, 0) + 1
+                ops.moments_welford(ch.theta, self._cyc1[cycle], self._cyc2[cycle], n_w, div_mode=self.div_mode)
+                self.samples_per_cycle[cycle] = n_w
+
+    def _cycle_variance_spec(self, cycle):
+        """(second buffer, var_mode, scale) for bdl_draw; keeps the reference's evaluation order so that a cycle with
+        exactly one sample raises ZeroDivisionError in the 'avg' scheme (Appendix B.7)."""
+        if self.CAPTURE == "avg":
+            cnt = self.samples_per_cycle.get(cycle, 0)
+            ratio = cnt / (cnt - 1)
+            return self._cyc2[cycle], ops.VAR_FROM_MOMENTS, (ratio if cnt > 1 else 1.0)
+        cnt = self.samples_per_cycle.get(cycle, 0)
+        if cnt > 1:
+            return self._cyc2[cycle], ops.VAR_FROM_WELFORD, float(cnt - 1)
+        return None, ops.VAR_TINY, 1.0
+
+    # ---- GMM ensemble (methods/csgld.py:333-456) -----------------------------------------------------------------
+    def evaluate(self, test_loader):
+        args = self.args
+        dev = args.device
+        ch = self._chain()
+        gmm_weights = self.calculate_gmm_weights()
+        self.logger.info(f"GMM component weights: {gmm_weights}")
+        ev = _EvalNet(self.net, ch.layout)
+        self._eval_calls += 1
+        cycles = [c for c in self._cyc1 if not gmm_weights.get(c, 0.0) < 1e-10]
+        specs = {c: self._cycle_variance_spec(c) for c in cycles} if self.nst > 0 else {}
+        loss_sum = torch.zeros(1, dtype=torch.float64, device=dev)
+        err_cnt = torch.zeros(1, dtype=torch.int32, device=dev)
+        nb, ys, lgs, lgalls = 0, [], [], []
+        with torch.no_grad(), tqdm(test_loader, unit="batch") as tepoch:
+            for b_idx, (x, y) in enumerate(tepoch):
+                x, y = x.to(dev, non_blocking=True), y.to(dev, non_blocking=True)
+                comps = []
+                batch_logits = None
+                for ci, c in enumerate(cycles):
+                    outs = []
+                    if self.nst == 0:
+                        ev.load(self._cyc1[c])
+                        outs.append(ev.net(x))
+                    else:
+                        second, var_mode, scale = specs[c]
+                        for ii in range(self.nst):
+                            ev.draw(self._cyc1[c], second, var_mode, scale, self.noise_mode, self.seed,
+                                    _pack_subseq(self._eval_calls, b_idx, c, ii), self.div_mode)
+                            outs.append(ev.net(x))
+                    comp = torch.stack(outs, 2).contiguous().float()
+                    comps.append(comp)
+                    if batch_logits is None:
+                        batch_logits = torch.empty(comp.shape[:2], dtype=torch.float32, device=dev)
+                    # weighted sum of log-probabilities (Appendix B.5); nst == 0 uses the raw logits (csgld.py:419-420)
+                    if self.nst == 0:
+                        w = torch.tensor(gmm_weights.get(c, 0.0), dtype=torch.float32, device=dev)
+                        batch_logits = w * comp.squeeze(2) if ci == 0 else batch_logits + w * comp.squeeze(2)
+                    else:
+                        ops.ensemble(comp, batch_logits, self.nst, weight=gmm_weights.get(c, 0.0), mode=1 if ci == 0 else 2)
+                batch_logits_all = torch.stack(comps, dim=3) if comps else \
+                    torch.zeros((x.size(0), args.num_classes, 1, 1), device=dev)
+                ops.ce_err(batch_logits.contiguous(), y, loss_sum, err_cnt)
+                ys.append(y)
+                lgs.append(batch_logits)
+                lgalls.append(batch_logits_all)
+                nb += len(y)
+        return self._finish_eval(loss_sum, err_cnt, nb, ys, lgs, lgalls)
+
+    # ---- cycle likelihoods and GMM weights (methods/csgld.py:508-594) ----------------------------------------
+    def full_batch_likelihoods(self, train_loader):
+        """exp(-mean CE over the training set) for max(1, nst) draws around the cycle's centre."""
+        self.logger.info(f"Calculating full-batch likelihood for current cycle using {self.nst} samples...")
+        ch = self._chain()
+        dev = self.args.device
+        c = self.current_cycle
+        spec = None
+        if self.LIKELIHOOD_MEAN == "theta":
+            mean = ch.theta
+            if c in self._cyc2 and c in self._cyc1 and self.samples_per_cycle.get(c, 0) > 1:
+                spec = self._cycle_variance_spec(c)
+        else:
+            mean = self._cyc1[c]                          # KeyError if the cycle captured nothing, as the reference
+            if self.CAPTURE == "welford":
+                spec = self._cycle_variance_spec(c) if c in self._cyc2 else None
+            elif c in self._cyc2 and self.samples_per_cycle.get(c, 0) > 1:
+                spec = self._cycle_variance_spec(c)
+            else:
+                raise TypeError("cycle variance is None (reference: vector_to_parameters(None, ...), Appendix B.8)")
+        ev = _EvalNet(self.net, ch.layout)
+        self._eval_calls += 1
+        likelihoods = []
+        n_draws = max(1, self.nst)
+        for sample_idx in range(n_draws):
+            if self.nst > 0 and spec is not None:
+                second, var_mode, scale = spec
+                ev.draw(mean, second, var_mode, scale, self.noise_mode, self.seed,
+                        _pack_subseq(self._eval_calls, 0xFFFFFF, c, sample_idx), self.div_mode)
+            else:
+                ev.load(ch.theta)                        # net_sample = deepcopy(self.net), no perturbation
+            avg_loss, _ = self._point_estimate(train_loader, ev.net)
+            likelihood = np.exp(-avg_loss)
+            likelihoods.append(likelihood)
+            self.logger.info(f"Sample {sample_idx + 1} - Full batch average loss: {avg_loss:.6f}, "
+                             f"likelihood: {likelihood:.6e}")
+        return likelihoods
+
+    def calculate_gmm_weights(self):
+        """w_c = 1 / mean_j(1 / L_cj), normalised (host fp64; methods/csgld.py:565-594)."""
+        if not self.cycle_likelihoods:
+            return {0: 1.0}
+        weights = {c: 1.0 / np.mean([1.0 / l for l in ls]) for c, ls in self.cycle_likelihoods.items()}
+        total = sum(weights.values())
+        if total > 0:
+            return {c: w / total for c, w in weights.items()}
+        return {c: 1.0 / len(weights) for c in weights}
+
+    # ---- checkpoints (methods/csgld.py:470-506) ----------------------------------------------------------------
+    def save_ckpt(self, epoch):
+        fname = os.path.join(self.args.log_dir, f"{self.current_cycle}_ckpt.pt")
+        last = self._dense(self._chain().theta).clone() if self.LAST_THETA_AS_VECTOR else self._state_dict_copy()
+        torch.save({
+            "last_theta": last,
+            "cycle_theta_mom1": {c: t.clone() for c, t in self.cycle_theta_mom1.items()},
+            "cycle_theta_mom2": {c: t.clone() for c, t in self.cycle_theta_mom2.items()},
+            "cycle_likelihoods": self.cycle_likelihoods,
+            "cycle_states": self.cycle_states,
+            "epoch": epoch,
+            "current_cycle": self.current_cycle,
+            "samples_per_cycle": self.samples_per_cycle,
+        }, fname)
+        return fname
+
+    def load_ckpt(self, ckpt_path):
+        ckpt = torch.load(ckpt_path, map_location=self.args.device, weights_only=False)
+        self.cycle_theta_mom1 = ckpt.get("cycle_theta_mom1", {})
+        self.cycle_theta_mom2 = ckpt.get("cycle_theta_mom2", {})
+        self.cycle_likelihoods = ckpt.get("cycle_likelihoods", {})
+        self.current_cycle = ckpt.get("current_cycle", 0)
+        self.samples_per_cycle = ckpt.get("samples_per_cycle", {})
+        return ckpt["epoch"]

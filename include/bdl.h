@@ -52,6 +52,7 @@ typedef enum {
 /* Element class bits (per run). */
 #define BDL_CLS_HEAD 1u    /* readout_name in pname  -> lr_head / head noise scale (methods/sghmc.py:485-488) */
 #define BDL_CLS_PRIOR 2u   /* prior pull enabled; cleared for 'bias' in pname && bias=='uninformative' (:494) */
+#define BDL_CLS_SKIP 4u    /* p.grad is None: the reference leaves such a tensor untouched (:484)            */
 
 /* A run = a contiguous range of the padded flat layout whose elements share one class
  * (and, optionally, one gradient tensor).  Runs are sorted, contiguous and cover [0, n). */

@@ -160,6 +160,7 @@ int bdl_oracle_step(int variant, float* theta, const float* g, const float* thet
     const uint32_t sid = nz->stream_id;
     for (uint32_t r = 0; r < nruns; ++r) {
         const bdl_run run = runs[r];
+        if (run.cls & BDL_CLS_SKIP) continue;
         const int64_t q0 = (int64_t)(run.begin / 4), q1 = (int64_t)(run.end / 4);
 #pragma omp parallel for schedule(static)
         for (int64_t q = q0; q < q1; ++q) {

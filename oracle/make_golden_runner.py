@@ -1,0 +1,236 @@
+"""Runner-level golden vectors: the reference's own ``Runner.train()`` executed end-to-end on CPU.
+
+A tiny network (``InjectNet``) makes the run fully deterministic and device-independent:
+  * in training, ``criterion(out, y) == out.sum()`` and ``out`` carries ``sum_t (p_t * G_t[step]).sum() / 16``
+    broadcast over a [4,4] output, so after ``backward()`` every ``p.grad`` equals the injected ``G_t[step]``
+    *exactly* (16 * 1/16 is exact in fp32);
+  * in evaluation (no grad) ``out`` is a small detached MLP of all sampled parameters and the criterion is the
+    ordinary cross entropy, so ``evaluate()`` / ``calibration.analyze`` see realistic logits;
+  * every ``torch.randn_like`` (training noise and posterior draws) is served from a recorded tape.
+The same ``InjectNet`` / criterion / tape are used by tests/test_runner_gpu.py to drive the drop-in Runner on the
+GPU, which must reproduce every recorded quantity.
+
+TEST INFRASTRUCTURE ONLY.  Run via ``python oracle/make_golden.py runner`` in the build container.
+"""
+import argparse
+import logging
+import os
+import tempfile
+from collections import OrderedDict
+
+import numpy as np
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from oracle import refshim
+
+K_CLASSES, BATCH, FEATS = 4, 4, 16
+SHAPES = OrderedDict([
+    ("layers.0.weight", (29, 11)), ("layers.0.bias", (29,)),
+    ("layers.2.weight", (17, 29)), ("layers.2.bias", (17,)),
+    ("norm.weight", (17,)), ("norm.bias", (17,)),
+    ("classifier.weight", (K_CLASSES, 17)), ("classifier.bias", (K_CLASSES,)),
+])
+
+
+class InjectNet(nn.Module):
+    readout_name = "classifier"
+
+    def __init__(self, seed, G=None):
+        super().__init__()
+        gen = torch.Generator().manual_seed(seed)
+        for name, shape in SHAPES.items():
+            parts = name.split(".")
+            mod = self
+            for part in parts[:-1]:
+                if not hasattr(mod, part):
+                    mod.add_module(part, nn.Module())
+                mod = getattr(mod, part)
+            scale = 1.0 if name == "norm.weight" else 0.3
+            mod.register_parameter(parts[-1], nn.Parameter(torch.randn(shape, generator=gen) * scale))
+        self.register_buffer("G", torch.zeros(1, 1) if G is None else torch.as_tensor(G, dtype=torch.float32))
+        self.train_calls = 0
+
+    def _mlp(self, x):
+        P = {n: p.detach() for n, p in self.named_parameters()}
+        f = x.reshape(x.shape[0], -1)[:, :11]
+        h = torch.tanh(f @ P["layers.0.weight"].t() + P["layers.0.bias"])
+        h = torch.tanh(h @ P["layers.2.weight"].t() + P["layers.2.bias"])
+        h = h * P["norm.weight"] + P["norm.bias"]
+        return h @ P["classifier.weight"].t() + P["classifier.bias"]
+
+    def forward(self, x):
+        out = self._mlp(x)
+        if self.training and torch.is_grad_enabled():
+            g = self.G[self.train_calls]
+            self.train_calls += 1
+            tot, pos = 0.0, 0
+            for p in self.parameters():
+                tot = tot + (p * g[pos:pos + p.numel()].view(p.shape)).sum()
+                pos += p.numel()
+            assert out.shape == (BATCH, K_CLASSES)
+            out = out + (tot * (1.0 / (BATCH * K_CLASSES))).expand(BATCH, K_CLASSES)
+        return out
+
+
+class InjectCriterion:
+    """train: sum of outputs (gradient injection); eval: mean cross entropy, like torch.nn.CrossEntropyLoss()."""
+
+    def __call__(self, out, y):
+        if out.requires_grad:
+            return out.sum()
+        return F.cross_entropy(out, y)
+
+
+def make_loaders(seed, n_train=3, n_val=2, n_test=2):
+    rng = np.random.default_rng(seed)
+
+    def mk(nb):
+        return [(torch.from_numpy(rng.standard_normal((BATCH, 1, 4, 4)).astype(np.float32)),
+                 torch.from_numpy(rng.integers(0, K_CLASSES, BATCH).astype(np.int64))) for _ in range(nb)]
+    return mk(n_train), mk(n_val), mk(n_test)
+
+
+def loaders_to_arrays(loaders):
+    out = {}
+    for nm, ld in zip(("train", "val", "test"), loaders):
+        out[f"x_{nm}"] = np.stack([x.numpy() for x, _ in ld])
+        out[f"y_{nm}"] = np.stack([y.numpy() for _, y in ld])
+    return out
+
+
+def loaders_from_arrays(z, device=None):
+    res = []
+    for nm in ("train", "val", "test"):
+        res.append([(torch.from_numpy(x), torch.from_numpy(y)) for x, y in zip(z[f"x_{nm}"], z[f"y_{nm}"])])
+    return res
+
+
+CASES = {
+    # name: (method, hparams, args overrides)
+    "sgld": ("sgld", dict(prior_sig=0.8, Ninflate=5.0, nd=0.6, burnin=1, thin=2, nst=3, bias="informative"),
+             dict(momentum=0.5, epochs=3)),
+    "sghmc": ("sghmc", dict(prior_sig=0.8, Ninflate=5.0, nd=0.6, burnin=1, thin=1, nst=3, bias="uninformative",
+                            momentum_decay=0.18), dict(momentum=0.9, epochs=3)),
+    "adam_sghmc": ("adam_sghmc", dict(prior_sig=0.8, Ninflate=5.0, nd=0.6, burnin=1, thin=2, nst=2, bias="informative",
+                                      momentum_decay=0.1, beta1=0.9, beta2=0.99, epsilon=1e-6),
+                   dict(momentum=0.5, epochs=3)),
+    "sgld_nst0": ("sgld", dict(prior_sig=0.8, Ninflate=5.0, nd=0.6, burnin=1, thin=2, nst=0, bias="informative"),
+                  dict(momentum=0.0, epochs=2)),
+    "csgld": ("csgld", dict(prior_sig=0.8, Ninflate=5.0, nd=0.6, thin=1, nst=2, bias="informative"),
+              dict(momentum=0.5, epochs=4, num_cycles=2)),
+    "csghmc": ("csghmc", dict(prior_sig=0.05, Ninflate=5.0, nd=0.6, burnin=0, thin=1, nst=2, bias="informative",
+                              momentum_decay=0.18), dict(momentum=0.0, epochs=4, num_cycles=2)),
+    "adam_csghmc": ("adam_csghmc", dict(prior_sig=0.8, Ninflate=5.0, nd=0.6, burnin=0, thin=1, nst=2,
+                                        bias="uninformative", momentum_decay=0.1, beta1=0.9, beta2=0.99, epsilon=1e-6,
+                                        temperature=1.5), dict(momentum=0.0, epochs=4, num_cycles=2)),
+}
+
+
+def make_args(hparams, log_dir, device, *, momentum, epochs, num_cycles=2, lr=5e-3, lr_head=2e-2, ND=12):
+    a = argparse.Namespace()
+    a.device = device
+    a.ND = ND
+    a.lr, a.lr_head, a.momentum, a.epochs = lr, lr_head, momentum, epochs
+    a.pretrained = "synthetic"
+    a.hparams = {k: str(v) for k, v in hparams.items()}
+    a.num_cycles = num_cycles
+    a.proportion_exploration = 0.5
+    a.full_sample = False
+    a.test_eval_freq = 1
+    a.ece_num_bins = 15
+    a.num_classes = K_CLASSES
+    a.log_dir = log_dir
+    a.seed = 1234
+    return a
+
+
+def n_params():
+    return sum(int(np.prod(s)) for s in SHAPES.values())
+
+
+def run_reference_case(name):
+    method, hp, over = CASES[name]
+    mod = refshim.load(f"methods.{method}")
+    seed = 500 + sorted(CASES).index(name)
+    rng = np.random.default_rng(seed)
+    loaders = make_loaders(seed)
+    steps = over["epochs"] * len(loaders[0])
+    G = (rng.standard_normal((steps, n_params())) * 0.05).astype(np.float32)
+    tape = rng.standard_normal(400_000).astype(np.float32)
+    net = InjectNet(seed, G)
+    net0 = InjectNet(seed + 1)
+    theta_init = torch.cat([p.detach().reshape(-1) for p in net.parameters()]).numpy().copy()
+    theta0 = torch.cat([p.detach().reshape(-1) for p in net0.parameters()]).numpy().copy()
+    log_dir = tempfile.mkdtemp(prefix="bdl_golden_runner_")
+    args = make_args(hp, log_dir, torch.device("cpu"), **over)
+    logger = logging.getLogger(f"golden.{name}")
+    logger.addHandler(logging.NullHandler())
+    logger.propagate = False
+    runner = mod.Runner(net, net0, args, logger)
+    runner.criterion = InjectCriterion()
+
+    evals = []
+    orig_eval = runner.evaluate
+
+    def recording_eval(loader):
+        res = orig_eval(loader)
+        evals.append(res)
+        return res
+    runner.evaluate = recording_eval
+
+    cwd = os.getcwd()
+    os.chdir(log_dir)
+    try:
+        with refshim.injected_noise(tape) as tp:
+            ret = runner.train(loaders[0], loaders[1], loaders[2])
+            used = tp.pos
+    finally:
+        os.chdir(cwd)
+
+    rec = dict(G=G, tape=tape[:used], tape_used=used, theta_init=theta_init, theta0=theta0,
+               theta_final=torch.cat([p.detach().reshape(-1) for p in runner.net.parameters()]).numpy(),
+               n_evals=len(evals), **loaders_to_arrays(loaders))
+    for i, (loss, err, targets, logits, logits_all) in enumerate(evals):
+        rec[f"eval{i}_loss"], rec[f"eval{i}_err"] = loss, err
+        rec[f"eval{i}_targets"], rec[f"eval{i}_logits"], rec[f"eval{i}_logits_all"] = targets, logits, logits_all
+    if hasattr(runner, "post_theta_mom1"):
+        rec["post_theta_mom1"] = runner.post_theta_mom1.numpy()
+        if hasattr(runner, "post_theta_mom2"):
+            rec["post_theta_mom2"] = runner.post_theta_mom2.numpy()
+        rec["post_theta_cnt"] = runner.post_theta_cnt
+    if hasattr(runner, "cycle_theta_mom1"):
+        cyc = sorted(runner.cycle_theta_mom1)
+        rec["cycles"] = np.array(cyc)
+        for c in cyc:
+            rec[f"cyc{c}_mom1"] = runner.cycle_theta_mom1[c].numpy()
+            rec[f"cyc{c}_mom2"] = runner.cycle_theta_mom2[c].numpy()
+            rec[f"cyc{c}_count"] = runner.samples_per_cycle[c]
+            rec[f"cyc{c}_lik"] = np.asarray(runner.cycle_likelihoods[c], dtype=np.float64)
+        rec["samples_collected"] = runner.samples_collected
+        rec["losses_train"] = ret["losses_train"]
+        rec["losses_test"] = ret["losses_test"]
+    if hasattr(runner.model, "momentum_buffer"):
+        names = [n for n, _ in runner.net.named_parameters()]
+        rec["v_final"] = torch.cat([runner.model.momentum_buffer[n].reshape(-1) for n in names]).numpy()
+    # checkpoint key inventory (on-disk contract)
+    ck_files = sorted(f for f in os.listdir(log_dir) if f.endswith("ckpt.pt"))
+    rec["ckpt_files"] = np.array(ck_files)
+    if ck_files:
+        ck = torch.load(os.path.join(log_dir, ck_files[-1]), map_location="cpu", weights_only=False)
+        rec["ckpt_keys"] = np.array(sorted(ck.keys()))
+        lt = ck.get("last_theta")
+        rec["ckpt_last_theta_kind"] = np.array("none" if lt is None else ("vector" if torch.is_tensor(lt) else "state_dict"))
+    rec["hp_keys"] = np.array(sorted(hp))
+    rec["hp_vals"] = np.array([str(hp[k]) for k in sorted(hp)])
+    rec["method"] = np.array(method)
+    return rec
+
+
+def main(save):
+    torch.set_num_threads(1)
+    for name in CASES:
+        rec = run_reference_case(name)
+        save(f"runner_{name}", **rec)
+        print(f"  {name}: tape used {rec['tape_used']}, evaluate() calls {rec['n_evals']}")

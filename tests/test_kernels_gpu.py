@@ -1,0 +1,173 @@
+"""GPU parity of the capture / draw / ensemble / calibration kernels against the oracle and reference goldens."""
+import numpy as np
+import pytest
+import torch
+
+import golden_util as gu
+from oracle import sampler_oracle as so
+
+pytestmark = pytest.mark.gpu
+
+
+def bits_equal(a, b):
+    return np.array_equal(np.asarray(a, np.float32).view(np.uint32), np.asarray(b, np.float32).view(np.uint32))
+
+
+@pytest.mark.parametrize("n", [4, 1028, 100_004, 3_000_000])
+@pytest.mark.parametrize("div_name", ["true", "recip"])
+def test_moments_avg_and_welford_bit_exact(cuda_device, n, div_name):
+    from bayesdll_b200 import ops
+    div = dict(true=0, recip=1)[div_name]
+    rng = np.random.default_rng(n)
+    th = rng.standard_normal(n).astype(np.float32)
+    d = lambda a: torch.from_numpy(a).to(cuda_device)
+    m1, m2 = so.moments_init(th)
+    g1, g2 = torch.empty(n, device=cuda_device), torch.empty(n, device=cuda_device)
+    ops.moments_avg(d(th), g1, g2, 0, init=True)
+    assert bits_equal(g1.cpu().numpy(), m1) and bits_equal(g2.cpu().numpy(), m2)
+    mean, M2 = th.copy(), np.zeros(n, np.float32)
+    w1, w2 = torch.empty(n, device=cuda_device), torch.empty(n, device=cuda_device)
+    ops.moments_welford(d(th), w1, w2, 1, init=True)
+    for cnt in range(1, 6):
+        th = rng.standard_normal(n).astype(np.float32)
+        m1, m2 = so.moments_avg(th, m1, m2, cnt, div_name)
+        ops.moments_avg(d(th), g1, g2, cnt, div_mode=div)
+        assert bits_equal(g1.cpu().numpy(), m1) and bits_equal(g2.cpu().numpy(), m2)
+        nw = 2 * cnt + 1                                    # the reference's double-counted n: 3, 5, 7, ...
+        mean, M2 = so.moments_welford(th, mean, M2, nw, div_name)
+        ops.moments_welford(d(th), w1, w2, nw, div_mode=div)
+        assert bits_equal(w1.cpu().numpy(), mean) and bits_equal(w2.cpu().numpy(), M2)
+    # mom2 == None (nst == 0)
+    only1 = torch.empty(n, device=cuda_device)
+    ops.moments_avg(d(th), only1, None, 0, init=True)
+    assert bits_equal(only1.cpu().numpy(), th * np.float32(1.0))
+
+
+@pytest.mark.parametrize("n", [8, 40_004, 2_000_000])
+def test_posterior_draw_bit_exact_and_philox_equivalent(cuda_device, n):
+    from bayesdll_b200 import _lib, ops
+    rng = np.random.default_rng(n + 1)
+    mean = rng.standard_normal(n).astype(np.float32)
+    mom2 = (mean * mean + np.abs(rng.standard_normal(n)).astype(np.float32) * np.float32(1e-3)).astype(np.float32)
+    mom2[::7] = mean[::7] ** 2 - np.float32(1e-6)           # negative raw variance -> clamp path
+    M2 = np.abs(rng.standard_normal(n)).astype(np.float32)
+    eps = rng.standard_normal(n).astype(np.float32)
+    d = lambda a: torch.from_numpy(a).to(cuda_device)
+    out = torch.empty(n, device=cuda_device)
+    ops.draw(d(mean), d(mom2), out, ops.VAR_FROM_MOMENTS, 5 / 4, ops.make_noise(xi=d(eps)))
+    assert bits_equal(out.cpu().numpy(), so.posterior_draw(mean, so.variance_from_moments(mean, mom2, 5 / 4), eps))
+    for div_name, div in (("true", 0), ("recip", 1)):
+        ops.draw(d(mean), d(M2), out, ops.VAR_FROM_WELFORD, 6.0, ops.make_noise(xi=d(eps)), div_mode=div)
+        assert bits_equal(out.cpu().numpy(), so.posterior_draw(mean, so.variance_from_welford(M2, 7, div_name), eps))
+    ops.draw(d(mean), None, out, ops.VAR_TINY, 1.0, ops.make_noise(xi=d(eps)))
+    assert bits_equal(out.cpu().numpy(), so.posterior_draw(mean, so.variance_from_welford(M2, 1), eps))
+    # in-kernel Philox == injected Philox stream
+    xi = torch.empty(n, device=cuda_device)
+    ops.philox_normal(xi, 77, _lib.STREAM_DRAW, 12345)
+    a, b = torch.empty(n, device=cuda_device), torch.empty(n, device=cuda_device)
+    ops.draw(d(mean), d(mom2), a, ops.VAR_FROM_MOMENTS, 1.25, ops.make_noise(xi=xi))
+    ops.draw(d(mean), d(mom2), b, ops.VAR_FROM_MOMENTS, 1.25, ops.make_noise(seed=77, subseq=12345, stream_id=_lib.STREAM_DRAW))
+    assert torch.equal(a, b)
+
+
+@pytest.mark.parametrize("n", [4, 4096, 16384 * 5 + 4, 7_000_004])
+def test_ring_capture_tma_copy(cuda_device, n):
+    from bayesdll_b200 import ops
+    theta = torch.randn(n, device=cuda_device)
+    ring = torch.full((3, n), -1.0, device=cuda_device)
+    ops.capture_ring(theta, ring, 1)
+    torch.cuda.synchronize()
+    assert torch.equal(ring[1], theta)
+    assert (ring[0] == -1).all() and (ring[2] == -1).all()    # neighbours untouched
+    with pytest.raises(ops.BdlError):
+        ops.capture_ring(theta, ring, 3)
+
+
+@pytest.mark.parametrize("B,K,S", [(16, 37, 5), (64, 37, 40), (3, 10, 1), (128, 1000, 2), (1, 2, 7)])
+def test_ensemble_matches_oracle_and_torch(cuda_device, B, K, S):
+    from bayesdll_b200 import ops
+    rng = np.random.default_rng(B * K * S)
+    L = (rng.standard_normal((B, K, S)) * 3).astype(np.float32)
+    y = rng.integers(0, K, B).astype(np.int64)
+    Ld = torch.from_numpy(L).to(cuda_device)
+    out = torch.empty(B, K, device=cuda_device)
+    nst = S if S > 1 else 0
+    ops.ensemble(Ld, out, nst)
+    want = so.ensemble_average(L, nst)
+    np.testing.assert_allclose(out.cpu().numpy(), want, atol=1e-5, rtol=1e-5)
+    # the reference's own expression (methods/sgld.py:300), evaluated by torch on the same device
+    ref = torch.log_softmax(Ld, 1).logsumexp(-1) - (np.log(nst) if nst else 0.0)
+    np.testing.assert_allclose(out.cpu().numpy(), ref.cpu().numpy(), atol=1e-5, rtol=1e-5)
+    # mixture accumulation in log space (methods/csgld.py:428-431)
+    L2 = (rng.standard_normal((B, K, S)) * 3).astype(np.float32)
+    mixt = torch.empty(B, K, device=cuda_device)
+    ops.ensemble(Ld, mixt, nst, weight=0.3, mode=1)
+    ops.ensemble(torch.from_numpy(L2).to(cuda_device), mixt, nst, weight=0.7, mode=2)
+    want_mix = so.mixture([L, L2], [0.3, 0.7], nst) if nst else None
+    if nst:
+        np.testing.assert_allclose(mixt.cpu().numpy(), want_mix, atol=1e-5, rtol=1e-5)
+    # CE + error count
+    loss = torch.zeros(1, dtype=torch.float64, device=cuda_device)
+    err = torch.zeros(1, dtype=torch.int32, device=cuda_device)
+    ops.ce_err(out, torch.from_numpy(y).to(cuda_device), loss, err)
+    ops.ce_err(out, torch.from_numpy(y).to(cuda_device), loss, err)      # accumulates
+    ce = torch.nn.functional.cross_entropy(out, torch.from_numpy(y).to(cuda_device), reduction="sum").item()
+    assert abs(loss.item() - 2 * ce) <= 2e-5 * max(1.0, abs(ce))
+    assert err.item() == 2 * int((out.argmax(1).cpu().numpy() != y).sum())
+
+
+def test_probsum_path_equals_ensemble(cuda_device):
+    """Sample-sharded formulation: sum of softmax over samples, then log - log S == logsumexp of log_softmax."""
+    from bayesdll_b200 import ops
+    B, K, S = 32, 37, 8
+    L = torch.randn(B, K, S, device=cuda_device) * 2
+    direct = torch.empty(B, K, device=cuda_device)
+    ops.ensemble(L, direct, S)
+    acc = torch.zeros(B, K, device=cuda_device)
+    for s in range(S):
+        ops.probsum_accum(L[:, :, s].contiguous(), acc)
+    out = torch.empty(B, K, device=cuda_device)
+    ops.probsum_finalize(acc, out, S)
+    np.testing.assert_allclose(out.cpu().numpy(), direct.cpu().numpy(), atol=2e-6, rtol=2e-6)
+
+
+@pytest.mark.parametrize("tag", ["a", "b", "c", "d"])
+@pytest.mark.parametrize("tname", ["T1", "Tarr"])
+def test_calibration_matches_reference_golden(cuda_device, tag, tname):
+    """Bin counts bit-exact, ECE/MCE/NLL within 1e-6 of the reference's calibration.analyze (north star iii)."""
+    from bayesdll_b200 import calibration
+    z = np.load(gu.golden_path("calibration"))
+    logits, labels, M = z[f"{tag}_logits"], z[f"{tag}_labels"], int(z[f"{tag}_M"])
+    T = 1 if tname == "T1" else z[f"{tag}_{tname}_T"]
+    pre = f"{tag}_{tname}_"
+    bins, binned, accs, confs, sizes = calibration.calc_bins(labels, logits, M, T)
+    assert np.array_equal(bins, z[pre + "bins"])
+    assert np.array_equal(sizes, z[pre + "sizes"]), "bin counts must be bit-exact"
+    assert np.array_equal(binned, z[pre + "binned"])
+    assert np.array_equal(accs, z[pre + "accs"])                      # integer count / integer count in fp64
+    np.testing.assert_allclose(confs, z[pre + "confs"], rtol=1e-6)
+    ece, mce, nll = calibration.analyze(labels, logits, M, None, T)
+    assert calibration.last_near_edge == 0                            # certified: no probability within 16 ulp of an edge
+    assert abs(ece - z[pre + "ece"]) <= 1e-6 and abs(mce - z[pre + "mce"]) <= 1e-6
+    assert abs(nll - z[pre + "nll"]) <= 1e-6 * max(1.0, abs(z[pre + "nll"]))
+
+
+def test_calibration_edge_cases(cuda_device):
+    from bayesdll_b200 import calibration
+    # one-hot certain predictions: p == 1.0 must land in the last bin thanks to the 1+1e-8 upper edge
+    logits = np.full((8, 4), -200.0, np.float32)
+    labels = np.arange(8) % 4
+    logits[np.arange(8), labels] = 200.0
+    bins, binned, accs, confs, sizes = calibration.calc_bins(labels, logits, 15)
+    o = so.calc_bins(labels, logits, 15)
+    assert np.array_equal(sizes, o[4]) and sizes[-1] == 8 and sizes[0] == 24
+    assert np.array_equal(binned, o[1])
+    # uniform predictions, K = 1 class, a single row
+    for lg, lb in ((np.zeros((5, 10), np.float32), np.zeros(5, np.int64)), (np.zeros((3, 1), np.float32), np.zeros(3, np.int64)),
+                   (np.array([[0.3, -1.2, 2.0]], np.float32), np.array([2]))):
+        got = calibration.calc_bins(lb, lg, 15)
+        want = so.calc_bins(lb, lg, 15)
+        assert np.array_equal(got[4], want[4]) and np.array_equal(got[1], want[1])
+        e1, m1, n1 = calibration.analyze(lb, lg, 15, None)
+        e2, m2, n2 = so.analyze(lb, lg, 15)
+        assert abs(e1 - e2) < 1e-6 and abs(m1 - m2) < 1e-6 and abs(n1 - n2) < 1e-6

@@ -1,0 +1,155 @@
+"""GPU end-to-end parity: the drop-in ``Runner.train()`` against recordings of the reference's own
+``Runner.train()`` (tests/golden/runner_*.npz, produced by oracle/make_golden_runner.py).
+
+Gradients are injected through ``InjectNet`` and every ``torch.randn_like`` -- sampler noise and posterior draws --
+is served from the recorded tape, so both implementations consume identical inputs in identical order.  The test
+reads like the reference's own usage: build args, construct ``Runner(net, net0, args, logger)``, call ``train``.
+"""
+import logging
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import golden_util as gu
+
+pytestmark = pytest.mark.gpu
+
+CASES = ["sgld", "sghmc", "adam_sghmc", "sgld_nst0", "csgld", "csghmc", "adam_csghmc"]
+BIT_EXACT = {"sgld", "sghmc", "sgld_nst0", "csgld", "csghmc"}
+
+
+def _logger():
+    lg = logging.getLogger("test_runner")
+    lg.addHandler(logging.NullHandler())
+    lg.propagate = False
+    return lg
+
+
+def _run(name, device, tmp_path, extra_hp=None):
+    import importlib
+    from oracle import make_golden_runner as mgr
+    from oracle import refshim
+    z = np.load(gu.golden_path(f"runner_{name}"), allow_pickle=False)
+    method, hp, over = mgr.CASES[name]
+    hp = dict(hp, noise="torch", div="ieee", **(extra_hp or {}))
+    seed = 500 + sorted(mgr.CASES).index(name)
+    net, net0 = mgr.InjectNet(seed, z["G"]), mgr.InjectNet(seed + 1)
+    assert np.array_equal(torch.cat([p.detach().reshape(-1) for p in net.parameters()]).numpy(), z["theta_init"])
+    args = mgr.make_args(hp, str(tmp_path), device, **over)
+    Runner = importlib.import_module(f"bayesdll_b200.methods.{method}").Runner
+    runner = Runner(net, net0, args, _logger())
+    runner.criterion = mgr.InjectCriterion()
+    evals = []
+    orig = runner.evaluate
+
+    def rec(loader):
+        r = orig(loader)
+        evals.append(r)
+        return r
+    runner.evaluate = rec
+    loaders = mgr.loaders_from_arrays(z)
+    cwd = os.getcwd()
+    os.chdir(tmp_path)
+    try:
+        with refshim.injected_noise(z["tape"]) as tape:
+            ret = runner.train(*loaders)
+    finally:
+        os.chdir(cwd)
+    return z, runner, evals, ret, tape
+
+
+def _close(name, got, want, what, rel=1e-6):
+    got, want = np.asarray(got), np.asarray(want)
+    assert got.shape == want.shape, f"{what}: shape {got.shape} != {want.shape}"
+    if name in BIT_EXACT:
+        assert np.array_equal(got.view(np.uint32), want.view(np.uint32)), \
+            f"{what}: {(got.view(np.uint32) != want.view(np.uint32)).sum()} of {got.size} elements differ"
+    else:
+        assert gu.max_rel(got, want) <= rel, f"{what}: rel {gu.max_rel(got, want):.2e}"
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_runner_train_matches_reference(cuda_device, tmp_path, name):
+    z, runner, evals, ret, tape = _run(name, cuda_device, tmp_path)
+    # every recorded draw was consumed, in order, and none beyond
+    assert tape.pos == int(z["tape_used"])
+    dense = lambda flat: runner._dense(flat).cpu().numpy()
+    _close(name, dense(runner.model.chain.theta), z["theta_final"], "theta_final")
+    if "v_final" in z.files:
+        _close(name, dense(runner.model.chain.v), z["v_final"], "momentum_buffer")
+    if "post_theta_mom1" in z.files:
+        assert runner.post_theta_cnt == int(z["post_theta_cnt"])
+        _close(name, runner.post_theta_mom1.cpu().numpy(), z["post_theta_mom1"], "post_theta_mom1")
+        if "post_theta_mom2" in z.files:
+            _close(name, runner.post_theta_mom2.cpu().numpy(), z["post_theta_mom2"], "post_theta_mom2")
+    if "cycles" in z.files:
+        assert sorted(runner.cycle_theta_mom1) == z["cycles"].tolist()
+        assert runner.samples_collected == int(z["samples_collected"])
+        for c in z["cycles"].tolist():
+            assert runner.samples_per_cycle[c] == int(z[f"cyc{c}_count"])
+            _close(name, runner.cycle_theta_mom1[c].cpu().numpy(), z[f"cyc{c}_mom1"], f"cycle {c} mom1")
+            _close(name, runner.cycle_theta_mom2[c].cpu().numpy(), z[f"cyc{c}_mom2"], f"cycle {c} mom2", rel=2e-5)
+            np.testing.assert_allclose(runner.cycle_likelihoods[c], z[f"cyc{c}_lik"], rtol=2e-5)
+        np.testing.assert_allclose(ret["losses_train"], z["losses_train"], rtol=1e-5, atol=1e-6)
+        np.testing.assert_allclose(ret["losses_test"], z["losses_test"], rtol=2e-5, atol=1e-6)
+    # evaluate(): same number of calls, same outputs (logits go through a GPU matmul -> tolerance, SURVEY 8c iii)
+    assert len(evals) == int(z["n_evals"])
+    for i, (loss, err, targets, logits, logits_all) in enumerate(evals):
+        assert np.array_equal(targets, z[f"eval{i}_targets"]) and targets.dtype == np.int64
+        assert logits.dtype == np.float32 and logits_all.dtype == np.float32
+        assert logits_all.shape == z[f"eval{i}_logits_all"].shape
+        np.testing.assert_allclose(logits_all, z[f"eval{i}_logits_all"], atol=1e-5, rtol=1e-5)
+        np.testing.assert_allclose(logits, z[f"eval{i}_logits"], atol=1e-5, rtol=1e-5)
+        assert abs(loss - float(z[f"eval{i}_loss"])) <= 1e-5 * max(1.0, abs(float(z[f"eval{i}_loss"])))
+        assert err == float(z[f"eval{i}_err"])
+    # on-disk contract: same checkpoint files and keys
+    files = sorted(f for f in os.listdir(tmp_path) if f.endswith("ckpt.pt"))
+    assert files == z["ckpt_files"].tolist()
+    if files:
+        ck = torch.load(os.path.join(tmp_path, files[-1]), map_location="cpu", weights_only=False)
+        assert sorted(ck.keys()) == z["ckpt_keys"].tolist()
+        kind = "none" if ck.get("last_theta") is None else ("vector" if torch.is_tensor(ck["last_theta"]) else "state_dict")
+        assert kind == str(z["ckpt_last_theta_kind"])
+        n_dense = z["theta_init"].size
+        for key in ("post_theta_mom1", "post_theta_mom2"):
+            if ck.get(key) is not None:
+                assert ck[key].shape == (n_dense,)          # dense parameters_to_vector order, no padding
+        if kind == "vector":
+            assert ck["last_theta"].shape == (n_dense,)
+        assert os.path.exists(os.path.join(tmp_path, "logits_test.pkl"))
+
+
+def test_runner_flat_gradient_mode_is_identical(cuda_device, tmp_path):
+    """grad=flat (gather into the flat buffer) and grad=table (read p.grad in place) give the same trajectory."""
+    z, runner, _, _, _ = _run("sghmc", cuda_device, tmp_path, extra_hp=dict(grad="flat"))
+    got = runner._dense(runner.model.chain.theta).cpu().numpy()
+    assert np.array_equal(got.view(np.uint32), z["theta_final"].view(np.uint32))
+
+
+def test_model_forward_keeps_reference_contract(cuda_device):
+    """Model.forward(x, y, net, net0, criterion, lrs, Ninflate, nd) -> (float, detached [B,K]); optimizer.step() after it
+    is harmless; state is reachable under the reference's attribute names."""
+    from oracle import make_golden_runner as mgr
+    from bayesdll_b200.methods import adam_sghmc
+    z = np.load(gu.golden_path("runner_adam_sghmc"), allow_pickle=False)
+    net, net0 = mgr.InjectNet(1, z["G"]).to(cuda_device), mgr.InjectNet(2).to(cuda_device)
+    args = mgr.make_args(dict(mgr.CASES["adam_sghmc"][1]), "/tmp", cuda_device, momentum=0.5, epochs=1)
+    runner = adam_sghmc.Runner(net, net0, args, _logger())
+    x = torch.randn(mgr.BATCH, 1, 4, 4, device=cuda_device)
+    y = torch.randint(0, mgr.K_CLASSES, (mgr.BATCH,), device=cuda_device)
+    net.train()
+    before = torch.cat([p.detach().reshape(-1) for p in net.parameters()]).clone()
+    loss, out = runner.model(x, y, runner.net, runner.net0, mgr.InjectCriterion(),
+                             [pg["lr"] for pg in runner.optimizer.param_groups], runner.Ninflate, runner.nd)
+    after = torch.cat([p.detach().reshape(-1) for p in net.parameters()]).clone()
+    runner.optimizer.step()
+    assert isinstance(loss, float) and out.shape == (mgr.BATCH, mgr.K_CLASSES) and not out.requires_grad
+    assert not torch.equal(before, after)
+    assert torch.equal(after, torch.cat([p.detach().reshape(-1) for p in net.parameters()]))   # step() is a no-op
+    names = [n for n, _ in net.named_parameters()]
+    assert list(runner.model.momentum_buffer) == names and list(runner.model.m) == names and list(runner.model.v) == names
+    assert runner.model.t == 1
+    sd = runner.optimizer.state_dict()
+    assert len(sd["state"]) == len(names) and all("momentum_buffer" in s for s in sd["state"].values())
