@@ -18,6 +18,7 @@ VARIANT_NAMES = {SGLD: "sgld", SGHMC: "sghmc", CSGHMC: "csghmc", ADAM_SGHMC: "ad
 CLS_HEAD, CLS_PRIOR, CLS_SKIP = 1, 2, 4
 DIV_IEEE, DIV_RECIP = 0, 1
 STREAM_STEP, STREAM_DRAW, STREAM_USER = 0, 1, 2
+BUF_THETA, BUF_THETA0, BUF_V, BUF_M, BUF_S, BUF_SGD, BUF_GRAD = range(7)
 MAX_RUNS = 2048
 
 
@@ -55,12 +56,18 @@ SIGNATURES = {
     "bdl_moments_avg": [_P, _P, _P, _U64, _F, _F, _I32, _I32, _P],
     "bdl_moments_welford": [_P, _P, _P, _U64, _F, _I32, _I32, _P],
     "bdl_capture_ring": [_P, _P, _U64, _U64, _P],
-    "bdl_draw": [_P, _P, _P, _U64, _I32, _F, _I32, C.POINTER(Noise), _P],
+    "bdl_draw": [_P, _P, _P, _P, _U64, _I32, _F, _I32, C.POINTER(Noise), _P],
     "bdl_ensemble": [_P, _U32, _U32, _U32, _F, _F, _I32, _P, _P],
     "bdl_ce_err": [_P, _P, _U32, _U32, _P, _P, _P],
     "bdl_probsum_accum": [_P, _U32, _U32, _P, _P],
     "bdl_probsum_finalize": [_P, _U32, _U32, _F, _F, _I32, _P, _P],
     "bdl_calibrate": [_P, _P, _U64, _U32, _D, _I32, _P, _U32, _P, _P, _P, _P, _P, _P, _P],
+    "bdl_chain_create": [_U64, _I32, _I32, _U64, C.POINTER(_P)],
+    "bdl_chain_destroy": [_P],
+    "bdl_chain_upload": [_P, _I32, _P],
+    "bdl_chain_download": [_P, _I32, _P],
+    "bdl_chain_device_ptr": [_P, _I32, C.POINTER(_P)],
+    "bdl_chain_step_host": [_P, _P, _P, _P, _U32, C.POINTER(Scalars), C.POINTER(Noise)],
 }
 
 _lib = None

@@ -215,7 +215,7 @@ calibrate_kernel(const float* __restrict__ logits, const int64_t* __restrict__ l
             // rounding could then land in the neighbouring bin)
             const double tol = p * (sizeof(T) == 4 ? 16.0 * 5.9604644775390625e-08 : 16.0 * 1.1102230246251565e-16);
             const double dl = b > 0 ? p - s_edges[b - 1] : 1.0;
-            const double dr = b < static_cast<int>(M) ? s_edges[b] - p : 1.0;
+            const double dr = b + 1 < static_cast<int>(M) ? s_edges[b] - p : 1.0;   // p <= 1 < last edge for any softmax
             if (dl <= tol || dr <= tol) atomicAdd(&s_near, 1u);
             if (binned) binned[static_cast<size_t>(r) * K + k] = b;
             if (b < static_cast<int>(M)) {

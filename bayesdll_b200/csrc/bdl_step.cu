@@ -33,7 +33,8 @@ struct StepParams {
     const float* xi;
     const bdl_run* runs;
     uint32_t nruns;
-    uint32_t n4;  // number of float4 groups
+    uint32_t n4;       // one past the last float4 group to process
+    uint32_t q_begin;  // first float4 group to process (0 except for chunked host-buffer steps)
     // scalars (already rounded to fp32 by the host)
     float lr[2], neg_lr[2], c[2];
     float oma, sig2, inv_sig2, N, inv_N, mu;
@@ -160,12 +161,12 @@ __global__ void __launch_bounds__(kThreads, (min_blocks<kVariant, kHasBuf, kPhil
 step_kernel(const StepParams p) {
     using U = Uses<kVariant>;
     const uint32_t tile_groups = kThreads * kU;
-    const uint32_t ntiles = (p.n4 + tile_groups - 1) / tile_groups;
+    const uint32_t ntiles = (p.n4 - p.q_begin + tile_groups - 1) / tile_groups;
     RunCursor cur;
     cursor_load(cur, p, 0);
 
     for (uint32_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-        const uint32_t q0 = tile * tile_groups + threadIdx.x;
+        const uint32_t q0 = p.q_begin + tile * tile_groups + threadIdx.x;
         float4 th[kU], g[kU], th0[kU], v[kU], m[kU], s[kU], b[kU], xi[kU];
         uint32_t cls[kU];
         bool act[kU];
@@ -239,7 +240,7 @@ static int launch_u(const StepParams& p, cudaStream_t st) {
                              : min_blocks<kVariant, kHasBuf, kPhilox, 4>();
     }
     const uint32_t tile_groups = kThreads * unroll;
-    const uint32_t ntiles = (p.n4 + tile_groups - 1) / tile_groups;
+    const uint32_t ntiles = (p.n4 - p.q_begin + tile_groups - 1) / tile_groups;
     uint32_t grid = static_cast<uint32_t>(num_sms() * per_sm);
     if (grid > ntiles) grid = ntiles;
     if (grid == 0) return BDL_OK;
@@ -275,15 +276,19 @@ extern "C" int bdl_set_launch_config(int ctas_per_sm, int unroll) {
     return BDL_OK;
 }
 
-extern "C" int bdl_step(int variant, float* theta, const float* g, const float* theta0, float* v, float* m,
-                        float* s, float* buf, uint64_t n, const bdl_run* runs, uint32_t nruns,
-                        const bdl_scalars* sc, const bdl_noise* nz, void* stream) {
-    using namespace bdl;
+namespace bdl {
+
+// Update the float4 groups [q_begin, q_end) of the flat state; all pointers are the bases of the full buffers,
+// so Philox counters and the run table keep their absolute indexing (results do not depend on chunking).
+int step_range(int variant, float* theta, const float* g, const float* theta0, float* v, float* m, float* s, float* buf,
+               uint64_t n, uint64_t q_begin, uint64_t q_end, const bdl_run* runs, uint32_t nruns, const bdl_scalars* sc,
+               const bdl_noise* nz, cudaStream_t st) {
     BDL_REQUIRE(variant >= BDL_SGLD && variant <= BDL_ADAM_CSGHMC, BDL_ERR_INVALID, "bdl_step: unknown variant %d", variant);
-    if (n == 0) return BDL_OK;                      // empty state: nothing to do (pointers may be null)
+    if (n == 0 || q_begin >= q_end) return BDL_OK;   // empty state / empty range: nothing to do (pointers may be null)
     BDL_REQUIRE(theta && runs && sc && nz, BDL_ERR_INVALID, "bdl_step: null theta/runs/scalars/noise");
     BDL_REQUIRE(n % 4 == 0, BDL_ERR_INVALID, "bdl_step: n=%llu is not a multiple of 4", (unsigned long long)n);
     BDL_REQUIRE((n >> 2) < 0xFFFFFFFFull, BDL_ERR_INVALID, "bdl_step: n too large for 32-bit group index");
+    BDL_REQUIRE(q_end <= (n >> 2), BDL_ERR_INVALID, "bdl_step: range end beyond n");
     BDL_REQUIRE(nruns >= 1 && nruns <= BDL_MAX_RUNS, BDL_ERR_INVALID, "bdl_step: nruns=%u out of range", nruns);
     const bool adam = variant == BDL_ADAM_SGHMC || variant == BDL_ADAM_CSGHMC;
     const bool has_buf = (variant == BDL_SGLD || variant == BDL_ADAM_SGHMC) && sc->mu != 0.0f;
@@ -297,7 +302,8 @@ extern "C" int bdl_step(int variant, float* theta, const float* g, const float* 
 
     StepParams p{};
     p.theta = theta; p.g = g; p.theta0 = theta0; p.v = v; p.m = m; p.s = s; p.buf = buf;
-    p.xi = nz->xi_dev; p.runs = runs; p.nruns = nruns; p.n4 = static_cast<uint32_t>(n >> 2);
+    p.xi = nz->xi_dev; p.runs = runs; p.nruns = nruns;
+    p.n4 = static_cast<uint32_t>(q_end); p.q_begin = static_cast<uint32_t>(q_begin);
     for (int h = 0; h < 2; ++h) {
         p.lr[h] = sc->lr[h];
         p.neg_lr[h] = -sc->lr[h];
@@ -318,7 +324,6 @@ extern "C" int bdl_step(int variant, float* theta, const float* g, const float* 
     p.key.sub_lo = static_cast<uint32_t>(nz->subseq); p.key.sub_hi = static_cast<uint32_t>(nz->subseq >> 32);
 
     const bool philox = nz->xi_dev == nullptr;
-    cudaStream_t st = static_cast<cudaStream_t>(stream);
     const int d = sc->div_mode;
     switch (variant) {
         case BDL_SGLD:
@@ -333,4 +338,13 @@ extern "C" int bdl_step(int variant, float* theta, const float* g, const float* 
         default:
             return launch_nd<BDL_ADAM_CSGHMC, false>(p, philox, d, st);
     }
+}
+
+}  // namespace bdl
+
+extern "C" int bdl_step(int variant, float* theta, const float* g, const float* theta0, float* v, float* m,
+                        float* s, float* buf, uint64_t n, const bdl_run* runs, uint32_t nruns,
+                        const bdl_scalars* sc, const bdl_noise* nz, void* stream) {
+    return bdl::step_range(variant, theta, g, theta0, v, m, s, buf, n, 0, n >> 2, runs, nruns, sc, nz,
+                           static_cast<cudaStream_t>(stream));
 }

@@ -1,0 +1,205 @@
+"""Multi-GPU paths.  The reference is single-device; both paths are new surface.
+
+* Independent chains: one process per GPU (``torchrun``), distinct seeds, **no communication** -- nothing to do
+  here beyond ``chain_seed``.
+* Sample-sharded posterior-predictive ensemble: the S = cycles x nst posterior samples are dealt round-robin to the
+  ranks; every rank draws its samples with the counter-based Philox stream keyed by (evaluation, batch, cycle,
+  sample) -- so the draws do not depend on the rank count --, runs the backbone forward and accumulates
+  sum_s softmax(logits_s) per cycle.  One all-reduce (NCCL over NVLink; ``[C, N, K]`` fp32, 4.3 MB at Pets size)
+  combines the ranks; the log / GMM mixture / CE / calibration reductions follow, the calibration bins being
+  sharded by row with a second tiny all-reduce of the 3*M+2 bin statistics.
+"""
+import copy
+import time
+
+import numpy as np
+import torch
+
+from . import _lib, ops
+from .flat import adopt_parameters, alloc_flat
+
+
+def chain_seed(base_seed, rank):
+    """Seeds 42, 43, ... for chains 0, 1, ... (BASELINE.md cfg 4)."""
+    return int(base_seed) + int(rank)
+
+
+def shard_samples(n_components, nst, rank, world):
+    """Round-robin assignment of the flat sample index j = component * nst + s."""
+    return [(j // nst, j % nst) for j in range(n_components * nst) if j % world == rank]
+
+
+class CudaBackend:
+    """The product's kernels.  (Tests inject an oracle-backed stand-in to exercise the host logic under gloo on CPU.)"""
+    name = "cuda"
+
+    def draw(self, comp, out_flat, seed, subseq, div_mode):
+        ops.draw(comp["mean"], comp["second"], out_flat, comp["var_mode"], comp["scale"],
+                 ops.make_noise(seed=seed, subseq=subseq, stream_id=_lib.STREAM_DRAW), div_mode)
+
+    def probsum_accum(self, logits, prob_sum):
+        ops.probsum_accum(logits, prob_sum)
+
+    def probsum_finalize(self, prob_sum, out, n_samples, weight, mode):
+        ops.probsum_finalize(prob_sum, out, n_samples, weight, mode)
+
+    def ce_err(self, logits, y):
+        loss = torch.zeros(1, dtype=torch.float64, device=logits.device)
+        err = torch.zeros(1, dtype=torch.int32, device=logits.device)
+        for i in range(0, logits.shape[0], 4096):            # the kernel is a single CTA per call
+            ops.ce_err(logits[i:i + 4096].contiguous(), y[i:i + 4096].contiguous(), loss, err)
+        return loss, err
+
+    def calibrate(self, logits, labels, edges):
+        size, acc, conf, nll, near, _ = ops.calibrate(logits, labels, edges)
+        return torch.cat([size, acc, conf, nll, near.double()])
+
+
+def _pack_subseq(eval_id, batch, cycle, sample):
+    return ((eval_id & 0xFFFF) << 48) | ((batch & 0xFFFFFF) << 24) | ((cycle & 0xFF) << 16) | (sample & 0xFFFF)
+
+
+class ShardedEnsemble:
+    """components: list of dicts {cycle, mean, second, var_mode, scale, weight} (padded flat tensors on this rank's
+    device).  ``mixture=False`` (non-cyclical runners): exactly one component, logits = log mean_s softmax.
+    ``mixture=True``: weighted sum of per-cycle log-mean-softmax (the reference's log-space GMM, Appendix B.5)."""
+
+    def __init__(self, net, layout, components, nst, seed, *, mixture, eval_id=1, rank=0, world=1, group=None,
+                 div_mode=_lib.DIV_RECIP, backend=None):
+        if nst < 1:
+            raise ValueError("sample sharding needs nst >= 1")
+        self.layout, self.components, self.nst, self.seed = layout, components, int(nst), int(seed)
+        self.mixture, self.eval_id, self.rank, self.world, self.group = mixture, eval_id, rank, world, group
+        self.div_mode = div_mode
+        self.backend = backend or CudaBackend()
+        self.net = copy.deepcopy(net).eval()
+        dev = next(net.parameters()).device
+        self.flat = alloc_flat(layout.n_padded, dev) if dev.type == "cuda" else torch.zeros(layout.n_padded)
+        adopt_parameters(self.net, layout, self.flat)
+        self.mine = shard_samples(len(components), self.nst, rank, world)
+
+    def _all_reduce(self, t):
+        if self.world > 1:
+            import torch.distributed as dist
+            dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.group)
+        return t
+
+    def evaluate(self, loader):
+        """-> (loss, err, targets[N] int64 numpy, logits[N,K] f32 numpy); identical on every rank."""
+        dev = self.flat.device
+        C = len(self.components)
+        sums, ys = [], []
+        with torch.no_grad():
+            for b_idx, (x, y) in enumerate(loader):
+                x, y = x.to(dev, non_blocking=True), y.to(dev, non_blocking=True)
+                acc = None
+                for (ci, s) in self.mine:
+                    comp = self.components[ci]
+                    self.backend.draw(comp, self.flat, self.seed, _pack_subseq(self.eval_id, b_idx, comp["cycle"], s),
+                                      self.div_mode)
+                    out = self.net(x).float().contiguous()
+                    if acc is None:
+                        acc = torch.zeros((C,) + tuple(out.shape), dtype=torch.float32, device=dev)
+                    self.backend.probsum_accum(out, acc[ci])
+                if acc is None:                               # more ranks than samples: contribute zeros
+                    with torch.no_grad():
+                        k = self.net(x).shape[1]
+                    acc = torch.zeros((C, x.shape[0], k), dtype=torch.float32, device=dev)
+                sums.append(acc)
+                ys.append(y)
+        prob = torch.cat(sums, dim=1).contiguous()           # [C, N, K]
+        self._all_reduce(prob)                               # the path's single data exchange
+        y = torch.cat(ys)
+        N, K = prob.shape[1], prob.shape[2]
+        logits = torch.empty(N, K, dtype=torch.float32, device=dev)
+        for ci, comp in enumerate(self.components):
+            if self.mixture:
+                self.backend.probsum_finalize(prob[ci], logits, self.nst, comp["weight"], 1 if ci == 0 else 2)
+            else:
+                self.backend.probsum_finalize(prob[ci], logits, self.nst, 1.0, 0)
+        loss, err = self.backend.ce_err(logits, y)
+        return loss.item() / N, err.item() / N, y.cpu().numpy(), logits.cpu().numpy()
+
+    def calibrate(self, targets, logits, num_bins):
+        """ECE / MCE / NLL with the rows of ``logits`` sharded over the ranks -> (ece, mce, nll)."""
+        from .calibration import bin_edges
+        dev = self.flat.device
+        lg = torch.as_tensor(logits, dtype=torch.float32)[self.rank::self.world].contiguous().to(dev)
+        lb = torch.as_tensor(targets, dtype=torch.int64)[self.rank::self.world].contiguous().to(dev)
+        edges = torch.from_numpy(bin_edges(num_bins)).to(dev)
+        M = num_bins
+        if lg.shape[0] > 0:
+            stats = self.backend.calibrate(lg, lb, edges)
+        else:
+            stats = torch.zeros(3 * M + 2, dtype=torch.float64, device=dev)
+        self._all_reduce(stats)
+        h = stats.cpu().numpy()
+        sizes, acc_sum, conf_sum, nll_sum = h[:M], h[M:2 * M], h[2 * M:3 * M], h[3 * M]
+        nz = sizes > 0
+        accs, confs = np.zeros(M), np.zeros(M)
+        accs[nz], confs[nz] = acc_sum[nz] / sizes[nz], conf_sum[nz] / sizes[nz]
+        ece = (np.abs(accs - confs) * (sizes / sizes.sum())).sum()
+        mce = np.abs(accs - confs).max()
+        return ece, mce, nll_sum / len(targets)
+
+
+def components_from_runner(runner):
+    """Build the component list of a trained drop-in Runner (burn-in or cyclical)."""
+    if hasattr(runner, "_cyc1"):
+        w = runner.calculate_gmm_weights()
+        comps = []
+        for c in runner._cyc1:
+            if w.get(c, 0.0) < 1e-10:
+                continue
+            second, var_mode, scale = runner._cycle_variance_spec(c)
+            comps.append(dict(cycle=c, mean=runner._cyc1[c], second=second, var_mode=var_mode, scale=scale, weight=w.get(c, 0.0)))
+        return comps, True
+    return [dict(cycle=0, mean=runner._mom1, second=runner._mom2, var_mode=ops.VAR_FROM_MOMENTS,
+                 scale=runner._variance_ratio(), weight=1.0)], False
+
+
+def bench_sharded_ensemble(device, rank, world, rows=512, batch=64, cycles=8, nst=5, backbone="resnet101", num_bins=15):
+    """BASELINE.json configs[4]: ResNet-101 cSGLD 8 cycles x nst 5 = 40-sample ensemble + ECE/MCE/NLL, samples sharded over
+    the ranks.  Returns a dict for bench.py's ``ensemble`` key (preds/s = rows * samples / wall time, max over ranks)."""
+    from . import shapes
+    from .flat import FlatLayout
+    torch.manual_seed(7)                                     # same weights and per-cycle statistics on every rank
+    with torch.device(device):
+        net = shapes.create_backbone(backbone, 37)
+    lay = FlatLayout.from_module(net)
+    theta = alloc_flat(lay.n_padded, device)
+    adopt_parameters(net, lay, theta)
+    gen = torch.Generator(device=device).manual_seed(11)
+    comps = []
+    for c in range(1, cycles + 1):
+        mean = theta + 1e-3 * torch.randn(lay.n_padded, device=device, generator=gen)
+        second = mean * mean + 1e-6 * torch.rand(lay.n_padded, device=device, generator=gen)
+        comps.append(dict(cycle=c, mean=mean, second=second, var_mode=ops.VAR_FROM_MOMENTS, scale=nst / (nst - 1.0),
+                          weight=1.0 / cycles))
+    rows = max(batch, rows // batch * batch)
+    x_host = torch.randn(batch, 3, 224, 224).pin_memory()
+    y_all = torch.randint(0, 37, (rows,), generator=torch.Generator().manual_seed(3))
+    loader = [(x_host, y_all[i:i + batch].pin_memory()) for i in range(0, rows, batch)]
+    ens = ShardedEnsemble(net, lay, comps, nst, seed=42, mixture=True, rank=rank, world=world)
+    ens.evaluate(loader[:1])                                 # warm-up (cuDNN autotune, allocator)
+    if world > 1:
+        import torch.distributed as dist
+        dist.barrier()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    loss, err, targets, logits = ens.evaluate(loader)
+    ece, mce, nll = ens.calibrate(targets, logits, num_bins)
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    if world > 1:
+        import torch.distributed as dist
+        t = torch.tensor([dt], dtype=torch.float64, device=device)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dt = t.item()
+    S = cycles * nst
+    return {"metric": "ensemble preds/s (ResNet-101 cSGLD 40-sample posterior-predictive ensemble + ECE/MCE/NLL)",
+            "value": rows * S / dt, "unit": "preds/s", "rows": rows, "samples": S, "seconds": dt, "n_gpus": world,
+            "sharding": "by sample, round-robin; one all-reduce of [C,N,K] prob sums + one of the bin statistics",
+            "ece": float(ece), "nll": float(nll), "loss": float(loss),
+            "note": "per-sample cost = 1 draw kernel (12 B/param) + PyTorch fp32 forward of 64 images; samples re-drawn "
+                    "for every batch as the reference does (Appendix B.6)"}

@@ -162,7 +162,7 @@ class _EvalNet:
     def load(self, flat_values):
         self.flat.copy_(flat_values)
 
-    def draw(self, mean, second, var_mode, scale, noise_mode, seed, subseq, div_mode):
+    def draw(self, mean, second, var_mode, scale, noise_mode, seed, subseq, div_mode, center=None):
         if noise_mode == "philox":
             nz = ops.make_noise(seed=seed, subseq=subseq, stream_id=_lib.STREAM_DRAW)
         else:                                             # parity mode: torch.randn_like per tensor (sgld.py:294)
@@ -172,7 +172,7 @@ class _EvalNet:
             for view in self._xi_views:
                 view.copy_(torch.randn_like(view))
             nz = ops.make_noise(xi=self._xi)
-        ops.draw(mean, second, self.flat, var_mode, scale, nz, div_mode)
+        ops.draw(mean, second, self.flat, var_mode, scale, nz, div_mode, center=center)
 
 
 def _pack_subseq(eval_id, batch, cycle, sample):
@@ -762,9 +762,11 @@ class CyclicalRunner(_RunnerCommon):
         ch = self._chain()
         dev = self.args.device
         c = self.current_cycle
-        spec = None
+        spec, center = None, None
         if self.LIKELIHOOD_MEAN == "theta":
-            mean = ch.theta
+            # centre = current theta, variance = the cycle's ratio*(mom2 - mom1^2)   (csgld.py:518-528, 541)
+            center = ch.theta
+            mean = self._cyc1.get(c)
             if c in self._cyc2 and c in self._cyc1 and self.samples_per_cycle.get(c, 0) > 1:
                 spec = self._cycle_variance_spec(c)
         else:
@@ -783,7 +785,7 @@ class CyclicalRunner(_RunnerCommon):
             if self.nst > 0 and spec is not None:
                 second, var_mode, scale = spec
                 ev.draw(mean, second, var_mode, scale, self.noise_mode, self.seed,
-                        _pack_subseq(self._eval_calls, 0xFFFFFF, c, sample_idx), self.div_mode)
+                        _pack_subseq(self._eval_calls, 0xFFFFFF, c, sample_idx), self.div_mode, center=center)
             else:
                 ev.load(ch.theta)                        # net_sample = deepcopy(self.net), no perturbation
             avg_loss, _ = self._point_estimate(train_loader, ev.net)

@@ -155,8 +155,10 @@ def capture_ring(theta, ring, slot):
 VAR_FROM_MOMENTS, VAR_FROM_WELFORD, VAR_TINY, VAR_GIVEN = 0, 1, 2, 3
 
 
-def draw(mean, second, out, var_mode, scale, noise, div_mode=DIV_RECIP):
-    rc = _lib.load().bdl_draw(_ptr(mean, "mean"), _ptr(second, "second", allow_none=True), _ptr(out, "out"),
+def draw(mean, second, out, var_mode, scale, noise, div_mode=DIV_RECIP, center=None):
+    """out = (center or mean) + sqrt(var(mean, second)) * eps   (see bdl_draw)."""
+    rc = _lib.load().bdl_draw(_ptr(mean, "mean"), _ptr(second, "second", allow_none=True),
+                              _ptr(center, "center", allow_none=True), _ptr(out, "out"),
                               mean.numel(), int(var_mode), float(scale), div_mode, C.byref(noise), _stream())
     _lib.check(rc, "bdl_draw")
 
@@ -209,3 +211,43 @@ def calibrate(logits, labels, edges, temperature=1.0, use_f64=False, want_binned
         near.data_ptr(), None if binned is None else binned.data_ptr(), _stream())
     _lib.check(rc, "bdl_calibrate")
     return stats[:M], stats[M:2 * M], stats[2 * M:3 * M], stats[3 * M:], near, binned
+
+
+class HostChain:
+    """Python handle of the host-buffer chain API (bdl_chain_*): sampler state resident in HBM, gradient in / theta
+    out through pinned host tensors.  See include/bdl.h."""
+
+    def __init__(self, n, variant, with_sgd_momentum=False, chunk_elems=0):
+        self._h = C.c_void_p()
+        self.n, self.variant = int(n), int(variant)
+        _lib.check(_lib.load().bdl_chain_create(self.n, self.variant, int(with_sgd_momentum), int(chunk_elems),
+                                                C.byref(self._h)), "bdl_chain_create")
+
+    def close(self):
+        if self._h:
+            _lib.load().bdl_chain_destroy(self._h)
+            self._h = C.c_void_p()
+
+    __del__ = close
+
+    @staticmethod
+    def _host(t, n):
+        if not (isinstance(t, torch.Tensor) and t.device.type == "cpu" and t.dtype == torch.float32 and t.is_contiguous()
+                and t.numel() == n):
+            raise BdlError("expected a contiguous fp32 CPU tensor of the chain's length")
+        return t.data_ptr()
+
+    def upload(self, which, host):
+        _lib.check(_lib.load().bdl_chain_upload(self._h, int(which), self._host(host, self.n)), "bdl_chain_upload")
+
+    def download(self, which, host):
+        _lib.check(_lib.load().bdl_chain_download(self._h, int(which), self._host(host, self.n)), "bdl_chain_download")
+        return host
+
+    def step_host(self, g_host, theta_out_host, run_array, scalars, noise):
+        for t in (g_host, theta_out_host):
+            if not t.is_pinned():
+                raise BdlError("bdl_chain_step_host needs pinned host tensors (tensor.pin_memory())")
+        _lib.check(_lib.load().bdl_chain_step_host(self._h, self._host(g_host, self.n), self._host(theta_out_host, self.n),
+                                                   run_array, len(run_array), C.byref(scalars), C.byref(noise)),
+                   "bdl_chain_step_host")

@@ -1,0 +1,473 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the B200-native BayesDLL sampler hot path.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
+        bench.py --gpus N --steps K --warmup W
+
+Workload (BASELINE.json configs[2], the configuration the metric is quoted on): fused SGHMC update of a ViT-L/32
+chain (37-class head, n = 305 548 325 fp32 parameters, net0 prior mean, in-kernel Philox noise), hyper-parameters
+``prior_sig=1.0,Ninflate=1e3,nd=1.0,momentum_decay=0.18,bias=informative`` with lr 1e-4 / lr_head 1e-2, ND=1840.
+A "step" is one pass of the fused update over the whole flat state (theta, g, theta0, v resident in HBM; 4.9 GB of
+inputs per step >> 126 MB L2, so no L2 flush is needed between iterations).  One independent chain per GPU
+(weak scaling, no collective on the data path -- SURVEY.md section 8e).
+
+value       params/s over all GPUs, state resident in HBM, CUDA events on the launching stream, max over ranks.
+e2e         the same update through the host-buffer C ABI (bdl_chain_step_host): the gradient comes from pinned HOST
+            memory and the new theta returns to pinned HOST memory every step (4 B/param each way, inside the timed
+            region); theta0 / momentum stay resident.  This is what a CPU-resident caller of the reference binds.
+roofline    HBM-bound; achieved = 24 B/param * n / average kernel duration; peak = MEASURED_PEAKS.json hbm_gbs.
+cpu_baseline  the fused C/OpenMP port of the reference path (oracle/bdl_oracle.c) on the host cores, rank 0, N=1.
+train_step  (extra) the full user call Model.forward on a real torchvision ViT-L/32, batch 64: x,y from pinned host,
+            PyTorch fwd/bwd, fused update reading autograd's gradients in place, loss.item().
+ensemble    (extra) sample-sharded 40-sample ResNet-101 posterior-predictive ensemble + ECE, preds/s.
+
+--impl reference times the CPU port on the same config / metric / unit (rank 0 only).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+BYTES_PER_PARAM = 24          # SGHMC: R theta,g,theta0,v ; W v,theta   
+HP = dict(prior_sig=1.0, Ninflate=1e3, nd=1.0, alpha=0.18, lr_body=1e-4, lr_head=1e-2, ND=1840)
+METRIC = "sampler step params/s (ViT-L/32 fused SGHMC update)"
+WORKLOAD = "ViT-L/32 (K=37, n=305548325) SGHMC fused step, net0 prior mean, in-kernel Philox; BASELINE.json configs[2]"
+
+
+def env_int(name, default):
+    return int(os.environ.get(name, default))
+
+
+def measured_peak():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def recorded_traffic():
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu capture, or None."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+            return json.load(f).get("sghmc_step_dram_bytes_per_launch")
+    except Exception:
+        return None
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled while the GPU is under load (B200_PROFILING.md recipe)."""
+    FIELDS = ("timestamp,index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+              "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.rows, self.proc, self.gpu = [], None, gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.gpu}", f"--query-gpu={self.FIELDS}",
+                                          "--format=csv,noheader,nounits", "-lms", "50"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.time(), line.strip()))
+
+    def stop(self):
+        if self.proc is not None:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=5)
+            except Exception:
+                self.proc.kill()
+
+    def summary(self, t0, t1):
+        sm, mx, reasons = [], [], set()
+        for ts, line in self.rows:
+            parts = [p.strip() for p in line.split(",")]
+            if len(parts) < 9:
+                continue
+            try:
+                clk, cmax = float(parts[2]), float(parts[3])
+            except ValueError:
+                continue
+            if t0 - 0.05 <= ts <= t1 + 0.05:
+                sm.append(clk)
+                mx.append(cmax)
+                for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), parts[5:9]):
+                    if val.lower().startswith("active"):
+                        reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------------------
+def build_layout():
+    from bayesdll_b200 import shapes
+    from bayesdll_b200.flat import FlatLayout
+    named, readout = shapes.named_shapes("vit_l_32", 37)
+    return FlatLayout(named, readout)
+
+
+def make_scalars(variant):
+    from bayesdll_b200 import _lib, ops
+    return ops.make_scalars(variant, lr_body=HP["lr_body"], lr_head=HP["lr_head"], ND=HP["ND"], Ninflate=HP["Ninflate"],
+                            prior_sig=HP["prior_sig"], nd=HP["nd"], alpha=HP["alpha"], div_mode=_lib.DIV_RECIP)
+
+
+def synth_state(n, device, seed):
+    """Random-init weights of the named shapes, synthetic gradients g ~ N(0, 1e-2^2)."""
+    gen = torch.Generator(device=device).manual_seed(seed)
+    theta = torch.randn(n, device=device, generator=gen) * 0.02
+    theta0 = torch.randn(n, device=device, generator=gen) * 0.02
+    g = torch.randn(n, device=device, generator=gen) * 0.01
+    v = torch.zeros(n, device=device)
+    return theta, g, theta0, v
+
+
+def allmax(x, world, device):
+    if world == 1:
+        return x
+    import torch.distributed as dist
+    t = torch.tensor([x], dtype=torch.float64, device=device)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return t.item()
+
+
+def barrier(world):
+    if world > 1:
+        import torch.distributed as dist
+        dist.barrier()
+
+
+# ------------------------------------------------------------------------------------------------------------
+def run_ours(args):
+    from bayesdll_b200 import _lib, ops
+    rank, local_rank, world = env_int("RANK", 0), env_int("LOCAL_RANK", 0), env_int("WORLD_SIZE", 1)
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local_rank)
+    device = torch.device("cuda", local_rank)
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=device)
+    _lib.load()
+    lay = build_layout()
+    n, n_dense = lay.n_padded, lay.n_dense
+    theta, g, theta0, v = synth_state(n, device, 42 + rank)
+    runs_dev, nruns = ops.upload_runs(lay.run_table("informative"), device)
+    sc = make_scalars(_lib.SGHMC)
+    seed = 42 + rank
+    K, W = args.steps, max(args.warmup, 3)
+
+    def step(i):
+        ops.step(_lib.SGHMC, theta, g, theta0, v, None, None, None, runs_dev, nruns, sc,
+                 ops.make_noise(seed=seed, subseq=i, stream_id=_lib.STREAM_STEP))
+
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    for i in range(W):
+        step(i)
+    barrier(world)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t_region0 = time.time()
+    e0.record()
+    for i in range(K):
+        step(W + i)
+    e1.record()
+    torch.cuda.synchronize()
+    t_region1 = time.time()
+    barrier(world)
+    ms_total = allmax(e0.elapsed_time(e1), world, device)
+    ms_per_step = ms_total / K
+    value = world * n_dense * K / (ms_total * 1e-3)
+    # keep the sampler's region long enough for >= a few nvidia-smi samples
+    t_extra = time.time()
+    while rank == 0 and time.time() - t_extra < 0.4:
+        step(0)
+        torch.cuda.synchronize()
+    t_region1b = time.time()
+    assert torch.isfinite(theta[:: max(1, n // 4096)]).all(), "state diverged"
+
+    # ---- roofline of the dominant (only) kernel -------------------------------------------------
+    peak, peak_kind = measured_peak()
+    kernel_ms = e0.elapsed_time(e1) / K                      # this rank's average launch duration
+    achieved = BYTES_PER_PARAM * n_dense / (kernel_ms * 1e-3) / 1e9
+    roofline = {"bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
+                "frac": round(achieved / peak, 4), "traffic": recorded_traffic(), "peak_source": peak_kind,
+                "frac_of_nominal_8TBps": round(achieved / 8000.0, 4), "kernel": "bdl::step_kernel<SGHMC,philox,recip,U=2>",
+                "algorithmic_bytes_per_launch": BYTES_PER_PARAM * n_dense, "kernel_ms": round(kernel_ms, 4)}
+
+    # ---- e2e through the host-buffer C ABI ----------------------------------------------------------
+    e2e = None
+    if not args.no_e2e:
+        tab = lay.run_table("informative")
+        chain = ops.HostChain(n, _lib.SGHMC)
+        stage = torch.empty(n, dtype=torch.float32).pin_memory()
+        stage.copy_(theta)
+        chain.upload(_lib.BUF_THETA, stage)
+        stage.copy_(theta0)
+        chain.upload(_lib.BUF_THETA0, stage)
+        g_host = stage                                       # pinned host gradient (synthetic)
+        g_host.copy_(g)
+        theta_host = torch.empty(n, dtype=torch.float32).pin_memory()
+        Ke = max(3, min(K, args.e2e_steps))
+        for i in range(2):
+            chain.step_host(g_host, theta_host, tab, sc, ops.make_noise(seed=seed, subseq=i))
+        barrier(world)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for i in range(Ke):
+            chain.step_host(g_host, theta_host, tab, sc, ops.make_noise(seed=seed, subseq=2 + i))
+        torch.cuda.synchronize()
+        dt = allmax(time.perf_counter() - t0, world, device)
+        assert np.isfinite(theta_host[:1024].numpy()).all()
+        e2e = {"value": world * n_dense * Ke / dt, "unit": "params/s", "h2d_bytes_per_step": 4 * n, "d2h_bytes_per_step": 4 * n,
+               "steps": Ke, "ms_per_step": dt / Ke * 1e3,
+               "api": "bdl_chain_step_host (include/bdl.h): pinned host gradient in, pinned host theta out, "
+                      "theta0/momentum resident in HBM, chunk-pipelined H2D | fused step | D2H"}
+        chain.close()
+        del stage, theta_host, g_host
+    t_load_end = time.time()
+    if rank == 0:
+        sampler.stop()
+    clocks = sampler.summary(t_region0, t_region1b) if rank == 0 else None
+
+    # ---- extras --------------------------------------------------------------------------------------------
+    extras = {}
+    if not args.no_train_step:
+        del theta, g, theta0, v
+        torch.cuda.empty_cache()
+        extras["train_step"] = train_step_extra(device, rank, world)
+    if not args.no_ensemble:
+        torch.cuda.empty_cache()
+        extras["ensemble"] = ensemble_extra(device, rank, world, args)
+    cpu_baseline = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cpu_baseline = cpu_port_rate(lay, seconds=args.cpu_seconds, with_eager=True)
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": "params/s", "n_gpus": world, "steps": K, "warmup": W,
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic (random-init weights of the named shapes, g ~ N(0,1e-2^2))",
+            "config": {"workload": WORKLOAD, "hparams": "prior_sig=1.0,Ninflate=1e3,nd=1.0,momentum_decay=0.18,bias=informative",
+                       "lr": HP["lr_body"], "lr_head": HP["lr_head"], "ND": HP["ND"], "params_per_chain": n_dense,
+                       "chains": world, "parallelism": f"{world} independent chain(s), one per GPU, no data-path collective",
+                       "l2": "inputs (4.9 GB per step) larger than L2 (126 MB); no flush needed",
+                       "noise": "in-kernel Philox4x32-10 + Box-Muller", "division": "reciprocal (reference-on-CUDA semantics)"},
+            "hbm_gbs": achieved * 1.0, "roofline": roofline, "e2e": e2e, "gpu_launches": K, "clocks": clocks,
+            "cpu_baseline": cpu_baseline,
+        }
+        line.update(extras)
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        import torch.distributed as dist
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+# ------------------------------------------------------------------------------------------------------------
+def train_step_extra(device, rank, world, steps=6, batch=64):
+    """The call a user of the drop-in makes: Model.forward(x, y, net, net0, criterion, lrs, Ninflate, nd)."""
+    import argparse as ap
+    import logging
+    from bayesdll_b200 import shapes
+    from bayesdll_b200.methods import sghmc
+    torch.manual_seed(42 + rank)
+    with torch.device(device):
+        net = shapes.create_backbone("vit_l_32", 37)
+        net0 = shapes.create_backbone("vit_l_32", 37)
+    a = ap.Namespace(device=device, ND=HP["ND"], lr=HP["lr_body"], lr_head=HP["lr_head"], momentum=0.5, epochs=1,
+                     pretrained="synthetic", num_classes=37, ece_num_bins=15, test_eval_freq=1, log_dir=tempfile.gettempdir(),
+                     seed=42 + rank,
+                     hparams=dict(prior_sig="1.0", Ninflate="1e3", nd="1.0", momentum_decay="0.18", burnin="5", thin="1",
+                                  bias="informative", nst="5"))
+    lg = logging.getLogger("bench")
+    lg.addHandler(logging.NullHandler())
+    runner = sghmc.Runner(net, net0, a, lg)
+    runner.net.train()
+    x_host = torch.randn(batch, 3, 224, 224).pin_memory()
+    y_host = torch.randint(0, 37, (batch,)).pin_memory()
+    lrs = [pg["lr"] for pg in runner.optimizer.param_groups]
+
+    def one():
+        x, y = x_host.to(device, non_blocking=True), y_host.to(device, non_blocking=True)
+        loss, _ = runner.model(x, y, runner.net, runner.net0, runner.criterion, lrs, runner.Ninflate, runner.nd)
+        return loss
+    for _ in range(3):
+        one()
+    barrier(world)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        loss = one()
+    torch.cuda.synchronize()
+    dt = allmax(time.perf_counter() - t0, world, device)
+    n = runner.model.chain.layout.n_dense
+    res = {"value": world * n * steps / dt, "unit": "params/s", "ms_per_step": dt / steps * 1e3, "steps": steps,
+           "images_per_s": world * batch * steps / dt, "h2d_bytes_per_step": x_host.numel() * 4 + y_host.numel() * 8,
+           "d2h_bytes_per_step": 4, "last_loss": loss,
+           "api": "bayesdll_b200.methods.sghmc.Model.forward on torchvision vit_l_32, batch 64, fp32 fwd/bwd in PyTorch"}
+    del runner, net, net0
+    return res
+
+
+def ensemble_extra(device, rank, world, args):
+    from bayesdll_b200 import dist as bdist
+    return bdist.bench_sharded_ensemble(device, rank, world, rows=args.ensemble_rows, batch=64, cycles=8, nst=5)
+
+
+# ------------------------------------------------------------------------------------------------------------
+def cpu_port_rate(lay, seconds=15.0, with_eager=False, n_limit=None, steps=None, warmup=1):
+    """Time the fused C/OpenMP port of the reference path on the host cores (bounded sample)."""
+    import ctypes as C
+    from bayesdll_b200 import _lib
+    from oracle import c_oracle
+    c_oracle.build()
+    cores = os.cpu_count()
+    n_full = lay.n_padded
+    rng = np.random.default_rng(0)
+
+    def alloc(n):
+        th = torch.randn(n).mul_(0.02).numpy()
+        g = torch.randn(n).mul_(0.01).numpy()
+        th0 = torch.randn(n).mul_(0.02).numpy()
+        v = np.zeros(n, np.float32)
+        return th, g, th0, v
+
+    def table(n):
+        tab = (_lib.Run * 1)()
+        tab[0].begin, tab[0].end, tab[0].valid_end, tab[0].cls = 0, n, n, _lib.CLS_PRIOR
+        return tab
+    sc = make_scalars(_lib.SGHMC)
+    nz = _lib.Noise()
+    nz.seed, nz.stream_id = 42, _lib.STREAM_STEP
+    # probe on 16 Mi params to size the sample
+    n_probe = min(n_full, 16 << 20)
+    st = alloc(n_probe)
+    tab = table(n_probe)
+    c_oracle.step(_lib.SGHMC, st[0], st[1], st[2], st[3], None, None, None, tab, sc, nz)
+    t0 = time.perf_counter()
+    c_oracle.step(_lib.SGHMC, st[0], st[1], st[2], st[3], None, None, None, tab, sc, nz)
+    rate = n_probe / (time.perf_counter() - t0)
+    if steps is None:
+        steps = 3
+    n = n_limit or n_full
+    n = int(min(n, max(8 << 20, rate * seconds / (steps + warmup)))) // 4 * 4
+    if n != n_probe:
+        st = alloc(n)
+        tab = table(n)
+    for i in range(warmup):
+        nz.subseq = i
+        c_oracle.step(_lib.SGHMC, st[0], st[1], st[2], st[3], None, None, None, tab, sc, nz)
+    t0 = time.perf_counter()
+    for i in range(steps):
+        nz.subseq = warmup + i
+        c_oracle.step(_lib.SGHMC, st[0], st[1], st[2], st[3], None, None, None, tab, sc, nz)
+    dt = time.perf_counter() - t0
+    out = {"value": n * steps / dt, "unit": "params/s", "cores": cores, "kind": "port",
+           "sample": f"{steps} fused SGHMC steps over {n} of {lay.n_dense} ViT-L/32 parameters (oracle/bdl_oracle.c, "
+                     f"OpenMP, in-loop Philox+Box-Muller)", "ms_per_step": dt / steps * 1e3, "steps": steps, "n": n}
+    if with_eager:
+        out["reference_structure_eager"] = eager_rate(lay, cores)
+    return out
+
+
+def eager_rate(lay, cores, max_params=64 << 20):
+    """What the reference's own structure (per-tensor torch eager loop + SGD.step) achieves on these cores."""
+    from oracle import eager_port
+    torch.set_num_threads(cores)
+    segs, tot = [], 0
+    for s in lay.segments:
+        segs.append(s)
+        tot += s.numel
+        if tot >= max_params:
+            break
+    names = [s.name for s in segs]
+    params = [torch.randn(s.shape) * 0.02 for s in segs]
+    params0 = [torch.randn(s.shape) * 0.02 for s in segs]
+    grads = [torch.randn(s.shape) * 0.01 for s in segs]
+    mom = [torch.zeros(s.shape) for s in segs]
+    kw = dict(lr_body=HP["lr_body"], lr_head=HP["lr_head"], ND=HP["ND"], Ninflate=HP["Ninflate"], prior_sig=HP["prior_sig"],
+              nd=HP["nd"], alpha=HP["alpha"])
+    eager_port.sghmc_step_eager(params, grads, params0, mom, names, lay.readout_name, **kw)
+    t0 = time.perf_counter()
+    reps = 2
+    for _ in range(reps):
+        eager_port.sghmc_step_eager(params, grads, params0, mom, names, lay.readout_name, **kw)
+    dt = time.perf_counter() - t0
+    return {"value": tot * reps / dt, "unit": "params/s", "cores": cores, "kind": "port",
+            "sample": f"{reps} per-tensor torch-eager SGHMC steps over the first {len(segs)} ViT-L/32 tensors ({tot} params), "
+                      f"oracle/eager_port.py restating methods/sghmc.py:482-510 + SGD.step"}
+
+
+def run_reference(args):
+    """The reference arm: the CPU implementation of the path (fused C port; the reference itself is Python and cannot
+    travel to the GPU box).  Rank 0 only."""
+    rank = env_int("RANK", 0)
+    if rank != 0:
+        return
+    lay = build_layout()
+    K, W = args.steps, max(args.warmup, 1)
+    res = cpu_port_rate(lay, seconds=args.ref_seconds, steps=K, warmup=W)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": res["value"], "unit": "params/s", "n_gpus": env_int("WORLD_SIZE", 1),
+        "steps": K, "warmup": W, "ms_per_step": res["ms_per_step"], "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "sample": res["sample"]},
+        "cpu_baseline": {"value": res["value"], "unit": "params/s", "cores": res["cores"], "kind": "port", "sample": res["sample"]},
+        "e2e": {"value": res["value"], "unit": "params/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=300)
+    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--e2e-steps", type=int, default=10)
+    ap.add_argument("--cpu-seconds", type=float, default=15.0)
+    ap.add_argument("--ref-seconds", type=float, default=60.0)
+    ap.add_argument("--ensemble-rows", type=int, default=512)
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-train-step", action="store_true")
+    ap.add_argument("--no-ensemble", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    world = env_int("WORLD_SIZE", 1)
+    if args.gpus != world and args.impl == "ours" and world == 1 and args.gpus > 1:
+        # convenience: `python bench.py --gpus N` re-launches itself under torchrun
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}",
+               "--master-addr", "127.0.0.1", "--master-port", str(29500 + os.getpid() % 1000), os.path.abspath(__file__)] + sys.argv[1:]
+        raise SystemExit(subprocess.call(cmd))
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -155,9 +155,12 @@ int bdl_capture_ring(const float* theta_dev, float* ring_dev, uint64_t slot, uin
  *   var_mode 0: var = max(scale * (second - mean^2), 1e-12)   scale = fp32(ratio)  (sgld.py:338-348)
  *   var_mode 1: var = max(second / scale, 1e-12)              scale = fp32(n-1)    (csghmc.py:451-459)
  *   var_mode 2: var = 1e-12                                   (csghmc.py:458)
- *   var_mode 3: second already holds the variance */
-int bdl_draw(const float* mean_dev, const float* second_dev, float* theta_out_dev, uint64_t n, int var_mode,
-             float scale, int div_mode, const bdl_noise* noise, void* stream);
+ *   var_mode 3: second already holds the variance
+ *   center_dev (optional): draw around this vector instead of `mean` while the variance still comes from
+ *   (mean, second) -- cSGLD's cycle likelihoods perturb the *current* theta with the cycle's variance
+ *   (methods/csgld.py:518-541).  NULL -> centre = mean. */
+int bdl_draw(const float* mean_dev, const float* second_dev, const float* center_dev, float* theta_out_dev, uint64_t n,
+             int var_mode, float scale, int div_mode, const bdl_noise* noise, void* stream);
 
 /* (a10) Ensemble average for one test batch (methods/sgld.py:283-305):
  *   logits_all [B,K,S] fp32 (contiguous, S fastest, i.e. torch.stack(outs, 2)) ->
@@ -194,6 +197,27 @@ int bdl_calibrate(const float* logits_dev, const int64_t* labels_dev, uint64_t N
                   int use_f64, const double* edges_dev, uint32_t M, double* bin_size_dev, double* acc_sum_dev,
                   double* conf_sum_dev, double* nll_sum_dev, unsigned long long* near_edge_dev,
                   int32_t* binned_dev, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Host-buffer form: a chain whose state is resident in HBM, stepped from HOST memory.
+ * (The one place the library owns device memory.)  This is what a CPU-resident caller of the reference's
+ * update loop binds: per step only the gradient (in) and theta (out) cross PCIe; theta0, momentum, Adam
+ * moments and the SGD buffer never leave the device.  Pinned host buffers are required for the copies to be
+ * asynchronous (cudaHostAlloc / torch pin_memory()).
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct bdl_chain bdl_chain;
+enum { BDL_BUF_THETA = 0, BDL_BUF_THETA0 = 1, BDL_BUF_V = 2, BDL_BUF_M = 3, BDL_BUF_S = 4, BDL_BUF_SGD = 5 };
+
+/* n: padded-flat length; chunk_elems: pipeline chunk (0 = default 16 Mi elements). */
+int bdl_chain_create(uint64_t n, int variant, int with_sgd_momentum, uint64_t chunk_elems, bdl_chain** out);
+int bdl_chain_destroy(bdl_chain* chain);
+int bdl_chain_upload(bdl_chain* chain, int which, const float* host);     /* synchronous */
+int bdl_chain_download(bdl_chain* chain, int which, float* host);         /* synchronous */
+int bdl_chain_device_ptr(bdl_chain* chain, int which, float** out);       /* which == 6: gradient staging buffer */
+/* One sampler update: g_host (n floats, in) -> theta_out_host (n floats, out).  runs_host is a HOST array without
+ * per-run gradient pointers; in-kernel Philox noise only.  Returns when theta_out_host is complete. */
+int bdl_chain_step_host(bdl_chain* chain, const float* g_host, float* theta_out_host, const bdl_run* runs_host,
+                        uint32_t nruns, const bdl_scalars* scalars, const bdl_noise* noise);
 
 #ifdef __cplusplus
 }

@@ -182,8 +182,8 @@ int bdl_oracle_step(int variant, float* theta, const float* g, const float* thet
 }
 
 /* posterior draw, same contract as bdl_draw() */
-int bdl_oracle_draw(const float* mean, const float* second, float* out, uint64_t n, int var_mode, float scale,
-                    int div_mode, const bdl_noise* nz) {
+int bdl_oracle_draw(const float* mean, const float* second, const float* center, float* out, uint64_t n, int var_mode,
+                    float scale, int div_mode, const bdl_noise* nz) {
     if (n % 4) return BDL_ERR_INVALID;
     const float* xi = (const float*)(uintptr_t)nz->xi_dev;
     const float inv = 1.0f / scale;
@@ -199,7 +199,7 @@ int bdl_oracle_draw(const float* mean, const float* second, float* out, uint64_t
             else if (var_mode == 1) var = fmaxf(div_s(second[i], scale, inv, div_mode), 1e-12f);
             else if (var_mode == 2) var = 1e-12f;
             else var = second[i];
-            out[i] = mean[i] + (sqrtf(var) * z[k]);
+            out[i] = (center ? center[i] : mean[i]) + (sqrtf(var) * z[k]);
         }
     }
     return BDL_OK;

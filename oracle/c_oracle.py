@@ -58,8 +58,8 @@ def step(variant, theta, g, theta0, v, m, s, buf, runs, scalars, noise):
     assert rc == 0, rc
 
 
-def draw(mean, second, out, var_mode, scale, div_mode, noise):
-    rc = lib().bdl_oracle_draw(_fp(mean), _fp(second), _fp(out), C.c_uint64(mean.size), C.c_int(var_mode),
+def draw(mean, second, out, var_mode, scale, div_mode, noise, center=None):
+    rc = lib().bdl_oracle_draw(_fp(mean), _fp(second), _fp(center), _fp(out), C.c_uint64(mean.size), C.c_int(var_mode),
                                C.c_float(scale), C.c_int(div_mode), C.byref(noise))
     assert rc == 0
 

@@ -153,3 +153,38 @@ def test_model_forward_keeps_reference_contract(cuda_device):
     assert runner.model.t == 1
     sd = runner.optimizer.state_dict()
     assert len(sd["state"]) == len(names) and all("momentum_buffer" in s for s in sd["state"].values())
+
+
+@pytest.mark.parametrize("name", ["sghmc", "csgld", "csghmc"])
+def test_sharded_ensemble_equals_runner_evaluate(cuda_device, tmp_path, name):
+    """The sample-sharded formulation (prob sums + one all-reduce, here world=1) reproduces Runner.evaluate with the
+    same Philox keys: sharding changes where samples are computed, not what is computed."""
+    import importlib
+    from oracle import make_golden_runner as mgr
+    from bayesdll_b200 import dist as bdist
+    z = np.load(gu.golden_path(f"runner_{name}"), allow_pickle=False)
+    method, hp, over = mgr.CASES[name]
+    seed = 500 + sorted(mgr.CASES).index(name)
+    net, net0 = mgr.InjectNet(seed, z["G"]), mgr.InjectNet(seed + 1)
+    args = mgr.make_args(dict(hp), str(tmp_path), cuda_device, **over)     # default noise = in-kernel Philox
+    runner = importlib.import_module(f"bayesdll_b200.methods.{method}").Runner(net, net0, args, _logger())
+    runner.criterion = mgr.InjectCriterion()
+    loaders = mgr.loaders_from_arrays(z)
+    cwd = os.getcwd()
+    os.chdir(tmp_path)
+    try:
+        runner.train(*loaders)
+    finally:
+        os.chdir(cwd)
+    loss, err, targets, logits, _ = runner.evaluate(loaders[2])
+    comps, mixture = bdist.components_from_runner(runner)
+    ens = bdist.ShardedEnsemble(runner.net, runner.model.chain.layout, comps, runner.nst, runner.seed, mixture=mixture,
+                                eval_id=runner._eval_calls, div_mode=runner.div_mode)
+    loss2, err2, targets2, logits2 = ens.evaluate(loaders[2])
+    assert np.array_equal(targets, targets2)
+    np.testing.assert_allclose(logits2, logits, rtol=2e-5, atol=2e-5)
+    assert abs(loss - loss2) < 2e-5 * max(1.0, abs(loss)) and err == err2
+    from bayesdll_b200 import calibration
+    e1, m1, n1 = calibration.analyze(targets, logits2, 15, None)
+    e2, m2, n2 = ens.calibrate(targets2, logits2, 15)
+    assert abs(e1 - e2) < 1e-9 and abs(m1 - m2) < 1e-9 and abs(n1 - n2) < 1e-9
