@@ -59,8 +59,9 @@ SIGNATURES = {
     "bdl_draw": [_P, _P, _P, _P, _U64, _I32, _F, _I32, C.POINTER(Noise), _P],
     "bdl_ensemble": [_P, _U32, _U32, _U32, _F, _F, _I32, _P, _P],
     "bdl_ce_err": [_P, _P, _U32, _U32, _P, _P, _P],
-    "bdl_probsum_accum": [_P, _U32, _U32, _P, _P],
-    "bdl_probsum_finalize": [_P, _U32, _U32, _F, _F, _I32, _P, _P],
+    "bdl_lse_accum": [_P, _U32, _U32, _P, _P, _P],
+    "bdl_lse_rescale": [_P, _P, _P, _U64, _P],
+    "bdl_lse_finalize": [_P, _P, _U32, _U32, _F, _F, _I32, _P, _P],
     "bdl_calibrate": [_P, _P, _U64, _U32, _D, _I32, _P, _U32, _P, _P, _P, _P, _P, _P, _P],
     "bdl_chain_create": [_U64, _I32, _I32, _U64, C.POINTER(_P)],
     "bdl_chain_destroy": [_P],

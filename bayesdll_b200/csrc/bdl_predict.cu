@@ -3,7 +3,7 @@
 //
 //   bdl_ensemble          log-mean-softmax over S samples     methods/sgld.py:299-300, csgld.py:416-431
 //   bdl_ce_err            CE sum + error count                methods/sgld.py:302-306,314-315
-//   bdl_probsum_*         sample-sharded variant (one all-reduce of [B,K] probability sums, section 8e)
+//   bdl_lse_*             sample-sharded variant (running logsumexp; all-reduce MAX + SUM, section 8e)
 //   bdl_calibrate         reliability bins + NLL              calibration.py:43-65, 246-249
 //
 // These tensors are tiny ([B,K,S] <= 64*37*40, [N,K] = 3669*37): the kernels are latency-bound, one
@@ -82,9 +82,11 @@ ensemble_kernel(const float* __restrict__ L, uint32_t B, uint32_t K, uint32_t S,
     }
 }
 
-// prob_sum[b,k] += softmax_K(logits[b,:])[k]
+// Sample-sharded ensemble: running logsumexp over samples of log_softmax_K(logits), kept as (max, scaled sum) so that
+// probabilities that underflow in linear space (p < 1e-38) still combine exactly like the reference's
+// logsumexp(log_softmax) (methods/sgld.py:300).  m starts at -inf, s at 0.
 __global__ void __launch_bounds__(kPredThreads)
-probsum_accum_kernel(const float* __restrict__ logits, uint32_t B, uint32_t K, float* __restrict__ prob_sum) {
+lse_accum_kernel(const float* __restrict__ logits, uint32_t B, uint32_t K, float* __restrict__ m, float* __restrict__ s) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     for (uint32_t b = blockIdx.x * kPredWarps + warp; b < B; b += gridDim.x * kPredWarps) {
         const float* row = logits + static_cast<size_t>(b) * K;
@@ -93,16 +95,32 @@ probsum_accum_kernel(const float* __restrict__ logits, uint32_t B, uint32_t K, f
         mx = warp_max(mx);
         float sum = 0.f;
         for (uint32_t k = lane; k < K; k += 32) sum += expf(row[k] - mx);
-        sum = warp_sum(sum);
-        for (uint32_t k = lane; k < K; k += 32) prob_sum[static_cast<size_t>(b) * K + k] += expf(row[k] - mx) / sum;
+        const float lsum = logf(warp_sum(sum));
+        for (uint32_t k = lane; k < K; k += 32) {
+            const size_t i = static_cast<size_t>(b) * K + k;
+            const float ls = (row[k] - mx) - lsum;                  // log_softmax
+            const float mo = m[i], mn = fmaxf(mo, ls);
+            const float keep = mo == -CUDART_INF_F ? 0.f : s[i] * expf(mo - mn);
+            s[i] = keep + expf(ls - mn);
+            m[i] = mn;
+        }
+    }
+}
+
+// after all-reduce(MAX) of m: bring the local sums onto the global maximum so they can be all-reduce(SUM)ed
+__global__ void __launch_bounds__(kPredThreads)
+lse_rescale_kernel(const float* __restrict__ m_local, const float* __restrict__ m_global, float* __restrict__ s, uint32_t total) {
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+        const float ml = m_local[i];
+        s[i] = ml == -CUDART_INF_F ? 0.f : s[i] * expf(ml - m_global[i]);
     }
 }
 
 __global__ void __launch_bounds__(kPredThreads)
-probsum_finalize_kernel(const float* __restrict__ prob_sum, uint32_t total, float log_S, float weight, int mode,
-                        float* __restrict__ out) {
+lse_finalize_kernel(const float* __restrict__ m, const float* __restrict__ s, uint32_t total, float log_S, float weight,
+                    int mode, float* __restrict__ out) {
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
-        const float comp = logf(prob_sum[i]) - log_S;
+        const float comp = (logf(s[i]) + m[i]) - log_S;
         out[i] = mix(comp, weight, mode == 2 ? out[i] : 0.f, mode);
     }
 }
@@ -276,29 +294,42 @@ extern "C" int bdl_ce_err(const float* logits, const int64_t* y, uint32_t B, uin
     return check_cuda(cudaGetLastError(), "ce_err_kernel launch");
 }
 
-extern "C" int bdl_probsum_accum(const float* logits, uint32_t B, uint32_t K, float* prob_sum, void* stream) {
-    using namespace bdl;
-    BDL_REQUIRE(logits && prob_sum, BDL_ERR_INVALID, "bdl_probsum_accum: null pointer");
-    BDL_REQUIRE(K >= 1, BDL_ERR_INVALID, "bdl_probsum_accum: K must be >= 1");
-    if (B == 0) return BDL_OK;
-    probsum_accum_kernel<<<rows_grid(B), kPredThreads, 0, static_cast<cudaStream_t>(stream)>>>(logits, B, K, prob_sum);
-    return check_cuda(cudaGetLastError(), "probsum_accum_kernel launch");
+static uint32_t flat_grid(uint64_t total) {
+    uint32_t grid = static_cast<uint32_t>((total + bdl::kPredThreads - 1) / bdl::kPredThreads);
+    const uint32_t cap = static_cast<uint32_t>(bdl::num_sms() * 4);
+    return grid > cap ? cap : grid;
 }
 
-extern "C" int bdl_probsum_finalize(const float* prob_sum, uint32_t B, uint32_t K, float log_S, float weight, int mode,
-                                    float* out, void* stream) {
+extern "C" int bdl_lse_accum(const float* logits, uint32_t B, uint32_t K, float* m, float* s, void* stream) {
     using namespace bdl;
-    BDL_REQUIRE(prob_sum && out, BDL_ERR_INVALID, "bdl_probsum_finalize: null pointer");
-    BDL_REQUIRE(mode >= 0 && mode <= 2, BDL_ERR_INVALID, "bdl_probsum_finalize: mode must be 0,1,2");
-    const uint64_t total = static_cast<uint64_t>(B) * K;
-    BDL_REQUIRE(total < 0xFFFFFFFFull, BDL_ERR_INVALID, "bdl_probsum_finalize: B*K too large");
+    BDL_REQUIRE(logits && m && s, BDL_ERR_INVALID, "bdl_lse_accum: null pointer");
+    BDL_REQUIRE(K >= 1, BDL_ERR_INVALID, "bdl_lse_accum: K must be >= 1");
+    if (B == 0) return BDL_OK;
+    lse_accum_kernel<<<rows_grid(B), kPredThreads, 0, static_cast<cudaStream_t>(stream)>>>(logits, B, K, m, s);
+    return check_cuda(cudaGetLastError(), "lse_accum_kernel launch");
+}
+
+extern "C" int bdl_lse_rescale(const float* m_local, const float* m_global, float* s, uint64_t total, void* stream) {
+    using namespace bdl;
+    BDL_REQUIRE(m_local && m_global && s, BDL_ERR_INVALID, "bdl_lse_rescale: null pointer");
+    BDL_REQUIRE(total < 0xFFFFFFFFull, BDL_ERR_INVALID, "bdl_lse_rescale: too many elements");
     if (total == 0) return BDL_OK;
-    uint32_t grid = static_cast<uint32_t>((total + kPredThreads - 1) / kPredThreads);
-    const uint32_t cap = static_cast<uint32_t>(num_sms() * 4);
-    if (grid > cap) grid = cap;
-    probsum_finalize_kernel<<<grid, kPredThreads, 0, static_cast<cudaStream_t>(stream)>>>(
-        prob_sum, static_cast<uint32_t>(total), log_S, weight, mode, out);
-    return check_cuda(cudaGetLastError(), "probsum_finalize_kernel launch");
+    lse_rescale_kernel<<<flat_grid(total), kPredThreads, 0, static_cast<cudaStream_t>(stream)>>>(
+        m_local, m_global, s, static_cast<uint32_t>(total));
+    return check_cuda(cudaGetLastError(), "lse_rescale_kernel launch");
+}
+
+extern "C" int bdl_lse_finalize(const float* m, const float* s, uint32_t B, uint32_t K, float log_S, float weight, int mode,
+                                float* out, void* stream) {
+    using namespace bdl;
+    BDL_REQUIRE(m && s && out, BDL_ERR_INVALID, "bdl_lse_finalize: null pointer");
+    BDL_REQUIRE(mode >= 0 && mode <= 2, BDL_ERR_INVALID, "bdl_lse_finalize: mode must be 0,1,2");
+    const uint64_t total = static_cast<uint64_t>(B) * K;
+    BDL_REQUIRE(total < 0xFFFFFFFFull, BDL_ERR_INVALID, "bdl_lse_finalize: B*K too large");
+    if (total == 0) return BDL_OK;
+    lse_finalize_kernel<<<flat_grid(total), kPredThreads, 0, static_cast<cudaStream_t>(stream)>>>(
+        m, s, static_cast<uint32_t>(total), log_S, weight, mode, out);
+    return check_cuda(cudaGetLastError(), "lse_finalize_kernel launch");
 }
 
 extern "C" int bdl_calibrate(const float* logits, const int64_t* labels, uint64_t N, uint32_t K, double temperature,

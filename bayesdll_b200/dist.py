@@ -5,8 +5,9 @@
 * Sample-sharded posterior-predictive ensemble: the S = cycles x nst posterior samples are dealt round-robin to the
   ranks; every rank draws its samples with the counter-based Philox stream keyed by (evaluation, batch, cycle,
   sample) -- so the draws do not depend on the rank count --, runs the backbone forward and accumulates
-  sum_s softmax(logits_s) per cycle.  One all-reduce (NCCL over NVLink; ``[C, N, K]`` fp32, 4.3 MB at Pets size)
-  combines the ranks; the log / GMM mixture / CE / calibration reductions follow, the calibration bins being
+  a running logsumexp_s log_softmax(logits_s) per cycle as (max, scaled sum).  One exchange step (NCCL over NVLink:
+  all-reduce MAX then SUM of ``[C, N, K]`` fp32, 4.3 MB each at Pets size) combines the ranks; the log / GMM mixture /
+  CE / calibration reductions follow, the calibration bins being
   sharded by row with a second tiny all-reduce of the 3*M+2 bin statistics.
 """
 import copy
@@ -37,11 +38,14 @@ class CudaBackend:
         ops.draw(comp["mean"], comp["second"], out_flat, comp["var_mode"], comp["scale"],
                  ops.make_noise(seed=seed, subseq=subseq, stream_id=_lib.STREAM_DRAW), div_mode)
 
-    def probsum_accum(self, logits, prob_sum):
-        ops.probsum_accum(logits, prob_sum)
+    def lse_accum(self, logits, m, s):
+        ops.lse_accum(logits, m, s)
 
-    def probsum_finalize(self, prob_sum, out, n_samples, weight, mode):
-        ops.probsum_finalize(prob_sum, out, n_samples, weight, mode)
+    def lse_rescale(self, m_local, m_global, s):
+        ops.lse_rescale(m_local, m_global, s)
+
+    def lse_finalize(self, m, s, out, n_samples, weight, mode):
+        ops.lse_finalize(m, s, out, n_samples, weight, mode)
 
     def ce_err(self, logits, y):
         loss = torch.zeros(1, dtype=torch.float64, device=logits.device)
@@ -78,45 +82,53 @@ class ShardedEnsemble:
         adopt_parameters(self.net, layout, self.flat)
         self.mine = shard_samples(len(components), self.nst, rank, world)
 
-    def _all_reduce(self, t):
+    def _all_reduce(self, t, op="sum"):
         if self.world > 1:
             import torch.distributed as dist
-            dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.group)
+            dist.all_reduce(t, op=dist.ReduceOp.SUM if op == "sum" else dist.ReduceOp.MAX, group=self.group)
         return t
 
     def evaluate(self, loader):
         """-> (loss, err, targets[N] int64 numpy, logits[N,K] f32 numpy); identical on every rank."""
         dev = self.flat.device
         C = len(self.components)
-        sums, ys = [], []
+        ms, ss, ys = [], [], []
         with torch.no_grad():
             for b_idx, (x, y) in enumerate(loader):
                 x, y = x.to(dev, non_blocking=True), y.to(dev, non_blocking=True)
-                acc = None
-                for (ci, s) in self.mine:
+                m = s = None
+                for (ci, smp) in self.mine:
                     comp = self.components[ci]
-                    self.backend.draw(comp, self.flat, self.seed, _pack_subseq(self.eval_id, b_idx, comp["cycle"], s),
+                    self.backend.draw(comp, self.flat, self.seed, _pack_subseq(self.eval_id, b_idx, comp["cycle"], smp),
                                       self.div_mode)
                     out = self.net(x).float().contiguous()
-                    if acc is None:
-                        acc = torch.zeros((C,) + tuple(out.shape), dtype=torch.float32, device=dev)
-                    self.backend.probsum_accum(out, acc[ci])
-                if acc is None:                               # more ranks than samples: contribute zeros
-                    with torch.no_grad():
-                        k = self.net(x).shape[1]
-                    acc = torch.zeros((C, x.shape[0], k), dtype=torch.float32, device=dev)
-                sums.append(acc)
+                    if m is None:
+                        m = torch.full((C,) + tuple(out.shape), float("-inf"), dtype=torch.float32, device=dev)
+                        s = torch.zeros_like(m)
+                    self.backend.lse_accum(out, m[ci], s[ci])
+                if m is None:                                 # more ranks than samples: contribute the neutral element
+                    k = self.net(x).shape[1]
+                    m = torch.full((C, x.shape[0], k), float("-inf"), dtype=torch.float32, device=dev)
+                    s = torch.zeros_like(m)
+                ms.append(m)
+                ss.append(s)
                 ys.append(y)
-        prob = torch.cat(sums, dim=1).contiguous()           # [C, N, K]
-        self._all_reduce(prob)                               # the path's single data exchange
+        m_loc = torch.cat(ms, dim=1).contiguous()            # [C, N, K] running max of the local samples
+        s_loc = torch.cat(ss, dim=1).contiguous()
+        if self.world > 1:                                   # the path's only data exchange: MAX then SUM over [C,N,K]
+            m_glob = self._all_reduce(m_loc.clone(), "max")
+            self.backend.lse_rescale(m_loc, m_glob, s_loc)
+            self._all_reduce(s_loc, "sum")
+        else:
+            m_glob = m_loc
         y = torch.cat(ys)
-        N, K = prob.shape[1], prob.shape[2]
+        N, K = m_glob.shape[1], m_glob.shape[2]
         logits = torch.empty(N, K, dtype=torch.float32, device=dev)
         for ci, comp in enumerate(self.components):
             if self.mixture:
-                self.backend.probsum_finalize(prob[ci], logits, self.nst, comp["weight"], 1 if ci == 0 else 2)
+                self.backend.lse_finalize(m_glob[ci], s_loc[ci], logits, self.nst, comp["weight"], 1 if ci == 0 else 2)
             else:
-                self.backend.probsum_finalize(prob[ci], logits, self.nst, 1.0, 0)
+                self.backend.lse_finalize(m_glob[ci], s_loc[ci], logits, self.nst, 1.0, 0)
         loss, err = self.backend.ce_err(logits, y)
         return loss.item() / N, err.item() / N, y.cpu().numpy(), logits.cpu().numpy()
 
@@ -199,7 +211,7 @@ def bench_sharded_ensemble(device, rank, world, rows=512, batch=64, cycles=8, ns
     S = cycles * nst
     return {"metric": "ensemble preds/s (ResNet-101 cSGLD 40-sample posterior-predictive ensemble + ECE/MCE/NLL)",
             "value": rows * S / dt, "unit": "preds/s", "rows": rows, "samples": S, "seconds": dt, "n_gpus": world,
-            "sharding": "by sample, round-robin; one all-reduce of [C,N,K] prob sums + one of the bin statistics",
+            "sharding": "by sample, round-robin; all-reduce MAX+SUM of the [C,N,K] running logsumexp + one of the bin statistics",
             "ece": float(ece), "nll": float(nll), "loss": float(loss),
             "note": "per-sample cost = 1 draw kernel (12 B/param) + PyTorch fp32 forward of 64 images; samples re-drawn "
                     "for every batch as the reference does (Appendix B.6)"}

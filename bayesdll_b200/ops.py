@@ -16,7 +16,7 @@ from ._lib import (ADAM_CSGHMC, ADAM_SGHMC, CSGHMC, DIV_IEEE, DIV_RECIP, SGHMC, 
                    STREAM_USER, BdlError, Noise, Run, Scalars)
 
 __all__ = ["make_scalars", "upload_runs", "step", "philox_normal", "moments_avg", "moments_welford",
-           "capture_ring", "draw", "ensemble", "ce_err", "probsum_accum", "probsum_finalize", "calibrate",
+           "capture_ring", "draw", "ensemble", "ce_err", "lse_accum", "lse_rescale", "lse_finalize", "calibrate",
            "set_launch_config"]
 
 
@@ -181,18 +181,24 @@ def ce_err(logits, y, loss_sum, err_count):
     _lib.check(rc, "bdl_ce_err")
 
 
-def probsum_accum(logits, prob_sum):
+def lse_accum(logits, m, s):
+    """Running logsumexp over samples of log_softmax(logits): (m, s) <- combine((m, s), log_softmax(logits))."""
     B, K = logits.shape
-    rc = _lib.load().bdl_probsum_accum(_ptr(logits, "logits"), B, K, _ptr(prob_sum, "prob_sum"), _stream())
-    _lib.check(rc, "bdl_probsum_accum")
+    rc = _lib.load().bdl_lse_accum(_ptr(logits, "logits"), B, K, _ptr(m, "m"), _ptr(s, "s"), _stream())
+    _lib.check(rc, "bdl_lse_accum")
 
 
-def probsum_finalize(prob_sum, out, n_samples, weight=1.0, mode=0):
-    B, K = prob_sum.shape
+def lse_rescale(m_local, m_global, s):
+    rc = _lib.load().bdl_lse_rescale(_ptr(m_local, "m_local"), _ptr(m_global, "m_global"), _ptr(s, "s"), s.numel(), _stream())
+    _lib.check(rc, "bdl_lse_rescale")
+
+
+def lse_finalize(m, s, out, n_samples, weight=1.0, mode=0):
+    B, K = out.shape
     log_S = float(np.float32(np.log(n_samples))) if n_samples > 0 else 0.0
-    rc = _lib.load().bdl_probsum_finalize(_ptr(prob_sum, "prob_sum"), B, K, log_S, float(weight), int(mode),
-                                          _ptr(out, "out"), _stream())
-    _lib.check(rc, "bdl_probsum_finalize")
+    rc = _lib.load().bdl_lse_finalize(_ptr(m, "m"), _ptr(s, "s"), B, K, log_S, float(weight), int(mode), _ptr(out, "out"),
+                                      _stream())
+    _lib.check(rc, "bdl_lse_finalize")
     return out
 
 

@@ -177,12 +177,15 @@ int bdl_ensemble(const float* logits_all_dev, uint32_t B, uint32_t K, uint32_t S
 int bdl_ce_err(const float* logits_dev, const int64_t* y_dev, uint32_t B, uint32_t K, double* loss_sum_dev,
                int32_t* err_count_dev, void* stream);
 
-/* Sample-sharded ensembles (section 8e): prob_sum[B,K] += softmax_K(logits[B,K]) for one sample; after the
- * (NCCL) all-reduce of prob_sum, bdl_probsum_finalize forms comp = log(prob_sum) - log_S and applies the
- * same mode / weight rule as bdl_ensemble. */
-int bdl_probsum_accum(const float* logits_dev, uint32_t B, uint32_t K, float* prob_sum_dev, void* stream);
-int bdl_probsum_finalize(const float* prob_sum_dev, uint32_t B, uint32_t K, float log_S, float weight, int mode,
-                         float* out_logits_dev, void* stream);
+/* Sample-sharded ensembles (section 8e): running logsumexp over samples of log_softmax_K(logits[B,K]), kept per
+ * element as (m = running max, s = sum of exp(. - m)) so values whose probability underflows in linear space
+ * combine exactly like the reference's logsumexp(log_softmax) (methods/sgld.py:300).  Initialise m = -inf, s = 0.
+ * Across ranks: all-reduce(MAX) m -> m_global; bdl_lse_rescale; all-reduce(SUM) s; bdl_lse_finalize forms
+ * comp = log(s) + m - log_S and applies the same mode / weight rule as bdl_ensemble. */
+int bdl_lse_accum(const float* logits_dev, uint32_t B, uint32_t K, float* m_dev, float* s_dev, void* stream);
+int bdl_lse_rescale(const float* m_local_dev, const float* m_global_dev, float* s_dev, uint64_t total, void* stream);
+int bdl_lse_finalize(const float* m_dev, const float* s_dev, uint32_t B, uint32_t K, float log_S, float weight, int mode,
+                     float* out_logits_dev, void* stream);
 
 /* (a11) Calibration bins (calibration.py:24-67) and NLL (calibration.py:246-249).
  *   logits [N,K] fp32, labels [N] int64, edges [M] fp64 right bin boundaries (host: np.linspace(0,1+1e-8,M+1)[1:]).

@@ -26,11 +26,18 @@ class OracleBackend:
         var = so.variance_from_moments(mean, second, comp["scale"])
         out_flat.copy_(torch.from_numpy(so.posterior_draw(mean, var, eps)))
 
-    def probsum_accum(self, logits, prob_sum):
-        prob_sum += torch.softmax(logits, 1)
+    def lse_accum(self, logits, m, s):
+        ls = torch.log_softmax(logits, 1)
+        mn = torch.maximum(m, ls)
+        keep = torch.where(torch.isinf(m), torch.zeros_like(s), s * torch.exp(m - mn))
+        s.copy_(keep + torch.exp(ls - mn))
+        m.copy_(mn)
 
-    def probsum_finalize(self, prob_sum, out, n_samples, weight, mode):
-        comp = torch.log(prob_sum) - np.float32(np.log(n_samples))
+    def lse_rescale(self, m_local, m_global, s):
+        s.copy_(torch.where(torch.isinf(m_local), torch.zeros_like(s), s * torch.exp(m_local - m_global)))
+
+    def lse_finalize(self, m, s, out, n_samples, weight, mode):
+        comp = (torch.log(s) + m) - np.float32(np.log(n_samples))
         if mode == 0:
             out.copy_(comp)
         elif mode == 1:

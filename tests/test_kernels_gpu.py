@@ -116,19 +116,35 @@ def test_ensemble_matches_oracle_and_torch(cuda_device, B, K, S):
     assert err.item() == 2 * int((out.argmax(1).cpu().numpy() != y).sum())
 
 
-def test_probsum_path_equals_ensemble(cuda_device):
-    """Sample-sharded formulation: sum of softmax over samples, then log - log S == logsumexp of log_softmax."""
+def test_lse_path_equals_ensemble(cuda_device):
+    """Sample-sharded formulation: running (max, sum) logsumexp over samples, split over two 'ranks', merged with
+    MAX / rescale / SUM == the direct [B,K,S] reduction -- including logits whose probabilities underflow in fp32."""
     from bayesdll_b200 import ops
     B, K, S = 32, 37, 8
     L = torch.randn(B, K, S, device=cuda_device) * 2
+    L[:4] *= 200.0                                            # softmax underflows to exactly 0 for most classes
     direct = torch.empty(B, K, device=cuda_device)
     ops.ensemble(L, direct, S)
-    acc = torch.zeros(B, K, device=cuda_device)
-    for s in range(S):
-        ops.probsum_accum(L[:, :, s].contiguous(), acc)
+    parts = []
+    for samples in (range(0, S, 2), range(1, S, 2)):          # two ranks, round-robin
+        m = torch.full((B, K), float("-inf"), device=cuda_device)
+        s = torch.zeros(B, K, device=cuda_device)
+        for i in samples:
+            ops.lse_accum(L[:, :, i].contiguous(), m, s)
+        parts.append((m, s))
+    m_glob = torch.maximum(parts[0][0], parts[1][0])          # all-reduce(MAX)
+    for m, s in parts:
+        ops.lse_rescale(m, m_glob, s)
+    s_glob = parts[0][1] + parts[1][1]                        # all-reduce(SUM)
     out = torch.empty(B, K, device=cuda_device)
-    ops.probsum_finalize(acc, out, S)
-    np.testing.assert_allclose(out.cpu().numpy(), direct.cpu().numpy(), atol=2e-6, rtol=2e-6)
+    ops.lse_finalize(m_glob, s_glob, out, S)
+    assert torch.isfinite(out).all() and torch.isfinite(direct).all()
+    np.testing.assert_allclose(out.cpu().numpy(), direct.cpu().numpy(), atol=1e-4, rtol=2e-6)
+    # a rank without samples contributes the neutral element
+    m0 = torch.full((B, K), float("-inf"), device=cuda_device)
+    s0 = torch.zeros(B, K, device=cuda_device)
+    ops.lse_rescale(m0, m_glob, s0)
+    assert (s0 == 0).all()
 
 
 @pytest.mark.parametrize("tag", ["a", "b", "c", "d"])
