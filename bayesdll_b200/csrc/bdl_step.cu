@@ -319,9 +319,7 @@ int step_range(int variant, float* theta, const float* g, const float* theta0, f
     p.eps = sc->eps; p.two_alpha = sc->two_alpha; p.nd = sc->nd;
     p.T = sc->temperature; p.inv_T = 1.0f / sc->temperature;
     p.first_step = sc->first_step; p.add_noise = sc->add_noise;
-    p.key.k0 = static_cast<uint32_t>(nz->seed); p.key.k1 = static_cast<uint32_t>(nz->seed >> 32);
-    p.key.stream_id = nz->stream_id;
-    p.key.sub_lo = static_cast<uint32_t>(nz->subseq); p.key.sub_hi = static_cast<uint32_t>(nz->subseq >> 32);
+    p.key = host_noise_key(nz->seed, nz->stream_id, nz->subseq);
 
     const bool philox = nz->xi_dev == nullptr;
     const int d = sc->div_mode;
