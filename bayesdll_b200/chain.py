@@ -149,3 +149,39 @@ class ChainState:
         for t in (self.v, self.m, self.s):
             if t is not None:
                 t.zero_()
+
+
+class SampleRing:
+    """Preallocated HBM ring of raw posterior samples (north star (b)); replaces ``theta_vec.clone()`` into a Python
+    dict (methods/csgld.py:278-279).  Each capture is one TMA bulk-copy kernel (bdl_capture_ring, 8 B/param) into the
+    next slot; when the ring wraps the oldest sample is overwritten and its key dropped."""
+
+    def __init__(self, layout, device, expected_samples, mem_fraction=0.25):
+        free, _ = torch.cuda.mem_get_info(device)
+        per_slot = layout.n_padded * 4
+        cap = max(1, min(int(expected_samples), int(free * mem_fraction) // per_slot))
+        self.layout = layout
+        self.buf = torch.empty((cap, layout.n_padded), dtype=torch.float32, device=device)
+        self.keys = [None] * cap
+        self.count = 0
+
+    @property
+    def capacity(self):
+        return self.buf.shape[0]
+
+    def capture(self, theta_flat, key, store):
+        """Copy ``theta_flat`` into the next slot; ``store[key]`` becomes the dense view of that slot."""
+        slot = self.count % self.capacity
+        old = self.keys[slot]
+        if old is not None:
+            store.pop(old, None)
+        ops.capture_ring(theta_flat, self.buf, slot)
+        self.keys[slot] = key
+        self.count += 1
+        row = self.buf[slot]
+        store[key] = row[:self.layout.n_dense] if self._tail_only() else self.layout.to_dense(row)
+        return slot
+
+    def _tail_only(self):
+        segs = self.layout.segments
+        return all(s.begin == s.dense_begin for s in segs)

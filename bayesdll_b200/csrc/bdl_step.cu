@@ -121,8 +121,8 @@ __device__ __forceinline__ void update_one(const StepParams& p, uint32_t cls, fl
         const float mh = div_scalar<kDiv>(m, p.bc1, p.inv_bc1);
         const float sh = div_scalar<kDiv>(s, p.bc2, p.inv_bc2);
         const float den = __fadd_rn(__fsqrt_rn(sh), p.eps);
-        const float pg = __fdiv_rn(mh, den);
-        const float pre = __frcp_rn(den);               // 1.0 / den
+        const float pre = __frcp_rn(den);               // 1.0 / den, correctly rounded
+        const float pg = div_by_rcp(mh, den, pre);      // m_hat / den, correctly rounded (shares the reciprocal)
         const float ns = __fmul_rn(p.nd, __fsqrt_rn(div_scalar<kDiv>(__fmul_rn(p.two_alpha, pre), p.N, p.inv_N)));
         const float noise = __fmul_rn(ns, xi);
         v = __fadd_rn(__fadd_rn(__fmul_rn(v, p.oma), __fmul_rn(lr, pg)), noise);

@@ -25,7 +25,7 @@ import torch.nn as nn
 from tqdm import tqdm
 
 from .. import _lib, calibration, ops
-from ..chain import ChainState
+from ..chain import ChainState, SampleRing
 from ..flat import adopt_parameters, alloc_flat
 from .cyclical import CyclicalSGMCMC
 
@@ -524,7 +524,9 @@ class CyclicalRunner(_RunnerCommon):
         self._cyc1, self._cyc2 = {}, {}      # cycle -> padded flat moment buffers
         self.cycle_likelihoods = {}
         self.cycle_states = {}
-        self.all_samples = {}
+        self.all_samples = {}                # key "<epoch>_<batch>" -> dense view of a slot of the HBM sample ring
+        self._ring = None
+        self._batches_per_epoch = None
 
     # dict views under the reference's names: cycle -> dense vector
     @property
@@ -614,7 +616,7 @@ class CyclicalRunner(_RunnerCommon):
         err_acc = torch.zeros((), dtype=torch.int64, device=dev)
         nb_samples = 0
         cycle_updated = False
-        B = len(train_loader)
+        B = self._batches_per_epoch = len(train_loader)
         with tqdm(train_loader, unit="batch") as tepoch:
             for batch_idx, (x, y) in enumerate(tepoch):
                 pos = dict(epoch=sched.current_epoch, batch=batch_idx, batches_per_epoch=B)
@@ -678,8 +680,10 @@ class CyclicalRunner(_RunnerCommon):
             self._cyc1[cycle] = alloc_flat(n, ch.device, zero=False)
             self._cyc2[cycle] = alloc_flat(n, ch.device, zero=False)
         if self.CAPTURE == "avg":
-            if self.STORE_ALL_SAMPLES and getattr(self.args, "full_sample", False):
-                self.all_samples[f"{epoch}_{batch_idx}"] = self._dense(ch.theta).clone()      # csgld.py:278-279
+            if self.STORE_ALL_SAMPLES and getattr(self.args, "full_sample", False):            # csgld.py:278-279
+                if self._ring is None:
+                    self._ring = SampleRing(ch.layout, ch.device, self._expected_samples())
+                self._ring.capture(ch.theta, f"{epoch}_{batch_idx}", self.all_samples)
             if first:
                 ops.moments_avg(ch.theta, self._cyc1[cycle], self._cyc2[cycle], 0, init=True)
             else:
@@ -693,6 +697,12 @@ class CyclicalRunner(_RunnerCommon):
                 n_w = self.samples_per_cycle.get(cycle, 0) + 1
                 ops.moments_welford(ch.theta, self._cyc1[cycle], self._cyc2[cycle], n_w, div_mode=self.div_mode)
                 self.samples_per_cycle[cycle] = n_w
+
+    def _expected_samples(self):
+        """Number of captures the schedule will make over the whole run (host arithmetic, sizes the ring)."""
+        sched, B = self.cyclical_scheduler, self._batches_per_epoch or 1
+        return max(1, sum(1 for e in range(self.args.epochs) for b in range(B)
+                          if b % self.thin == 0 and sched.should_sample(epoch=e, batch=b, batches_per_epoch=B)))
 
     def _cycle_variance_spec(self, cycle):
         """(second buffer, var_mode, scale) for bdl_draw; keeps the reference's evaluation order so that a cycle with

@@ -261,6 +261,9 @@ def run_ours(args):
     if not args.no_ensemble:
         torch.cuda.empty_cache()
         extras["ensemble"] = ensemble_extra(device, rank, world, args)
+    if rank == 0 and world == 1 and not args.no_eager_gpu:
+        torch.cuda.empty_cache()
+        extras["reference_eager_gpu"] = eager_gpu_rate(lay, device)
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cpu_baseline = cpu_port_rate(lay, seconds=args.cpu_seconds, with_eager=True)
@@ -421,6 +424,33 @@ def eager_rate(lay, cores, max_params=64 << 20):
                       f"oracle/eager_port.py restating methods/sghmc.py:482-510 + SGD.step"}
 
 
+def eager_gpu_rate(lay, device, reps=3):
+    """The reference's own structure on the SAME B200: per-tensor eager loop + SGD.step (oracle/eager_port.py restating
+    methods/sghmc.py:482-510, :229) over all 296 ViT-L/32 tensors.  This is the number the fused kernel replaces
+    ('reference on the same B200')."""
+    from oracle import eager_port
+    names = [s.name for s in lay.segments]
+    gen = torch.Generator(device=device).manual_seed(1)
+    mk = lambda sc: [torch.randn(s.shape, device=device, generator=gen) * sc for s in lay.segments]
+    params, params0, grads = mk(0.02), mk(0.02), mk(0.01)
+    mom = [torch.zeros(s.shape, device=device) for s in lay.segments]
+    kw = dict(lr_body=HP["lr_body"], lr_head=HP["lr_head"], ND=HP["ND"], Ninflate=HP["Ninflate"], prior_sig=HP["prior_sig"],
+              nd=HP["nd"], alpha=HP["alpha"])
+    for _ in range(2):
+        eager_port.sghmc_step_eager(params, grads, params0, mom, names, lay.readout_name, **kw)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        eager_port.sghmc_step_eager(params, grads, params0, mom, names, lay.readout_name, **kw)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / reps
+    return {"value": lay.n_dense / (ms * 1e-3), "unit": "params/s", "ms_per_step": ms, "steps": reps,
+            "kernel_launches_per_step": "~12 eager kernels x 296 tensors",
+            "sample": "per-tensor torch-eager SGHMC loop + SGD step on cuda:0, all 296 ViT-L/32 tensors (oracle/eager_port.py)"}
+
+
 def run_reference(args):
     """The reference arm: the CPU implementation of the path (fused C port; the reference itself is Python and cannot
     travel to the GPU box).  Rank 0 only."""
@@ -456,6 +486,7 @@ def main():
     ap.add_argument("--no-train-step", action="store_true")
     ap.add_argument("--no-ensemble", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-eager-gpu", action="store_true")
     args = ap.parse_args()
     world = env_int("WORLD_SIZE", 1)
     if args.gpus != world and args.impl == "ours" and world == 1 and args.gpus > 1:

@@ -188,3 +188,41 @@ def test_sharded_ensemble_equals_runner_evaluate(cuda_device, tmp_path, name):
     e1, m1, n1 = calibration.analyze(targets, logits2, 15, None)
     e2, m2, n2 = ens.calibrate(targets2, logits2, 15)
     assert abs(e1 - e2) < 1e-9 and abs(m1 - m2) < 1e-9 and abs(n1 - n2) < 1e-9
+
+
+def test_csgld_full_sample_uses_hbm_ring(cuda_device, tmp_path):
+    """args.full_sample: raw samples land in the preallocated HBM ring through the TMA copy kernel; ``all_samples``
+    keeps the reference's "<epoch>_<batch>" keys and every stored vector equals theta at capture time."""
+    import importlib
+    from oracle import make_golden_runner as mgr
+    z = np.load(gu.golden_path("runner_csgld"), allow_pickle=False)
+    method, hp, over = mgr.CASES["csgld"]
+    seed = 500 + sorted(mgr.CASES).index("csgld")
+    net, net0 = mgr.InjectNet(seed, z["G"]), mgr.InjectNet(seed + 1)
+    args = mgr.make_args(dict(hp, noise="torch", div="ieee"), str(tmp_path), cuda_device, **over)
+    args.full_sample = True
+    from oracle import refshim
+    runner = importlib.import_module("bayesdll_b200.methods.csgld").Runner(net, net0, args, _logger())
+    runner.criterion = mgr.InjectCriterion()
+    captured = {}
+    orig = runner._capture
+
+    def spy(cycle, epoch, batch_idx):
+        orig(cycle, epoch, batch_idx)
+        captured[f"{epoch}_{batch_idx}"] = runner._dense(runner.model.chain.theta).clone()
+    runner._capture = spy
+    cwd = os.getcwd()
+    os.chdir(tmp_path)
+    try:
+        with refshim.injected_noise(z["tape"]):
+            runner.train(*mgr.loaders_from_arrays(z))
+    finally:
+        os.chdir(cwd)
+    assert runner._ring is not None and runner._ring.capacity == int(z["samples_collected"])
+    assert sorted(runner.all_samples) == sorted(captured) and len(captured) == int(z["samples_collected"])
+    for k, v in captured.items():
+        assert torch.equal(runner.all_samples[k], v)
+    assert os.path.exists(os.path.join(tmp_path, "all_samples_TEST.ckpt"))
+    # trajectory unchanged by the capture
+    got = runner._dense(runner.model.chain.theta).cpu().numpy()
+    assert np.array_equal(got.view(np.uint32), z["theta_final"].view(np.uint32))
