@@ -181,6 +181,16 @@ def bench_sharded_ensemble(device, rank, world, rows=512, batch=64, cycles=8, ns
     lay = FlatLayout.from_module(net)
     theta = alloc_flat(lay.n_padded, device)
     adopt_parameters(net, lay, theta)
+    x_host = torch.randn(batch, 3, 224, 224, generator=torch.Generator().manual_seed(5)).pin_memory()
+    # one training-mode pass with momentum 1 sets the BatchNorm running statistics to those of a synthetic batch, so
+    # the random-init network yields finite O(1) logits in eval mode (running stats are buffers, not sampled)
+    for mod in net.modules():
+        if isinstance(mod, torch.nn.modules.batchnorm._BatchNorm):
+            mod.momentum = 1.0
+    net.train()
+    with torch.no_grad():
+        net(x_host.to(device))
+    net.eval()
     gen = torch.Generator(device=device).manual_seed(11)
     comps = []
     for c in range(1, cycles + 1):
@@ -189,7 +199,6 @@ def bench_sharded_ensemble(device, rank, world, rows=512, batch=64, cycles=8, ns
         comps.append(dict(cycle=c, mean=mean, second=second, var_mode=ops.VAR_FROM_MOMENTS, scale=nst / (nst - 1.0),
                           weight=1.0 / cycles))
     rows = max(batch, rows // batch * batch)
-    x_host = torch.randn(batch, 3, 224, 224).pin_memory()
     y_all = torch.randint(0, 37, (rows,), generator=torch.Generator().manual_seed(3))
     loader = [(x_host, y_all[i:i + batch].pin_memory()) for i in range(0, rows, batch)]
     ens = ShardedEnsemble(net, lay, comps, nst, seed=42, mixture=True, rank=rank, world=world)
@@ -209,7 +218,26 @@ def bench_sharded_ensemble(device, rank, world, rows=512, batch=64, cycles=8, ns
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         dt = t.item()
     S = cycles * nst
-    return {"metric": "ensemble preds/s (ResNet-101 cSGLD 40-sample posterior-predictive ensemble + ECE/MCE/NLL)",
+    # context: cost of materialising ONE posterior sample, ours (bdl_draw) vs the reference's structure on this GPU
+    # (deepcopy(net) + randn_like / sqrt / mul / add / copy_ per tensor, methods/csgld.py:404-413)
+    comp = comps[0]
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for i in range(10):
+        ens.backend.draw(comp, ens.flat, 42, i, ens.div_mode)
+    torch.cuda.synchronize()
+    ours_draw_ms = (time.perf_counter() - t0) / 10 * 1e3
+    mean_views, var_views = lay.views(comp["mean"]), lay.views(torch.clamp(comp["second"] - comp["mean"] ** 2, min=1e-12))
+    t0 = time.perf_counter()
+    for i in range(3):
+        with torch.no_grad():
+            net_sample = copy.deepcopy(net)
+            for p, p_mean, p_var in zip(net_sample.parameters(), mean_views, var_views):
+                p.copy_(p_mean + p_var.sqrt() * torch.randn_like(p))
+    torch.cuda.synchronize()
+    ref_draw_ms = (time.perf_counter() - t0) / 3 * 1e3
+    del net_sample
+    return {"draw_ms": ours_draw_ms, "reference_structure_draw_ms": ref_draw_ms, "metric": "ensemble preds/s (ResNet-101 cSGLD 40-sample posterior-predictive ensemble + ECE/MCE/NLL)",
             "value": rows * S / dt, "unit": "preds/s", "rows": rows, "samples": S, "seconds": dt, "n_gpus": world,
             "sharding": "by sample, round-robin; all-reduce MAX+SUM of the [C,N,K] running logsumexp + one of the bin statistics",
             "ece": float(ece), "nll": float(nll), "loss": float(loss),
