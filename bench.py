@@ -217,6 +217,9 @@ def run_ours(args):
                 "frac_of_nominal_8TBps": round(achieved / 8000.0, 4), "kernel": "bdl::step_kernel<SGHMC,philox,recip,U=2>",
                 "algorithmic_bytes_per_launch": BYTES_PER_PARAM * n_dense, "kernel_ms": round(kernel_ms, 4)}
 
+    # ---- the other update rules on the same state (extra; BASELINE.json configs[1], [3], [4] kernels) ----------
+    variants = {} if args.no_variants else variant_rates(lay, theta, g, theta0, v, runs_dev, nruns, device, world, peak, seed)
+
     # ---- e2e through the host-buffer C ABI ----------------------------------------------------------
     e2e = None
     if not args.no_e2e:
@@ -281,6 +284,7 @@ def run_ours(args):
             "hbm_gbs": achieved * 1.0, "roofline": roofline, "e2e": e2e, "gpu_launches": K, "clocks": clocks,
             "cpu_baseline": cpu_baseline,
         }
+        line["variants"] = variants
         line.update(extras)
         print(json.dumps(line), flush=True)
     if world > 1:
@@ -290,6 +294,43 @@ def run_ours(args):
 
 
 # ------------------------------------------------------------------------------------------------------------
+def variant_rates(lay, theta, g, theta0, v, runs_dev, nruns, device, world, peak, seed, steps=30):
+    """params/s and roofline fraction of every other fused update rule at ViT-L/32 size (one chain per GPU)."""
+    from bayesdll_b200 import _lib, ops
+    n, n_dense = lay.n_padded, lay.n_dense
+    m = torch.zeros(n, device=device)
+    s2 = torch.full((n,), 1e-6, device=device)
+    buf = torch.zeros(n, device=device)
+    table = [("sgld_mu0.5", _lib.SGLD, 24, 0.5), ("sgld_mu0", _lib.SGLD, 16, 0.0), ("csghmc", _lib.CSGHMC, 20, 0.0),
+             ("adam_sghmc_mu0.5", _lib.ADAM_SGHMC, 48, 0.5), ("adam_csghmc", _lib.ADAM_CSGHMC, 40, 0.0)]
+    out = {}
+    for name, variant, bpp, mu in table:
+        adam = variant in (_lib.ADAM_SGHMC, _lib.ADAM_CSGHMC)
+        sc = ops.make_scalars(variant, lr_body=HP["lr_body"], lr_head=HP["lr_head"], ND=HP["ND"], Ninflate=HP["Ninflate"],
+                              prior_sig=HP["prior_sig"], nd=HP["nd"], alpha=0.05 if adam else HP["alpha"], mu=mu, t=10,
+                              div_mode=_lib.DIV_RECIP)
+
+        def one(i):
+            ops.step(variant, theta, g, None if variant == _lib.CSGHMC else theta0, None if variant == _lib.SGLD else v,
+                     m if adam else None, s2 if adam else None, buf if mu else None, runs_dev, nruns, sc,
+                     ops.make_noise(seed=seed, subseq=1000 + i))
+        for i in range(3):
+            one(i)
+        barrier(world)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(steps):
+            one(3 + i)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = allmax(e0.elapsed_time(e1), world, device) / steps
+        gbs = bpp * n_dense / (ms * 1e-3) / 1e9
+        out[name] = {"params_per_s": world * n_dense / (ms * 1e-3), "ms_per_step": ms, "bytes_per_param": bpp,
+                     "achieved_gbs_per_gpu": gbs, "frac_of_measured_peak": gbs / peak}
+    return out
+
+
 def train_step_extra(device, rank, world, steps=6, batch=64):
     """The call a user of the drop-in makes: Model.forward(x, y, net, net0, criterion, lrs, Ninflate, nd)."""
     import argparse as ap
@@ -487,6 +528,7 @@ def main():
     ap.add_argument("--no-ensemble", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-eager-gpu", action="store_true")
+    ap.add_argument("--no-variants", action="store_true")
     args = ap.parse_args()
     world = env_int("WORLD_SIZE", 1)
     if args.gpus != world and args.impl == "ours" and world == 1 and args.gpus > 1:

@@ -41,7 +41,14 @@ def main():
     ap.add_argument("--backbone", default="vit_l_32")
     ap.add_argument("--iters", type=int, default=20)
     ap.add_argument("--full", action="store_true")
+    ap.add_argument("--only", default=None, help="regex on the row tag: run only matching rows (for ncu captures)")
+    ap.add_argument("--warm", type=int, default=5)
     a = ap.parse_args()
+    import re
+    want = (lambda tag: re.search(a.only, tag) is not None) if a.only else (lambda tag: True)
+    global timeit
+    _timeit = timeit
+    timeit = lambda fn, iters: _timeit(fn, iters, warm=a.warm)
     dev = torch.device("cuda:0")
     named, readout = shapes.named_shapes(a.backbone)
     lay = FlatLayout(named, readout)
@@ -77,9 +84,12 @@ def main():
     # 1. launch-shape sweep on the headline kernel
     for unroll in (1, 2, 4):
         for per_sm in ((2, 3, 4, 5, 6, 8) if unroll < 4 else (1, 2, 3)):
+            tag = f"SGHMC philox recip  U={unroll} CTAs/SM={per_sm}"
+            if not want(tag):
+                continue
             ops.set_launch_config(per_sm, unroll)
             med, mn = timeit(stepper(_lib.SGHMC, 24), a.iters)
-            report(f"SGHMC philox recip  U={unroll} CTAs/SM={per_sm}", 24, med, mn)
+            report(tag, 24, med, mn)
     ops.set_launch_config(0, 0)
     # 2. every variant at the default launch shape
     table = [("SGHMC philox recip", _lib.SGHMC, 24, {}),
@@ -93,6 +103,8 @@ def main():
              ("Adam-cSGHMC philox", _lib.ADAM_CSGHMC, 40, {}),
              ("Adam-cSGHMC philox ieee-div", _lib.ADAM_CSGHMC, 40, dict(div=_lib.DIV_IEEE))]
     for tag, variant, bpp, kw in table:
+        if not want(tag):
+            continue
         med, mn = timeit(stepper(variant, bpp, **kw), a.iters)
         report(tag, bpp, med, mn)
     if a.full:
@@ -103,19 +115,22 @@ def main():
                 report(f"Adam-cSGHMC philox U={unroll} CTAs/SM={per_sm}", 40, med, mn)
         ops.set_launch_config(0, 0)
     # 3. capture / draw kernels
-    med, mn = timeit(lambda: ops.moments_avg(buf["theta"], buf["m"], buf["s"], 7), a.iters)
-    report("moments_avg (running mean / 2nd moment)", 20, med, mn)
-    med, mn = timeit(lambda: ops.moments_welford(buf["theta"], buf["m"], buf["s"], 7), a.iters)
-    report("moments_welford", 20, med, mn)
-    med, mn = timeit(lambda: ops.draw(buf["theta"], buf["s"], buf["b"], ops.VAR_FROM_MOMENTS, 1.1, ops.make_noise(seed=1, subseq=3, stream_id=1)), a.iters)
-    report("posterior draw (philox)", 12, med, mn)
     ring = buf["xi"].view(1, n)
-    med, mn = timeit(lambda: ops.capture_ring(buf["theta"], ring, 0), a.iters)
-    report("sample-ring TMA copy", 8, med, mn)
-    med, mn = timeit(lambda: buf["b"].copy_(buf["theta"]), a.iters)
-    report("torch copy_ (reference point for the peak)", 8, med, mn)
-    assert torch.equal(ring[0], buf["theta"]), "ring copy mismatch"
-    print("ring copy verified")
+    rows = [("moments_avg (running mean / 2nd moment)", 20, lambda: ops.moments_avg(buf["theta"], buf["m"], buf["s"], 7)),
+            ("moments_welford", 20, lambda: ops.moments_welford(buf["theta"], buf["m"], buf["s"], 7)),
+            ("posterior draw (philox)", 12, lambda: ops.draw(buf["theta"], buf["s"], buf["b"], ops.VAR_FROM_MOMENTS, 1.1,
+                                                            ops.make_noise(seed=1, subseq=3, stream_id=1))),
+            ("sample-ring TMA copy", 8, lambda: ops.capture_ring(buf["theta"], ring, 0)),
+            ("torch copy_ (reference point for the peak)", 8, lambda: buf["b"].copy_(buf["theta"]))]
+    for tag, bpp, fn in rows:
+        if not want(tag):
+            continue
+        med, mn = timeit(fn, a.iters)
+        report(tag, bpp, med, mn)
+    if want("sample-ring TMA copy"):
+        ops.capture_ring(buf["theta"], ring, 0)
+        assert torch.equal(ring[0], buf["theta"]), "ring copy mismatch"
+        print("ring copy verified")
 
 
 if __name__ == "__main__":
