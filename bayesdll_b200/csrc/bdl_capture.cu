@@ -11,7 +11,7 @@
 namespace bdl {
 
 constexpr int kCapThreads = 256;
-constexpr int kCapU = 2;
+constexpr int kCapU = 1;
 
 template <int kDiv, bool kInit, bool kHasMom2>
 __global__ void __launch_bounds__(kCapThreads, 4)
@@ -109,11 +109,10 @@ moments_welford_kernel(const float* __restrict__ theta, float* __restrict__ mean
     }
 }
 
-static uint32_t ew_grid(uint32_t n4, int per_sm) {
+// One tile per CTA, dispatched in address order (see the launch-shape note in bdl_step.cu).
+static uint32_t ew_grid(uint32_t n4, int /*per_sm*/) {
     const uint32_t tile_groups = kCapThreads * kCapU;
-    const uint32_t ntiles = (n4 + tile_groups - 1) / tile_groups;
-    uint32_t grid = static_cast<uint32_t>(num_sms() * per_sm);
-    return grid < ntiles ? grid : ntiles;
+    return (n4 + tile_groups - 1) / tile_groups;
 }
 
 // -------------------------------------------------------------------------------------------

@@ -142,54 +142,59 @@ struct Uses {
     static constexpr bool adam = (kVariant == BDL_ADAM_SGHMC || kVariant == BDL_ADAM_CSGHMC);
 };
 
-constexpr int kThreads = 256;
+constexpr int kDefaultThreads = 256;
+constexpr int kDefaultUnroll = 1;
 
-// Resident CTAs per SM the kernel is compiled for: 16 data registers per stream per unroll step plus
-// ~28 registers of addressing / Philox state, rounded to the allocation granule, against the 64K-entry RF.
-template <int kVariant, bool kHasBuf, bool kPhilox, int kU>
+// Resident CTAs per SM the kernel is compiled for: 16 data registers per stream per unroll step plus ~28 registers of
+// addressing / Philox state, rounded to the allocation granule, against the 64K-entry register file.
+template <int kVariant, bool kHasBuf, bool kPhilox, int kU, int kT>
 constexpr int min_blocks() {
     int streams = (kVariant == BDL_SGLD) ? 3 : (kVariant == BDL_SGHMC) ? 4 : (kVariant == BDL_CSGHMC) ? 3 : 6;
     streams += (kHasBuf ? 1 : 0) + (kPhilox ? 0 : 1);
     int regs = 4 * kU * streams + 28;
     regs = (regs + 7) / 8 * 8;
-    int blocks = 65536 / (kThreads * regs);
-    return blocks < 1 ? 1 : (blocks > 8 ? 8 : blocks);
+    int blocks = 65536 / (kT * regs);
+    const int cap = 2048 / kT;                     // 64 warps per SM
+    blocks = blocks > cap ? cap : blocks;
+    return blocks < 1 ? 1 : (blocks > 16 ? 16 : blocks);
 }
 
-template <int kVariant, bool kHasBuf, bool kPhilox, int kDiv, int kU>
-__global__ void __launch_bounds__(kThreads, (min_blocks<kVariant, kHasBuf, kPhilox, kU>()))
+// first run whose end is beyond group q (runs are sorted and contiguous)
+__device__ __forceinline__ uint32_t cursor_find(const StepParams& p, uint32_t q) {
+    uint32_t lo = 0, hi = p.nruns - 1;
+    while (lo < hi) {
+        const uint32_t mid = (lo + hi) >> 1;
+        if (q >= static_cast<uint32_t>(__ldg(&p.runs[mid].end) >> 2)) lo = mid + 1; else hi = mid;
+    }
+    return lo;
+}
+
+// Launch shape.  Default: ONE tile per CTA (grid = #tiles), CTAs dispatched in address order.  Measured on B200 this
+// beats a persistent grid-stride grid by ~8 % (6.87 vs 6.35 TB/s on the SGHMC step): in-order dispatch keeps the set
+// of DRAM pages being streamed compact, whereas persistent CTAs drift apart and scatter the access window.  The
+// tile loop remains for capped grids (bdl_set_launch_config) and for > 2^31 tiles.
+template <int kVariant, bool kHasBuf, bool kPhilox, int kDiv, int kU, int kT>
+__global__ void __launch_bounds__(kT, (min_blocks<kVariant, kHasBuf, kPhilox, kU, kT>()))
 step_kernel(const StepParams p) {
     using U = Uses<kVariant>;
-    const uint32_t tile_groups = kThreads * kU;
+    constexpr uint32_t tile_groups = kT * kU;
     const uint32_t ntiles = (p.n4 - p.q_begin + tile_groups - 1) / tile_groups;
     RunCursor cur;
-    cursor_load(cur, p, 0);
+    bool have_cursor = false;
 
     for (uint32_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         const uint32_t q0 = p.q_begin + tile * tile_groups + threadIdx.x;
         float4 th[kU], g[kU], th0[kU], v[kU], m[kU], s[kU], b[kU], xi[kU];
         uint32_t cls[kU];
         bool act[kU];
-        // ---- issue every load of the tile first (kU * #streams independent 128-bit requests) ----
+        // ---- 1. every load that does not depend on the run table (kU * #streams independent 128-bit requests) ----
 #pragma unroll
         for (int u = 0; u < kU; ++u) {
-            const uint32_t q = q0 + u * kThreads;
+            const uint32_t q = q0 + u * kT;
             act[u] = q < p.n4;
-            if (act[u]) {
-                cursor_seek(cur, p, q);
-                cls[u] = cur.cls;
-                act[u] = (cur.cls & BDL_CLS_SKIP) == 0;     // p.grad is None -> tensor left untouched
-            }
             if (act[u]) {
                 const uint64_t i = static_cast<uint64_t>(q) << 2;
                 th[u] = ld_stream(p.theta + i);
-                g[u] = ld_stream(cur.gbase + i);
-                if (cur.own_g && i + 4 > cur.valid_end) {  // tail group of a per-run gradient: zero the padding lanes
-                    if (i + 0 >= cur.valid_end) g[u].x = 0.f;
-                    if (i + 1 >= cur.valid_end) g[u].y = 0.f;
-                    if (i + 2 >= cur.valid_end) g[u].z = 0.f;
-                    if (i + 3 >= cur.valid_end) g[u].w = 0.f;
-                }
                 if constexpr (U::theta0) th0[u] = ld_stream(p.theta0 + i);
                 if constexpr (U::v) v[u] = ld_stream(p.v + i);
                 if constexpr (U::adam) {
@@ -200,10 +205,32 @@ step_kernel(const StepParams p) {
                 if constexpr (!kPhilox) xi[u] = ld_stream(p.xi + i);
             }
         }
-        // ---- compute + store ----
+        // ---- 2. element class / gradient pointer from the run table (L1-resident), then the gradient loads ----
 #pragma unroll
         for (int u = 0; u < kU; ++u) {
-            const uint32_t q = q0 + u * kThreads;
+            const uint32_t q = q0 + u * kT;
+            if (act[u]) {
+                if (!have_cursor) {
+                    cursor_load(cur, p, cursor_find(p, q));
+                    have_cursor = true;
+                }
+                cursor_seek(cur, p, q);
+                cls[u] = cur.cls;
+                const uint64_t i = static_cast<uint64_t>(q) << 2;
+                g[u] = ld_stream(cur.gbase + i);
+                if (cur.own_g && i + 4 > cur.valid_end) {  // tail group of a per-run gradient: zero the padding lanes
+                    if (i + 0 >= cur.valid_end) g[u].x = 0.f;
+                    if (i + 1 >= cur.valid_end) g[u].y = 0.f;
+                    if (i + 2 >= cur.valid_end) g[u].z = 0.f;
+                    if (i + 3 >= cur.valid_end) g[u].w = 0.f;
+                }
+                act[u] = (cur.cls & BDL_CLS_SKIP) == 0;     // p.grad is None -> tensor left untouched
+            }
+        }
+        // ---- 3. compute + store ----
+#pragma unroll
+        for (int u = 0; u < kU; ++u) {
+            const uint32_t q = q0 + u * kT;
             if (act[u]) {
                 const uint64_t i = static_cast<uint64_t>(q) << 2;
                 if constexpr (kPhilox) xi[u] = philox_normal4(p.key, q);
@@ -226,33 +253,35 @@ step_kernel(const StepParams p) {
 // -------------------------------------------------------------------------------------------
 // host side
 // -------------------------------------------------------------------------------------------
-static int g_ctas_per_sm = 0;   // 0 = default
-static int g_unroll = 0;
+static int g_ctas_per_sm = 0;   // 0 = one tile per CTA (default); > 0 = persistent grid of #SM * ctas_per_sm CTAs
+static int g_unroll = 0;        // 0 = default
+static int g_threads = 0;       // 0 = default
+
+template <int kVariant, bool kHasBuf, bool kPhilox, int kDiv, int kU, int kT>
+static int launch_shape(const StepParams& p, cudaStream_t st) {
+    constexpr uint32_t tile_groups = kT * kU;
+    const uint32_t ntiles = (p.n4 - p.q_begin + tile_groups - 1) / tile_groups;
+    uint64_t grid = ntiles;
+    if (g_ctas_per_sm > 0) {
+        const uint64_t cap = static_cast<uint64_t>(num_sms()) * g_ctas_per_sm;
+        if (grid > cap) grid = cap;
+    }
+    if (grid > 0x7FFFFFFFull) grid = 0x7FFFFFFFull;
+    if (grid == 0) return BDL_OK;
+    step_kernel<kVariant, kHasBuf, kPhilox, kDiv, kU, kT><<<static_cast<uint32_t>(grid), kT, 0, st>>>(p);
+    return check_cuda(cudaGetLastError(), "step_kernel launch");
+}
 
 template <int kVariant, bool kHasBuf, bool kPhilox, int kDiv>
 static int launch_u(const StepParams& p, cudaStream_t st) {
-    constexpr bool kAdam = (kVariant == BDL_ADAM_SGHMC || kVariant == BDL_ADAM_CSGHMC);
-    const int unroll = g_unroll ? g_unroll : (kAdam ? 1 : 2);
-    int per_sm = g_ctas_per_sm;
-    if (per_sm == 0) {
-        per_sm = unroll == 1 ? min_blocks<kVariant, kHasBuf, kPhilox, 1>()
-               : unroll == 2 ? min_blocks<kVariant, kHasBuf, kPhilox, 2>()
-                             : min_blocks<kVariant, kHasBuf, kPhilox, 4>();
-    }
-    const uint32_t tile_groups = kThreads * unroll;
-    const uint32_t ntiles = (p.n4 - p.q_begin + tile_groups - 1) / tile_groups;
-    uint32_t grid = static_cast<uint32_t>(num_sms() * per_sm);
-    if (grid > ntiles) grid = ntiles;
-    if (grid == 0) return BDL_OK;
-    switch (unroll) {
-        case 1: step_kernel<kVariant, kHasBuf, kPhilox, kDiv, 1><<<grid, kThreads, 0, st>>>(p); break;
-        case 2: step_kernel<kVariant, kHasBuf, kPhilox, kDiv, 2><<<grid, kThreads, 0, st>>>(p); break;
-        case 4: step_kernel<kVariant, kHasBuf, kPhilox, kDiv, 4><<<grid, kThreads, 0, st>>>(p); break;
-        default:
-            set_error("bdl_step: unsupported unroll %d (1, 2 or 4)", unroll);
-            return BDL_ERR_INVALID;
-    }
-    return check_cuda(cudaGetLastError(), "step_kernel launch");
+    const int unroll = g_unroll ? g_unroll : kDefaultUnroll;
+    const int threads = g_threads ? g_threads : kDefaultThreads;
+#define BDL_SHAPE(UU, TT) if (unroll == UU && threads == TT) return launch_shape<kVariant, kHasBuf, kPhilox, kDiv, UU, TT>(p, st)
+    BDL_SHAPE(1, 128); BDL_SHAPE(1, 256); BDL_SHAPE(1, 512);
+    BDL_SHAPE(2, 128); BDL_SHAPE(2, 256); BDL_SHAPE(2, 512);
+#undef BDL_SHAPE
+    set_error("bdl_step: unsupported launch shape unroll=%d threads=%d (unroll 1|2, threads 128|256|512)", unroll, threads);
+    return BDL_ERR_INVALID;
 }
 
 template <int kVariant, bool kHasBuf>
@@ -267,12 +296,15 @@ static int launch_nd(const StepParams& p, bool philox, int div, cudaStream_t st)
 
 }  // namespace bdl
 
-extern "C" int bdl_set_launch_config(int ctas_per_sm, int unroll) {
+extern "C" int bdl_set_launch_config(int ctas_per_sm, int unroll, int threads) {
     using namespace bdl;
-    BDL_REQUIRE(ctas_per_sm >= 0 && ctas_per_sm <= 32, BDL_ERR_INVALID, "ctas_per_sm out of range");
-    BDL_REQUIRE(unroll == 0 || unroll == 1 || unroll == 2 || unroll == 4, BDL_ERR_INVALID, "unroll must be 0,1,2,4");
+    BDL_REQUIRE(ctas_per_sm >= 0 && ctas_per_sm <= 65536, BDL_ERR_INVALID, "ctas_per_sm out of range");
+    BDL_REQUIRE(unroll == 0 || unroll == 1 || unroll == 2, BDL_ERR_INVALID, "unroll must be 0, 1 or 2");
+    BDL_REQUIRE(threads == 0 || threads == 128 || threads == 256 || threads == 512, BDL_ERR_INVALID,
+                "threads must be 0, 128, 256 or 512");
     g_ctas_per_sm = ctas_per_sm;
     g_unroll = unroll;
+    g_threads = threads;
     return BDL_OK;
 }
 

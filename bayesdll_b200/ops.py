@@ -38,8 +38,8 @@ def _stream():
     return torch.cuda.current_stream().cuda_stream
 
 
-def set_launch_config(ctas_per_sm=0, unroll=0):
-    _lib.check(_lib.load().bdl_set_launch_config(ctas_per_sm, unroll), "bdl_set_launch_config")
+def set_launch_config(ctas_per_sm=0, unroll=0, threads=0):
+    _lib.check(_lib.load().bdl_set_launch_config(ctas_per_sm, unroll, threads), "bdl_set_launch_config")
 
 
 # ----------------------------------------------------------------------------------------------

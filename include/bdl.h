@@ -114,8 +114,10 @@ typedef struct {
 int bdl_abi_version(void);
 const char* bdl_last_error(void);
 
-/* Optional launch tuning (0 = library default).  Used by bench sweeps; not needed for correctness. */
-int bdl_set_launch_config(int ctas_per_sm, int unroll);
+/* Optional launch tuning for bdl_step (0 = library default: one tile per CTA, 256 threads, 1 float4 group per
+ * thread).  ctas_per_sm > 0 caps the grid at #SM * ctas_per_sm persistent CTAs.  Used by bench sweeps and by the
+ * launch-shape-independence tests; not needed for correctness. */
+int bdl_set_launch_config(int ctas_per_sm, int unroll, int threads);
 
 /* (a1..a5) One fused sampler update over the whole flat state: prior pull, friction/momentum,
  * Adam moments, noise, SGD momentum and the parameter update in a single pass.

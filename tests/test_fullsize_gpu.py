@@ -49,9 +49,9 @@ def test_full_size_step_bit_exact_vs_c_oracle(cuda_device, case):
 
     # determinism + launch-shape independence at full size
     A = {k: t.clone() for k, t in D.items()}
-    ops.set_launch_config(3, 1)
+    ops.set_launch_config(3, 2, 512)
     ops.step(variant, *args(A), runs_dev, nruns, sc, ops.make_noise(seed=seed, subseq=sub))
-    ops.set_launch_config(0, 0)
+    ops.set_launch_config(0, 0, 0)
     ops.step(variant, *args(D), runs_dev, nruns, sc, ops.make_noise(seed=seed, subseq=sub))
     torch.cuda.synchronize()
     for k in ("theta", "v") + (("m", "s") if adam else ()):

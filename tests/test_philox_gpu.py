@@ -93,11 +93,11 @@ def test_inkernel_noise_equals_injected_stream(cuda_device, variant_name):
                  None if variant_name == "sgld" else st["v"], st["m"] if adam else None, st["s"] if adam else None,
                  st["buf"] if mu else None, runs_dev, nruns, sc, noise)
         torch.cuda.synchronize()
-        ops.set_launch_config(0, 0)
+        ops.set_launch_config(0, 0, 0)
         return st
 
-    ref = run(ops.make_noise(xi=xi), (0, 0))
-    for cfg in [(0, 0), (1, 1), (3, 2), (2, 4), (7, 1)]:
+    ref = run(ops.make_noise(xi=xi), (0, 0, 0))
+    for cfg in [(0, 0, 0), (1, 1, 128), (3, 2, 256), (0, 2, 512), (7, 1, 512), (64, 2, 128)]:
         got = run(ops.make_noise(seed=seed, subseq=step_no, stream_id=_lib.STREAM_STEP), cfg)
         for k in ("theta", "v", "m", "s", "buf"):
             assert torch.equal(got[k], ref[k]), f"{variant_name} {k} differs for launch config {cfg}"

@@ -81,16 +81,17 @@ def main():
                      buf["b"] if mu else None, rd, nr, sc, nz)
         return fn
 
-    # 1. launch-shape sweep on the headline kernel
-    for unroll in (1, 2, 4):
-        for per_sm in ((2, 3, 4, 5, 6, 8) if unroll < 4 else (1, 2, 3)):
-            tag = f"SGHMC philox recip  U={unroll} CTAs/SM={per_sm}"
-            if not want(tag):
-                continue
-            ops.set_launch_config(per_sm, unroll)
-            med, mn = timeit(stepper(_lib.SGHMC, 24), a.iters)
-            report(tag, 24, med, mn)
-    ops.set_launch_config(0, 0)
+    # 1. launch-shape sweep on the headline kernel (ctas_per_sm = 0: one tile per CTA, grid = #tiles)
+    for threads in (128, 256, 512):
+        for unroll in (1, 2):
+            for per_sm in (0, 4, 8, 64):
+                tag = f"SGHMC philox recip  T={threads} U={unroll} CTAs/SM={per_sm if per_sm else 'all'}"
+                if not want(tag):
+                    continue
+                ops.set_launch_config(per_sm, unroll, threads)
+                med, mn = timeit(stepper(_lib.SGHMC, 24), a.iters)
+                report(tag, 24, med, mn)
+    ops.set_launch_config(0, 0, 0)
     # 2. every variant at the default launch shape
     table = [("SGHMC philox recip", _lib.SGHMC, 24, {}),
              ("SGHMC philox ieee-div", _lib.SGHMC, 24, dict(div=_lib.DIV_IEEE)),
@@ -108,12 +109,18 @@ def main():
         med, mn = timeit(stepper(variant, bpp, **kw), a.iters)
         report(tag, bpp, med, mn)
     if a.full:
-        for unroll in (1, 2):
-            for per_sm in (2, 3, 4, 5):
-                ops.set_launch_config(per_sm, unroll)
+        for threads in (128, 256, 512):
+            for unroll in (1, 2):
+                tag = f"Adam-cSGHMC philox T={threads} U={unroll}"
+                if not want(tag):
+                    continue
+                ops.set_launch_config(0, unroll, threads)
                 med, mn = timeit(stepper(_lib.ADAM_CSGHMC, 40), a.iters)
-                report(f"Adam-cSGHMC philox U={unroll} CTAs/SM={per_sm}", 40, med, mn)
-        ops.set_launch_config(0, 0)
+                report(tag, 40, med, mn)
+                tag = f"SGLD mu=0 philox T={threads} U={unroll}"
+                med, mn = timeit(stepper(_lib.SGLD, 16), a.iters)
+                report(tag, 16, med, mn)
+        ops.set_launch_config(0, 0, 0)
     # 3. capture / draw kernels
     ring = buf["xi"].view(1, n)
     rows = [("moments_avg (running mean / 2nd moment)", 20, lambda: ops.moments_avg(buf["theta"], buf["m"], buf["s"], 7)),
