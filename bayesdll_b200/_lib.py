@@ -56,6 +56,7 @@ SIGNATURES = {
     "bdl_moments_avg": [_P, _P, _P, _U64, _F, _F, _I32, _I32, _P],
     "bdl_moments_welford": [_P, _P, _P, _U64, _F, _I32, _I32, _P],
     "bdl_capture_ring": [_P, _P, _U64, _U64, _P],
+    "bdl_set_ring_config": [_I32],
     "bdl_draw": [_P, _P, _P, _P, _U64, _I32, _F, _I32, C.POINTER(Noise), _P],
     "bdl_ensemble": [_P, _U32, _U32, _U32, _F, _F, _I32, _P, _P],
     "bdl_ce_err": [_P, _P, _U32, _U32, _P, _P, _P],

@@ -10,11 +10,11 @@
 
 namespace bdl {
 
-constexpr int kCapThreads = 256;
+constexpr int kCapThreads = 128;
 constexpr int kCapU = 1;
 
 template <int kDiv, bool kInit, bool kHasMom2>
-__global__ void __launch_bounds__(kCapThreads, 4)
+__global__ void __launch_bounds__(kCapThreads, 8)
 moments_avg_kernel(const float* __restrict__ theta, float* __restrict__ mom1, float* __restrict__ mom2, uint32_t n4,
                    float cnt, float cntp1, float inv_cntp1) {
     const uint32_t tile_groups = kCapThreads * kCapU;
@@ -62,7 +62,7 @@ moments_avg_kernel(const float* __restrict__ theta, float* __restrict__ mom1, fl
 }
 
 template <int kDiv, bool kInit>
-__global__ void __launch_bounds__(kCapThreads, 4)
+__global__ void __launch_bounds__(kCapThreads, 8)
 moments_welford_kernel(const float* __restrict__ theta, float* __restrict__ mean, float* __restrict__ M2, uint32_t n4,
                        float nf, float inv_nf) {
     const uint32_t tile_groups = kCapThreads * kCapU;
@@ -156,18 +156,19 @@ template <int N>
 __device__ __forceinline__ void tma_wait_all() { asm volatile("cp.async.bulk.wait_group %0;" ::"n"(N) : "memory"); }
 
 __global__ void __launch_bounds__(32, 3)
-ring_copy_kernel(const char* __restrict__ src, char* __restrict__ dst, uint64_t bytes) {
+ring_copy_kernel(const char* __restrict__ src, char* __restrict__ dst, uint64_t bytes, uint32_t per_cta) {
     extern __shared__ __align__(128) unsigned char smem[];
     __shared__ __align__(8) uint64_t bars[kRingStages];
     if (threadIdx.x != 0) return;
 
     const uint64_t nchunks = (bytes + kRingChunk - 1) / kRingChunk;
-    // chunks handled by this CTA: blockIdx.x, blockIdx.x + gridDim.x, ...
-    const uint64_t mine = nchunks > blockIdx.x ? (nchunks - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+    // this CTA copies the contiguous chunks [blockIdx.x * per_cta, ...): CTAs are dispatched in address order
+    const uint64_t c_begin = static_cast<uint64_t>(blockIdx.x) * per_cta;
+    const uint64_t mine = c_begin < nchunks ? (nchunks - c_begin < per_cta ? nchunks - c_begin : per_cta) : 0;
     for (int s = 0; s < kRingStages; ++s) mbar_init(smem_u32(&bars[s]), 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
 
-    auto chunk_off = [&](uint64_t k) { return (blockIdx.x + k * gridDim.x) * static_cast<uint64_t>(kRingChunk); };
+    auto chunk_off = [&](uint64_t k) { return (c_begin + k) * static_cast<uint64_t>(kRingChunk); };
     auto chunk_len = [&](uint64_t k) {
         const uint64_t off = chunk_off(k);
         return static_cast<uint32_t>(bytes - off < kRingChunk ? bytes - off : kRingChunk);
@@ -240,6 +241,14 @@ extern "C" int bdl_moments_welford(const float* theta, float* mean, float* M2, u
     return check_cuda(cudaGetLastError(), "moments_welford_kernel launch");
 }
 
+static uint32_t g_ring_chunks_per_cta = 8;
+extern "C" int bdl_set_ring_config(int chunks_per_cta) {
+    using namespace bdl;
+    BDL_REQUIRE(chunks_per_cta >= 1 && chunks_per_cta <= (1 << 20), BDL_ERR_INVALID, "chunks_per_cta out of range");
+    g_ring_chunks_per_cta = static_cast<uint32_t>(chunks_per_cta);
+    return BDL_OK;
+}
+
 extern "C" int bdl_capture_ring(const float* theta, float* ring, uint64_t slot, uint64_t n, void* stream) {
     using namespace bdl;
     BDL_REQUIRE(theta && ring, BDL_ERR_INVALID, "bdl_capture_ring: null pointer");
@@ -250,9 +259,9 @@ extern "C" int bdl_capture_ring(const float* theta, float* ring, uint64_t slot, 
     BDL_CUDA(cudaFuncSetAttribute(ring_copy_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
     const uint64_t bytes = n * sizeof(float);
     const uint64_t nchunks = (bytes + kRingChunk - 1) / kRingChunk;
-    uint64_t grid = static_cast<uint64_t>(num_sms()) * 3;
-    if (grid > nchunks) grid = nchunks;
+    const uint32_t per_cta = g_ring_chunks_per_cta;
+    const uint64_t grid = (nchunks + per_cta - 1) / per_cta;
     ring_copy_kernel<<<static_cast<uint32_t>(grid), 32, smem_bytes, static_cast<cudaStream_t>(stream)>>>(
-        reinterpret_cast<const char*>(theta), reinterpret_cast<char*>(ring + slot * n), bytes);
+        reinterpret_cast<const char*>(theta), reinterpret_cast<char*>(ring + slot * n), bytes, per_cta);
     return check_cuda(cudaGetLastError(), "ring_copy_kernel launch");
 }

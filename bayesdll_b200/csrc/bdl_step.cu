@@ -142,7 +142,7 @@ struct Uses {
     static constexpr bool adam = (kVariant == BDL_ADAM_SGHMC || kVariant == BDL_ADAM_CSGHMC);
 };
 
-constexpr int kDefaultThreads = 256;
+constexpr int kDefaultThreads = 128;
 constexpr int kDefaultUnroll = 1;
 
 // Resident CTAs per SM the kernel is compiled for: 16 data registers per stream per unroll step plus ~28 registers of
@@ -154,17 +154,30 @@ constexpr int min_blocks() {
     int regs = 4 * kU * streams + 28;
     regs = (regs + 7) / 8 * 8;
     int blocks = 65536 / (kT * regs);
-    const int cap = 2048 / kT;                     // 64 warps per SM
+    const int cap = 2048 / kT > 32 ? 32 : 2048 / kT;   // 64 warps and 32 CTAs per SM
     blocks = blocks > cap ? cap : blocks;
-    return blocks < 1 ? 1 : (blocks > 16 ? 16 : blocks);
+    return blocks < 1 ? 1 : blocks;
 }
 
-// first run whose end is beyond group q (runs are sorted and contiguous)
-__device__ __forceinline__ uint32_t cursor_find(const StepParams& p, uint32_t q) {
-    uint32_t lo = 0, hi = p.nruns - 1;
-    while (lo < hi) {
-        const uint32_t mid = (lo + hi) >> 1;
-        if (q >= static_cast<uint32_t>(__ldg(&p.runs[mid].end) >> 2)) lo = mid + 1; else hi = mid;
+// First run whose end is beyond group q (runs are sorted and contiguous).  Warp-cooperative 32-ary search: every lane
+// probes the last run of its slice of the candidate range, one ballot narrows the range 32x, so <= 2048 runs need at
+// most 3 dependent (L1-resident) loads instead of 11 for a scalar binary search.  q must be warp-uniform.
+__device__ __forceinline__ uint32_t cursor_find_warp(const StepParams& p, uint32_t q) {
+    const uint32_t lane = threadIdx.x & 31u;
+    uint32_t lo = 0, n = p.nruns;
+    while (n > 1) {
+        const uint32_t stride = (n + 31u) >> 5;
+        const uint32_t first = lo + lane * stride;
+        const bool valid = first < lo + n;
+        uint32_t last = first + stride - 1;
+        if (last > lo + n - 1) last = lo + n - 1;
+        const uint32_t end4 = valid ? static_cast<uint32_t>(__ldg(&p.runs[last].end) >> 2) : 0xFFFFFFFFu;
+        const uint32_t mask = __ballot_sync(0xFFFFFFFFu, valid && q < end4);
+        const uint32_t hit = mask ? static_cast<uint32_t>(__ffs(mask) - 1) : (n - 1) / stride;   // beyond the table: last slice
+        const uint32_t nlo = lo + hit * stride;
+        const uint32_t rem = lo + n - nlo;
+        n = rem < stride ? rem : stride;
+        lo = nlo;
     }
     return lo;
 }
@@ -206,14 +219,15 @@ step_kernel(const StepParams p) {
             }
         }
         // ---- 2. element class / gradient pointer from the run table (L1-resident), then the gradient loads ----
+        if (!have_cursor) {                                // all lanes take part (ballot); start from the warp's first group
+            const uint32_t qw = __shfl_sync(0xFFFFFFFFu, q0, 0);
+            cursor_load(cur, p, cursor_find_warp(p, qw < p.n4 ? qw : p.n4 - 1));
+            have_cursor = true;
+        }
 #pragma unroll
         for (int u = 0; u < kU; ++u) {
             const uint32_t q = q0 + u * kT;
             if (act[u]) {
-                if (!have_cursor) {
-                    cursor_load(cur, p, cursor_find(p, q));
-                    have_cursor = true;
-                }
                 cursor_seek(cur, p, q);
                 cls[u] = cur.cls;
                 const uint64_t i = static_cast<uint64_t>(q) << 2;
@@ -277,10 +291,10 @@ static int launch_u(const StepParams& p, cudaStream_t st) {
     const int unroll = g_unroll ? g_unroll : kDefaultUnroll;
     const int threads = g_threads ? g_threads : kDefaultThreads;
 #define BDL_SHAPE(UU, TT) if (unroll == UU && threads == TT) return launch_shape<kVariant, kHasBuf, kPhilox, kDiv, UU, TT>(p, st)
-    BDL_SHAPE(1, 128); BDL_SHAPE(1, 256); BDL_SHAPE(1, 512);
-    BDL_SHAPE(2, 128); BDL_SHAPE(2, 256); BDL_SHAPE(2, 512);
+    BDL_SHAPE(1, 64); BDL_SHAPE(1, 128); BDL_SHAPE(1, 256); BDL_SHAPE(1, 512);
+    BDL_SHAPE(2, 64); BDL_SHAPE(2, 128); BDL_SHAPE(2, 256); BDL_SHAPE(2, 512);
 #undef BDL_SHAPE
-    set_error("bdl_step: unsupported launch shape unroll=%d threads=%d (unroll 1|2, threads 128|256|512)", unroll, threads);
+    set_error("bdl_step: unsupported launch shape unroll=%d threads=%d (unroll 1|2, threads 64|128|256|512)", unroll, threads);
     return BDL_ERR_INVALID;
 }
 
@@ -300,8 +314,8 @@ extern "C" int bdl_set_launch_config(int ctas_per_sm, int unroll, int threads) {
     using namespace bdl;
     BDL_REQUIRE(ctas_per_sm >= 0 && ctas_per_sm <= 65536, BDL_ERR_INVALID, "ctas_per_sm out of range");
     BDL_REQUIRE(unroll == 0 || unroll == 1 || unroll == 2, BDL_ERR_INVALID, "unroll must be 0, 1 or 2");
-    BDL_REQUIRE(threads == 0 || threads == 128 || threads == 256 || threads == 512, BDL_ERR_INVALID,
-                "threads must be 0, 128, 256 or 512");
+    BDL_REQUIRE(threads == 0 || threads == 64 || threads == 128 || threads == 256 || threads == 512, BDL_ERR_INVALID,
+                "threads must be 0, 64, 128, 256 or 512");
     g_ctas_per_sm = ctas_per_sm;
     g_unroll = unroll;
     g_threads = threads;

@@ -144,6 +144,10 @@ def moments_welford(theta, mean, M2, n, init=False, div_mode=DIV_RECIP):
     _lib.check(rc, "bdl_moments_welford")
 
 
+def set_ring_config(chunks_per_cta=8):
+    _lib.check(_lib.load().bdl_set_ring_config(int(chunks_per_cta)), "bdl_set_ring_config")
+
+
 def capture_ring(theta, ring, slot):
     n = theta.numel()
     if ring.dim() != 2 or ring.shape[1] != n or not (0 <= slot < ring.shape[0]):

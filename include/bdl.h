@@ -152,6 +152,8 @@ int bdl_moments_welford(const float* theta_dev, float* mean_dev, float* m2_dev, 
  * bulk copies (cp.async.bulk global->shared->global).  Replaces theta_vec.clone() into a dict
  * (methods/csgld.py:278-279). */
 int bdl_capture_ring(const float* theta_dev, float* ring_dev, uint64_t slot, uint64_t n, void* stream);
+/* Tuning: 16 KiB chunks copied by one CTA of the ring kernel (default 8). */
+int bdl_set_ring_config(int chunks_per_cta);
 
 /* (a9) Posterior draw theta_s = mean + sqrt(var) * eps (methods/sgld.py:292-297, csgld.py:404-413).
  *   var_mode 0: var = max(scale * (second - mean^2), 1e-12)   scale = fp32(ratio)  (sgld.py:338-348)

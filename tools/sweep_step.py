@@ -82,9 +82,9 @@ def main():
         return fn
 
     # 1. launch-shape sweep on the headline kernel (ctas_per_sm = 0: one tile per CTA, grid = #tiles)
-    for threads in (128, 256, 512):
+    for threads in (64, 128, 256):
         for unroll in (1, 2):
-            for per_sm in (0, 4, 8, 64):
+            for per_sm in (0, 16):
                 tag = f"SGHMC philox recip  T={threads} U={unroll} CTAs/SM={per_sm if per_sm else 'all'}"
                 if not want(tag):
                     continue
@@ -109,8 +109,8 @@ def main():
         med, mn = timeit(stepper(variant, bpp, **kw), a.iters)
         report(tag, bpp, med, mn)
     if a.full:
-        for threads in (128, 256, 512):
-            for unroll in (1, 2):
+        for threads in (64, 128, 256):
+            for unroll in (1,):
                 tag = f"Adam-cSGHMC philox T={threads} U={unroll}"
                 if not want(tag):
                     continue
@@ -128,6 +128,10 @@ def main():
             ("posterior draw (philox)", 12, lambda: ops.draw(buf["theta"], buf["s"], buf["b"], ops.VAR_FROM_MOMENTS, 1.1,
                                                             ops.make_noise(seed=1, subseq=3, stream_id=1))),
             ("sample-ring TMA copy", 8, lambda: ops.capture_ring(buf["theta"], ring, 0)),
+            ("sample-ring TMA copy per_cta=4", 8, lambda: (ops.set_ring_config(4), ops.capture_ring(buf["theta"], ring, 0))),
+            ("sample-ring TMA copy per_cta=16", 8, lambda: (ops.set_ring_config(16), ops.capture_ring(buf["theta"], ring, 0))),
+            ("sample-ring TMA copy per_cta=64", 8, lambda: (ops.set_ring_config(64), ops.capture_ring(buf["theta"], ring, 0))),
+            ("sample-ring TMA copy per_cta=512", 8, lambda: (ops.set_ring_config(512), ops.capture_ring(buf["theta"], ring, 0))),
             ("torch copy_ (reference point for the peak)", 8, lambda: buf["b"].copy_(buf["theta"]))]
     for tag, bpp, fn in rows:
         if not want(tag):
