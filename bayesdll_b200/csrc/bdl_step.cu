@@ -288,8 +288,14 @@ static int launch_shape(const StepParams& p, cudaStream_t st) {
 
 template <int kVariant, bool kHasBuf, bool kPhilox, int kDiv>
 static int launch_u(const StepParams& p, cudaStream_t st) {
+    // Default block size, from the ViT-L/32 sweep (profiles/r01_sweep_final.log): the more streams a variant moves per
+    // element the smaller the CTA that keeps the in-order streaming window tight; the 16 B/param SGLD (mu = 0) kernel is
+    // issue-bound and prefers fewer, larger CTAs.
+    constexpr int kStreams = ((kVariant == BDL_SGLD) ? 3 : (kVariant == BDL_SGHMC) ? 4 : (kVariant == BDL_CSGHMC) ? 3 : 6) +
+                             (kHasBuf ? 1 : 0);
+    constexpr int kAutoThreads = kStreams >= 4 ? 64 : (kVariant == BDL_SGLD ? 256 : 128);
     const int unroll = g_unroll ? g_unroll : kDefaultUnroll;
-    const int threads = g_threads ? g_threads : kDefaultThreads;
+    const int threads = g_threads ? g_threads : kAutoThreads;
 #define BDL_SHAPE(UU, TT) if (unroll == UU && threads == TT) return launch_shape<kVariant, kHasBuf, kPhilox, kDiv, UU, TT>(p, st)
     BDL_SHAPE(1, 64); BDL_SHAPE(1, 128); BDL_SHAPE(1, 256); BDL_SHAPE(1, 512);
     BDL_SHAPE(2, 64); BDL_SHAPE(2, 128); BDL_SHAPE(2, 256); BDL_SHAPE(2, 512);

@@ -144,7 +144,7 @@ def moments_welford(theta, mean, M2, n, init=False, div_mode=DIV_RECIP):
     _lib.check(rc, "bdl_moments_welford")
 
 
-def set_ring_config(chunks_per_cta=8):
+def set_ring_config(chunks_per_cta=4):
     _lib.check(_lib.load().bdl_set_ring_config(int(chunks_per_cta)), "bdl_set_ring_config")
 
 

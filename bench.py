@@ -214,7 +214,7 @@ def run_ours(args):
     achieved = BYTES_PER_PARAM * n_dense / (kernel_ms * 1e-3) / 1e9
     roofline = {"bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
                 "frac": round(achieved / peak, 4), "traffic": recorded_traffic(), "peak_source": peak_kind,
-                "frac_of_nominal_8TBps": round(achieved / 8000.0, 4), "kernel": "bdl::step_kernel<SGHMC,philox,recip,U=2>",
+                "frac_of_nominal_8TBps": round(achieved / 8000.0, 4), "kernel": "bdl::step_kernel<SGHMC,philox,recip,U=1,T=64>, one tile per CTA",
                 "algorithmic_bytes_per_launch": BYTES_PER_PARAM * n_dense, "kernel_ms": round(kernel_ms, 4)}
 
     # ---- the other update rules on the same state (extra; BASELINE.json configs[1], [3], [4] kernels) ----------

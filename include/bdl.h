@@ -114,8 +114,8 @@ typedef struct {
 int bdl_abi_version(void);
 const char* bdl_last_error(void);
 
-/* Optional launch tuning for bdl_step (0 = library default: one tile per CTA, 256 threads, 1 float4 group per
- * thread).  ctas_per_sm > 0 caps the grid at #SM * ctas_per_sm persistent CTAs.  Used by bench sweeps and by the
+/* Optional launch tuning for bdl_step (0 = library default: one tile per CTA, 64-256 threads depending on the
+ * variant, 1 float4 group per thread).  ctas_per_sm > 0 caps the grid at #SM * ctas_per_sm persistent CTAs.  Used by bench sweeps and by the
  * launch-shape-independence tests; not needed for correctness. */
 int bdl_set_launch_config(int ctas_per_sm, int unroll, int threads);
 
@@ -152,7 +152,7 @@ int bdl_moments_welford(const float* theta_dev, float* mean_dev, float* m2_dev, 
  * bulk copies (cp.async.bulk global->shared->global).  Replaces theta_vec.clone() into a dict
  * (methods/csgld.py:278-279). */
 int bdl_capture_ring(const float* theta_dev, float* ring_dev, uint64_t slot, uint64_t n, void* stream);
-/* Tuning: 16 KiB chunks copied by one CTA of the ring kernel (default 8). */
+/* Tuning: 16 KiB chunks copied by one CTA of the ring kernel (default 4). */
 int bdl_set_ring_config(int chunks_per_cta);
 
 /* (a9) Posterior draw theta_s = mean + sqrt(var) * eps (methods/sgld.py:292-297, csgld.py:404-413).

@@ -128,10 +128,10 @@ def main():
             ("posterior draw (philox)", 12, lambda: ops.draw(buf["theta"], buf["s"], buf["b"], ops.VAR_FROM_MOMENTS, 1.1,
                                                             ops.make_noise(seed=1, subseq=3, stream_id=1))),
             ("sample-ring TMA copy", 8, lambda: ops.capture_ring(buf["theta"], ring, 0)),
-            ("sample-ring TMA copy per_cta=4", 8, lambda: (ops.set_ring_config(4), ops.capture_ring(buf["theta"], ring, 0))),
+            ("sample-ring TMA copy per_cta=2", 8, lambda: (ops.set_ring_config(2), ops.capture_ring(buf["theta"], ring, 0))),
+            ("sample-ring TMA copy per_cta=8", 8, lambda: (ops.set_ring_config(8), ops.capture_ring(buf["theta"], ring, 0))),
             ("sample-ring TMA copy per_cta=16", 8, lambda: (ops.set_ring_config(16), ops.capture_ring(buf["theta"], ring, 0))),
-            ("sample-ring TMA copy per_cta=64", 8, lambda: (ops.set_ring_config(64), ops.capture_ring(buf["theta"], ring, 0))),
-            ("sample-ring TMA copy per_cta=512", 8, lambda: (ops.set_ring_config(512), ops.capture_ring(buf["theta"], ring, 0))),
+            ("sample-ring TMA copy per_cta=4 (default)", 8, lambda: (ops.set_ring_config(4), ops.capture_ring(buf["theta"], ring, 0))),
             ("torch copy_ (reference point for the peak)", 8, lambda: buf["b"].copy_(buf["theta"]))]
     for tag, bpp, fn in rows:
         if not want(tag):
