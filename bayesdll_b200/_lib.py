@@ -51,7 +51,7 @@ _U64, _U32, _I32, _F, _D = C.c_uint64, C.c_uint32, C.c_int, C.c_float, C.c_doubl
 # tests/test_abi.py checks against include/bdl.h.
 SIGNATURES = {
     "bdl_set_launch_config": [_I32, _I32, _I32],
-    "bdl_step": [_I32, _P, _P, _P, _P, _P, _P, _P, _U64, _P, _U32, C.POINTER(Scalars), C.POINTER(Noise), _P],
+    "bdl_step": [_I32, _P, _P, _P, _P, _P, _P, _P, _U64, _P, _U32, _P, C.POINTER(Scalars), C.POINTER(Noise), _P],
     "bdl_philox_normal": [_P, _U64, _U64, _U32, _U64, _P],
     "bdl_moments_avg": [_P, _P, _P, _U64, _F, _F, _I32, _I32, _P],
     "bdl_moments_welford": [_P, _P, _P, _U64, _F, _I32, _I32, _P],

@@ -22,6 +22,8 @@
 
 namespace bdl {
 
+constexpr int kInlineRuns = 8;
+
 struct StepParams {
     float* theta;
     const float* g;
@@ -33,6 +35,9 @@ struct StepParams {
     const float* xi;
     const bdl_run* runs;
     uint32_t nruns;
+    uint32_t inl_n;            // > 0: the run table is small and has no gradient pointers -> inlined below (constant bank)
+    uint32_t inl_end4[kInlineRuns];
+    uint32_t inl_cls[kInlineRuns];
     uint32_t n4;       // one past the last float4 group to process
     uint32_t q_begin;  // first float4 group to process (0 except for chunked host-buffer steps)
     // scalars (already rounded to fp32 by the host)
@@ -218,7 +223,24 @@ step_kernel(const StepParams p) {
                 if constexpr (!kPhilox) xi[u] = ld_stream(p.xi + i);
             }
         }
-        // ---- 2. element class / gradient pointer from the run table (L1-resident), then the gradient loads ----
+        // ---- 2. element class / gradient pointer, then the gradient loads ----
+        if (p.inl_n) {
+            // small merged table (e.g. body | head): classes come from the kernel arguments, no table loads at all
+#pragma unroll
+            for (int u = 0; u < kU; ++u) {
+                const uint32_t q = q0 + u * kT;
+                if (act[u]) {
+                    uint32_t c = p.inl_cls[0];
+#pragma unroll
+                    for (int r = 1; r < kInlineRuns; ++r)
+                        if (r < static_cast<int>(p.inl_n) && q >= p.inl_end4[r - 1]) c = p.inl_cls[r];
+                    cls[u] = c;
+                    g[u] = ld_stream(p.g + (static_cast<uint64_t>(q) << 2));
+                    act[u] = (c & BDL_CLS_SKIP) == 0;
+                }
+            }
+        } else {
+        // run table in device memory (L1-resident after the first CTA of an SM touched it)
         if (!have_cursor) {                                // all lanes take part (ballot); start from the warp's first group
             const uint32_t qw = __shfl_sync(0xFFFFFFFFu, q0, 0);
             cursor_load(cur, p, cursor_find_warp(p, qw < p.n4 ? qw : p.n4 - 1));
@@ -240,6 +262,7 @@ step_kernel(const StepParams p) {
                 }
                 act[u] = (cur.cls & BDL_CLS_SKIP) == 0;     // p.grad is None -> tensor left untouched
             }
+        }
         }
         // ---- 3. compute + store ----
 #pragma unroll
@@ -333,11 +356,13 @@ namespace bdl {
 // Update the float4 groups [q_begin, q_end) of the flat state; all pointers are the bases of the full buffers,
 // so Philox counters and the run table keep their absolute indexing (results do not depend on chunking).
 int step_range(int variant, float* theta, const float* g, const float* theta0, float* v, float* m, float* s, float* buf,
-               uint64_t n, uint64_t q_begin, uint64_t q_end, const bdl_run* runs, uint32_t nruns, const bdl_scalars* sc,
-               const bdl_noise* nz, cudaStream_t st) {
+               uint64_t n, uint64_t q_begin, uint64_t q_end, const bdl_run* runs, uint32_t nruns, const bdl_run* runs_host,
+               const bdl_scalars* sc, const bdl_noise* nz, cudaStream_t st) {
     BDL_REQUIRE(variant >= BDL_SGLD && variant <= BDL_ADAM_CSGHMC, BDL_ERR_INVALID, "bdl_step: unknown variant %d", variant);
     if (n == 0 || q_begin >= q_end) return BDL_OK;   // empty state / empty range: nothing to do (pointers may be null)
-    BDL_REQUIRE(theta && runs && sc && nz, BDL_ERR_INVALID, "bdl_step: null theta/runs/scalars/noise");
+    BDL_REQUIRE(theta && (runs || runs_host) && sc && nz, BDL_ERR_INVALID, "bdl_step: null theta/runs/scalars/noise");
+    BDL_REQUIRE(runs || nruns <= static_cast<uint32_t>(kInlineRuns), BDL_ERR_INVALID,
+                "bdl_step: a device run table is required for more than %d runs", kInlineRuns);
     BDL_REQUIRE(n % 4 == 0, BDL_ERR_INVALID, "bdl_step: n=%llu is not a multiple of 4", (unsigned long long)n);
     BDL_REQUIRE((n >> 2) < 0xFFFFFFFFull, BDL_ERR_INVALID, "bdl_step: n too large for 32-bit group index");
     BDL_REQUIRE(q_end <= (n >> 2), BDL_ERR_INVALID, "bdl_step: range end beyond n");
@@ -355,6 +380,18 @@ int step_range(int variant, float* theta, const float* g, const float* theta0, f
     StepParams p{};
     p.theta = theta; p.g = g; p.theta0 = theta0; p.v = v; p.m = m; p.s = s; p.buf = buf;
     p.xi = nz->xi_dev; p.runs = runs; p.nruns = nruns;
+    p.inl_n = 0;
+    if (runs_host && nruns <= static_cast<uint32_t>(kInlineRuns) && g) {
+        bool plain = true;
+        for (uint32_t r = 0; r < nruns; ++r) plain = plain && runs_host[r].g_dev == nullptr;
+        if (plain) {
+            p.inl_n = nruns;
+            for (uint32_t r = 0; r < nruns; ++r) {
+                p.inl_end4[r] = static_cast<uint32_t>(runs_host[r].end >> 2);
+                p.inl_cls[r] = runs_host[r].cls;
+            }
+        }
+    }
     p.n4 = static_cast<uint32_t>(q_end); p.q_begin = static_cast<uint32_t>(q_begin);
     for (int h = 0; h < 2; ++h) {
         p.lr[h] = sc->lr[h];
@@ -393,8 +430,8 @@ int step_range(int variant, float* theta, const float* g, const float* theta0, f
 }  // namespace bdl
 
 extern "C" int bdl_step(int variant, float* theta, const float* g, const float* theta0, float* v, float* m,
-                        float* s, float* buf, uint64_t n, const bdl_run* runs, uint32_t nruns,
+                        float* s, float* buf, uint64_t n, const bdl_run* runs, uint32_t nruns, const bdl_run* runs_host,
                         const bdl_scalars* sc, const bdl_noise* nz, void* stream) {
-    return bdl::step_range(variant, theta, g, theta0, v, m, s, buf, n, 0, n >> 2, runs, nruns, sc, nz,
+    return bdl::step_range(variant, theta, g, theta0, v, m, s, buf, n, 0, n >> 2, runs, nruns, runs_host, sc, nz,
                            static_cast<cudaStream_t>(stream));
 }

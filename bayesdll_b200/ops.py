@@ -94,6 +94,7 @@ def upload_runs(run_array, device, out=None):
     if out is None or out.numel() < nbytes:
         out = torch.empty(nbytes, dtype=torch.uint8, device=device)
     out[:nbytes].copy_(host, non_blocking=False)
+    out._bdl_host = run_array          # host copy rides along: lets bdl_step inline small tables into the kernel arguments
     return out, len(run_array)
 
 
@@ -120,7 +121,7 @@ def step(variant, theta, g, theta0, v, m, s, buf, runs_dev, nruns, scalars, nois
         int(variant), _ptr(theta, "theta"), _ptr(g, "g", allow_none=True), _ptr(theta0, "theta0", allow_none=True),
         _ptr(v, "v", allow_none=True), _ptr(m, "m", allow_none=True), _ptr(s, "s", allow_none=True),
         _ptr(buf, "buf", allow_none=True), n, _ptr(runs_dev, "runs", torch.uint8), nruns,
-        C.byref(scalars), C.byref(noise), _stream())
+        getattr(runs_dev, "_bdl_host", None), C.byref(scalars), C.byref(noise), _stream())
     _lib.check(rc, "bdl_step")
 
 

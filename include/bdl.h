@@ -124,10 +124,13 @@ int bdl_set_launch_config(int ctas_per_sm, int unroll, int threads);
  *   theta, v, m, s, buf: updated in place.  g / theta0: read only.
  *   Unused state for a variant may be NULL (v: SGLD; m,s: non-Adam; buf: mu == 0; theta0: cSGHMC).
  *   g_dev may be NULL iff every run carries its own g_dev.
- *   runs_dev: DEVICE array of nruns bdl_run (<= BDL_MAX_RUNS). */
+ *   runs_dev: DEVICE array of nruns bdl_run (<= BDL_MAX_RUNS).
+ *   runs_host: optional HOST copy of the same table (may be NULL).  Tables of <= 8 runs without per-run gradient
+ *   pointers (the usual body | head split) are then passed inside the kernel arguments, which removes every table
+ *   load from the kernel; runs_dev may be NULL in that case. */
 int bdl_step(int variant, float* theta_dev, const float* g_dev, const float* theta0_dev,
              float* v_dev, float* m_dev, float* s_dev, float* buf_dev, uint64_t n,
-             const bdl_run* runs_dev, uint32_t nruns, const bdl_scalars* scalars,
+             const bdl_run* runs_dev, uint32_t nruns, const bdl_run* runs_host, const bdl_scalars* scalars,
              const bdl_noise* noise, void* stream);
 
 /* Fill out[0..n) with exactly the N(0,1) stream the step / draw kernels use for (seed, stream_id,
