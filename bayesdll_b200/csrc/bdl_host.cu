@@ -23,7 +23,7 @@ struct bdl_chain {
 
 namespace {
 constexpr int kGrad = 6;
-constexpr uint64_t kDefaultChunk = 16ull << 20;   // 16 Mi elements = 64 MiB per direction per chunk
+constexpr uint64_t kDefaultChunk = 8ull << 20;    // 8 Mi elements = 32 MiB per direction per chunk (best of the sweep in profiles/r01_e2e_chunks.log)
 
 bool needs(int variant, int which, bool has_mu) {
     switch (which) {

@@ -218,7 +218,7 @@ int bdl_calibrate(const float* logits_dev, const int64_t* labels_dev, uint64_t N
 typedef struct bdl_chain bdl_chain;
 enum { BDL_BUF_THETA = 0, BDL_BUF_THETA0 = 1, BDL_BUF_V = 2, BDL_BUF_M = 3, BDL_BUF_S = 4, BDL_BUF_SGD = 5 };
 
-/* n: padded-flat length; chunk_elems: pipeline chunk (0 = default 16 Mi elements). */
+/* n: padded-flat length; chunk_elems: pipeline chunk (0 = default 8 Mi elements). */
 int bdl_chain_create(uint64_t n, int variant, int with_sgd_momentum, uint64_t chunk_elems, bdl_chain** out);
 int bdl_chain_destroy(bdl_chain* chain);
 int bdl_chain_upload(bdl_chain* chain, int which, const float* host);     /* synchronous */

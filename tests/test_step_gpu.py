@@ -158,3 +158,30 @@ def test_step_empty_and_argument_errors(cuda_device):
     with pytest.raises(_lib.BdlError, match="CUDA tensor"):
         ops.step(_lib.SGHMC, torch.zeros(8), z(8), z(8), z(8), None, None, None, runs_dev, nruns, sc,
                  ops.make_noise(seed=1))
+
+
+@pytest.mark.parametrize("bias_mode", ["informative", "uninformative"])
+def test_inline_run_table_equals_device_run_table(cuda_device, bias_mode):
+    """Tables of <= 8 runs ride in the kernel arguments when the host copy is supplied; the device-table path (warp
+    search + cursor) must give the same bits.  Also covers a head run that starts in the middle of a warp's tile."""
+    from bayesdll_b200 import _lib, ops
+    from bayesdll_b200.flat import FlatLayout
+    lay = FlatLayout([("b.0.weight", (70_001,)), ("b.0.bias", (13,)), ("b.1.weight", (333,)), ("b.1.bias", (5,)),
+                      ("classifier.weight", (37, 11)), ("classifier.bias", (37,))], "classifier")
+    n = lay.n_padded
+    tab = lay.run_table(bias_mode)
+    assert len(tab) <= 8
+    gen = torch.Generator(device=cuda_device).manual_seed(0)
+    init = {k: torch.randn(n, device=cuda_device, generator=gen) * sc for k, sc in
+            dict(theta=0.1, g=0.05, theta0=0.1, v=0.01).items()}
+    sc = ops.make_scalars(_lib.SGHMC, lr_body=1e-3, lr_head=1e-2, ND=1840, Ninflate=10.0, alpha=0.18)
+    outs = []
+    for use_host in (True, False):
+        runs_dev, nruns = ops.upload_runs(tab, cuda_device)
+        if not use_host:
+            del runs_dev._bdl_host
+        st = {k: v.clone() for k, v in init.items()}
+        ops.step(_lib.SGHMC, st["theta"], st["g"], st["theta0"], st["v"], None, None, None, runs_dev, nruns, sc,
+                 ops.make_noise(seed=5, subseq=2))
+        outs.append(st)
+    assert torch.equal(outs[0]["theta"], outs[1]["theta"]) and torch.equal(outs[0]["v"], outs[1]["v"])
