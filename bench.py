@@ -514,6 +514,8 @@ def run_reference(args):
 
 
 def main():
+    # NCCL prints its version banner / debug lines to stdout by default; rank 0's stdout must carry the JSON line only
+    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=300)

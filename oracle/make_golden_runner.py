@@ -83,6 +83,86 @@ class InjectCriterion:
         return F.cross_entropy(out, y)
 
 
+class RealNet(nn.Module):
+    """A real little conv net with BatchNorm (buffers are not sampled, Appendix B.12) trained through ordinary
+    autograd -- no gradient injection.  Used for the end-to-end goldens ``runner_real_*``: the reference runs it on CPU,
+    the drop-in on the GPU, so gradients differ at the 1e-7 level and results are compared with a tolerance."""
+    readout_name = "classifier"
+
+    def __init__(self, seed):
+        super().__init__()
+        torch.manual_seed(seed)
+        self.features = nn.Sequential(nn.Conv2d(1, 6, 3, padding=1), nn.BatchNorm2d(6), nn.ReLU(), nn.MaxPool2d(2),
+                                      nn.Conv2d(6, 8, 3, padding=1, bias=False), nn.BatchNorm2d(8), nn.ReLU())
+        self.classifier = nn.Linear(8 * 2 * 2, K_CLASSES)
+
+    def forward(self, x):
+        return self.classifier(self.features(x).flatten(1))
+
+
+REAL_CASES = {
+    "real_sghmc": ("sghmc", dict(prior_sig=1.0, Ninflate=10.0, nd=0.3, burnin=1, thin=1, nst=3, bias="informative",
+                                 momentum_decay=0.18), dict(momentum=0.5, epochs=3)),
+    "real_csghmc": ("csghmc", dict(prior_sig=0.05, Ninflate=5.0, nd=0.3, burnin=0, thin=1, nst=2, bias="informative",
+                                   momentum_decay=0.18), dict(momentum=0.0, epochs=4, num_cycles=2)),
+    "real_adam_csghmc": ("adam_csghmc", dict(prior_sig=1.0, Ninflate=10.0, nd=0.3, burnin=0, thin=1, nst=2,
+                                             bias="uninformative", momentum_decay=0.1, beta1=0.9, beta2=0.99,
+                                             epsilon=1e-3, temperature=1.0), dict(momentum=0.0, epochs=4, num_cycles=2)),
+}
+
+
+def run_reference_real_case(name):
+    method, hp, over = REAL_CASES[name]
+    mod = refshim.load(f"methods.{method}")
+    seed = 900 + sorted(REAL_CASES).index(name)
+    rng = np.random.default_rng(seed)
+    loaders = make_loaders(seed)
+    tape = rng.standard_normal(200_000).astype(np.float32)
+    net, net0 = RealNet(seed), RealNet(seed + 1)
+    log_dir = tempfile.mkdtemp(prefix="bdl_golden_real_")
+    args = make_args(hp, log_dir, torch.device("cpu"), lr=2e-2, lr_head=5e-2, **over)
+    logger = logging.getLogger(f"golden.{name}")
+    logger.addHandler(logging.NullHandler())
+    logger.propagate = False
+    runner = mod.Runner(net, net0, args, logger)
+    evals = []
+    orig_eval = runner.evaluate
+
+    def recording_eval(loader):
+        res = orig_eval(loader)
+        evals.append(res)
+        return res
+    runner.evaluate = recording_eval
+    cwd = os.getcwd()
+    os.chdir(log_dir)
+    try:
+        with refshim.injected_noise(tape) as tp:
+            ret = runner.train(loaders[0], loaders[1], loaders[2])
+            used = tp.pos
+    finally:
+        os.chdir(cwd)
+    rec = dict(tape=tape[:used], tape_used=used, n_evals=len(evals), method=np.array(method),
+               theta_final=torch.cat([p.detach().reshape(-1) for p in runner.net.parameters()]).numpy(),
+               bn_mean=runner.net.features[1].running_mean.numpy().copy(),
+               bn_var=runner.net.features[1].running_var.numpy().copy(), **loaders_to_arrays(loaders))
+    for i, (loss, err, targets, logits, logits_all) in enumerate(evals):
+        rec[f"eval{i}_loss"], rec[f"eval{i}_err"] = loss, err
+        rec[f"eval{i}_targets"], rec[f"eval{i}_logits"] = targets, logits
+    if hasattr(runner, "post_theta_mom1"):
+        rec["post_theta_mom1"] = runner.post_theta_mom1.numpy()
+        rec["post_theta_mom2"] = runner.post_theta_mom2.numpy()
+        rec["post_theta_cnt"] = runner.post_theta_cnt
+    if hasattr(runner, "cycle_theta_mom1"):
+        cyc = sorted(runner.cycle_theta_mom1)
+        rec["cycles"] = np.array(cyc)
+        for c in cyc:
+            rec[f"cyc{c}_mom1"] = runner.cycle_theta_mom1[c].numpy()
+            rec[f"cyc{c}_count"] = runner.samples_per_cycle[c]
+            rec[f"cyc{c}_lik"] = np.asarray(runner.cycle_likelihoods[c], dtype=np.float64)
+        rec["losses_train"] = ret["losses_train"]
+    return rec
+
+
 def make_loaders(seed, n_train=3, n_val=2, n_test=2):
     rng = np.random.default_rng(seed)
 
@@ -232,5 +312,9 @@ def main(save):
     torch.set_num_threads(1)
     for name in CASES:
         rec = run_reference_case(name)
+        save(f"runner_{name}", **rec)
+        print(f"  {name}: tape used {rec['tape_used']}, evaluate() calls {rec['n_evals']}")
+    for name in REAL_CASES:
+        rec = run_reference_real_case(name)
         save(f"runner_{name}", **rec)
         print(f"  {name}: tape used {rec['tape_used']}, evaluate() calls {rec['n_evals']}")

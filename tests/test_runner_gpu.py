@@ -226,3 +226,56 @@ def test_csgld_full_sample_uses_hbm_ring(cuda_device, tmp_path):
     # trajectory unchanged by the capture
     got = runner._dense(runner.model.chain.theta).cpu().numpy()
     assert np.array_equal(got.view(np.uint32), z["theta_final"].view(np.uint32))
+
+
+@pytest.mark.parametrize("name", ["real_sghmc", "real_csghmc", "real_adam_csghmc"])
+def test_runner_real_network_end_to_end(cuda_device, tmp_path, name):
+    """A real conv + BatchNorm network trained through ordinary autograd: the reference on CPU (recorded) vs the drop-in
+    on the GPU, both fed the same noise tape.  Gradients come from different conv implementations (1e-7-level
+    differences), so trajectories are compared with a tolerance instead of bit-for-bit."""
+    import importlib
+    from oracle import make_golden_runner as mgr
+    from oracle import refshim
+    z = np.load(gu.golden_path(f"runner_{name}"), allow_pickle=False)
+    method, hp, over = mgr.REAL_CASES[name]
+    seed = 900 + sorted(mgr.REAL_CASES).index(name)
+    net, net0 = mgr.RealNet(seed), mgr.RealNet(seed + 1)
+    args = mgr.make_args(dict(hp, noise="torch", div="ieee"), str(tmp_path), cuda_device, lr=2e-2, lr_head=5e-2, **over)
+    runner = importlib.import_module(f"bayesdll_b200.methods.{method}").Runner(net, net0, args, _logger())
+    evals = []
+    orig = runner.evaluate
+
+    def rec(loader):
+        r = orig(loader)
+        evals.append(r)
+        return r
+    runner.evaluate = rec
+    cwd = os.getcwd()
+    os.chdir(tmp_path)
+    try:
+        with refshim.injected_noise(z["tape"]) as tape:
+            ret = runner.train(*mgr.loaders_from_arrays(z))
+    finally:
+        os.chdir(cwd)
+    assert tape.pos == int(z["tape_used"])
+    theta = runner._dense(runner.model.chain.theta).cpu().numpy()
+    assert gu.max_rel(theta, z["theta_final"]) <= 2e-4, gu.max_rel(theta, z["theta_final"])
+    # BatchNorm running statistics are buffers: updated by the forward passes, never sampled (Appendix B.12)
+    np.testing.assert_allclose(runner.net.features[1].running_mean.cpu().numpy(), z["bn_mean"], rtol=1e-4, atol=1e-6)
+    np.testing.assert_allclose(runner.net.features[1].running_var.cpu().numpy(), z["bn_var"], rtol=1e-4, atol=1e-6)
+    if "post_theta_mom1" in z.files:
+        assert runner.post_theta_cnt == int(z["post_theta_cnt"])
+        assert gu.max_rel(runner.post_theta_mom1.cpu().numpy(), z["post_theta_mom1"]) <= 2e-4
+        assert gu.max_rel(runner.post_theta_mom2.cpu().numpy(), z["post_theta_mom2"]) <= 4e-4
+    if "cycles" in z.files:
+        assert sorted(runner.cycle_theta_mom1) == z["cycles"].tolist()
+        for c in z["cycles"].tolist():
+            assert runner.samples_per_cycle[c] == int(z[f"cyc{c}_count"])
+            assert gu.max_rel(runner.cycle_theta_mom1[c].cpu().numpy(), z[f"cyc{c}_mom1"]) <= 2e-4
+            np.testing.assert_allclose(runner.cycle_likelihoods[c], z[f"cyc{c}_lik"], rtol=2e-3)
+        np.testing.assert_allclose(ret["losses_train"], z["losses_train"], rtol=1e-3, atol=1e-4)
+    assert len(evals) == int(z["n_evals"])
+    for i, (loss, err, targets, logits, _) in enumerate(evals):
+        assert np.array_equal(targets, z[f"eval{i}_targets"])
+        np.testing.assert_allclose(logits, z[f"eval{i}_logits"], atol=5e-3, rtol=5e-3)
+        assert abs(loss - float(z[f"eval{i}_loss"])) <= 5e-3
