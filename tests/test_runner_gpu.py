@@ -279,3 +279,51 @@ def test_runner_real_network_end_to_end(cuda_device, tmp_path, name):
         assert np.array_equal(targets, z[f"eval{i}_targets"])
         np.testing.assert_allclose(logits, z[f"eval{i}_logits"], atol=5e-3, rtol=5e-3)
         assert abs(loss - float(z[f"eval{i}_loss"])) <= 5e-3
+
+
+@pytest.mark.parametrize("name", ["sghmc", "adam_sghmc", "sgld", "csghmc"])
+def test_checkpoint_roundtrip(cuda_device, tmp_path, name):
+    """save_ckpt -> load_ckpt restores what the reference restores (moments, prior_sig, sampler state dicts, optimizer
+    state incl. the SGD momentum buffer living in the flat buffer) and keeps the reference's quirk
+    post_theta_cnt = epoch (Appendix B.11)."""
+    import importlib
+    from oracle import make_golden_runner as mgr
+    z, runner, _, _, _ = _run(name, cuda_device, tmp_path)
+    method = mgr.CASES[name][0]
+    cyclical = hasattr(runner, "_cyc1")
+    ck_path = runner.save_ckpt(7)
+    ck = torch.load(ck_path, map_location="cpu", weights_only=False)
+    # a fresh runner of the same kind, state initialised by one step so the flat buffers exist
+    seed = 500 + sorted(mgr.CASES).index(name)
+    hp = dict(mgr.CASES[name][1], noise="philox")
+    args = mgr.make_args(hp, str(tmp_path), cuda_device, **mgr.CASES[name][2])
+    fresh = importlib.import_module(f"bayesdll_b200.methods.{method}").Runner(mgr.InjectNet(seed, z["G"]), mgr.InjectNet(seed + 1),
+                                                                              args, _logger())
+    fresh.criterion = mgr.InjectCriterion()
+    x, y = mgr.loaders_from_arrays(z)[0][0]
+    fresh.net.train()
+    fresh.model(x.to(cuda_device), y.to(cuda_device), fresh.net, fresh.net0, fresh.criterion,
+                [pg["lr"] for pg in fresh.optimizer.param_groups], fresh.Ninflate, fresh.nd)
+    epoch = fresh.load_ckpt(ck_path)
+    assert epoch == 7
+    if cyclical:
+        assert sorted(fresh.cycle_theta_mom1) == sorted(runner.cycle_theta_mom1)
+        for c in runner.cycle_theta_mom1:
+            assert torch.equal(fresh.cycle_theta_mom1[c], runner.cycle_theta_mom1[c])
+            assert torch.equal(fresh.cycle_theta_mom2[c], runner.cycle_theta_mom2[c])
+        assert fresh.samples_per_cycle == runner.samples_per_cycle and fresh.current_cycle == runner.current_cycle
+        return
+    assert torch.equal(fresh.post_theta_mom1, runner.post_theta_mom1)
+    assert torch.equal(fresh.post_theta_mom2, runner.post_theta_mom2)
+    assert fresh.post_theta_cnt == 7                      # the reference's quirk: count overwritten by the epoch
+    if "momentum_buffer" in ck:
+        for k, v in runner.model.momentum_buffer.items():
+            assert torch.equal(fresh.model.momentum_buffer[k], v)
+    if "m" in ck:
+        for k in runner.model.m:
+            assert torch.equal(fresh.model.m[k], runner.model.m[k]) and torch.equal(fresh.model.v[k], runner.model.v[k])
+        assert fresh.model.t == runner.model.t
+    if runner.model.chain.buf is not None:                # SGD momentum buffer restored into the flat buffer
+        assert torch.equal(fresh.model.chain.buf, runner.model.chain.buf)
+        p0 = fresh.model.chain.params[0]
+        assert fresh.optimizer.state[p0]["momentum_buffer"].data_ptr() == fresh.model.chain.layout.views(fresh.model.chain.buf)[0].data_ptr()
