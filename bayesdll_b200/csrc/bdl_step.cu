@@ -147,7 +147,6 @@ struct Uses {
     static constexpr bool adam = (kVariant == BDL_ADAM_SGHMC || kVariant == BDL_ADAM_CSGHMC);
 };
 
-constexpr int kDefaultThreads = 128;
 constexpr int kDefaultUnroll = 1;
 
 // Resident CTAs per SM the kernel is compiled for: 16 data registers per stream per unroll step plus ~28 registers of

@@ -7,7 +7,6 @@ are ordinary elements that carry g = 0 and theta0 = 0 and are never visible thro
 
 Only host logic lives here (offsets, run tables, views); it is importable without CUDA.
 """
-import ctypes
 from dataclasses import dataclass
 from typing import List, Sequence
 

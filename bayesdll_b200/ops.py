@@ -6,14 +6,12 @@ conventions"), launches asynchronously on the caller's current CUDA stream and r
 a non-zero status.  There is no CPU implementation: CPU tensors are rejected.
 """
 import ctypes as C
-import math
 
 import numpy as np
 import torch
 
 from . import _lib
-from ._lib import (ADAM_CSGHMC, ADAM_SGHMC, CSGHMC, DIV_IEEE, DIV_RECIP, SGHMC, SGLD, STREAM_DRAW, STREAM_STEP,
-                   STREAM_USER, BdlError, Noise, Run, Scalars)
+from ._lib import ADAM_SGHMC, CSGHMC, DIV_RECIP, SGHMC, SGLD, STREAM_STEP, STREAM_USER, BdlError, Noise, Scalars
 
 __all__ = ["make_scalars", "upload_runs", "step", "philox_normal", "moments_avg", "moments_welford",
            "capture_ring", "draw", "ensemble", "ce_err", "lse_accum", "lse_rescale", "lse_finalize", "calibrate",

@@ -384,7 +384,6 @@ def ensemble_extra(device, rank, world, args):
 # ------------------------------------------------------------------------------------------------------------
 def cpu_port_rate(lay, seconds=15.0, with_eager=False, n_limit=None, steps=None, warmup=1):
     """Time the fused C/OpenMP port of the reference path on the host cores (bounded sample)."""
-    import ctypes as C
     from bayesdll_b200 import _lib
     from oracle import c_oracle
     c_oracle.build()

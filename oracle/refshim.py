@@ -18,7 +18,6 @@ import os
 import sys
 import types
 
-import numpy as np
 import torch
 import torch.nn as nn
 
