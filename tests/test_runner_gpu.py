@@ -324,6 +324,6 @@ def test_checkpoint_roundtrip(cuda_device, tmp_path, name):
             assert torch.equal(fresh.model.m[k], runner.model.m[k]) and torch.equal(fresh.model.v[k], runner.model.v[k])
         assert fresh.model.t == runner.model.t
     if runner.model.chain.buf is not None:                # SGD momentum buffer restored into the flat buffer
-        assert torch.equal(fresh.model.chain.buf, runner.model.chain.buf)
+        assert torch.equal(fresh._dense(fresh.model.chain.buf), runner._dense(runner.model.chain.buf))   # padding is not part of a ckpt
         p0 = fresh.model.chain.params[0]
         assert fresh.optimizer.state[p0]["momentum_buffer"].data_ptr() == fresh.model.chain.layout.views(fresh.model.chain.buf)[0].data_ptr()
