@@ -22,7 +22,7 @@ NVCC_FLAGS = [
     "--fmad=false",                     # no implicit contraction: fused ops are written explicitly (__fmaf_rn)
     "-Xcompiler", "-fPIC",
     "-I", os.path.join(ROOT, "include"),
-]
+] + os.environ.get("BDL_EXTRA_NVCC_FLAGS", "").split()
 
 
 def _nvcc():

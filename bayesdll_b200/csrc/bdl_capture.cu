@@ -10,11 +10,14 @@
 
 namespace bdl {
 
-constexpr int kCapThreads = 128;
+#ifndef BDL_CAP_THREADS
+#define BDL_CAP_THREADS 128
+#endif
+constexpr int kCapThreads = BDL_CAP_THREADS;
 constexpr int kCapU = 1;
 
 template <int kDiv, bool kInit, bool kHasMom2>
-__global__ void __launch_bounds__(kCapThreads, 8)
+__global__ void __launch_bounds__(kCapThreads, 1024 / kCapThreads)
 moments_avg_kernel(const float* __restrict__ theta, float* __restrict__ mom1, float* __restrict__ mom2, uint32_t n4,
                    float cnt, float cntp1, float inv_cntp1) {
     const uint32_t tile_groups = kCapThreads * kCapU;
@@ -62,7 +65,7 @@ moments_avg_kernel(const float* __restrict__ theta, float* __restrict__ mom1, fl
 }
 
 template <int kDiv, bool kInit>
-__global__ void __launch_bounds__(kCapThreads, 8)
+__global__ void __launch_bounds__(kCapThreads, 1024 / kCapThreads)
 moments_welford_kernel(const float* __restrict__ theta, float* __restrict__ mean, float* __restrict__ M2, uint32_t n4,
                        float nf, float inv_nf) {
     const uint32_t tile_groups = kCapThreads * kCapU;

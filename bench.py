@@ -49,6 +49,16 @@ def env_int(name, default):
     return int(os.environ.get(name, default))
 
 
+def guarded(what, fn, *a, **k):
+    """Extras must never take the headline line down with them: report the failure instead."""
+    try:
+        return fn(*a, **k)
+    except Exception as e:  # noqa: BLE001
+        import traceback
+        traceback.print_exc(file=sys.stderr)
+        return {"error": f"{what}: {type(e).__name__}: {e}"[:300]}
+
+
 def measured_peak():
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
@@ -218,38 +228,13 @@ def run_ours(args):
                 "algorithmic_bytes_per_launch": BYTES_PER_PARAM * n_dense, "kernel_ms": round(kernel_ms, 4)}
 
     # ---- the other update rules on the same state (extra; BASELINE.json configs[1], [3], [4] kernels) ----------
-    variants = {} if args.no_variants else variant_rates(lay, theta, g, theta0, v, runs_dev, nruns, device, world, peak, seed)
+    variants = {} if args.no_variants else guarded("variants", variant_rates, lay, theta, g, theta0, v, runs_dev, nruns, device,
+                                                   world, peak, seed)
 
     # ---- e2e through the host-buffer C ABI ----------------------------------------------------------
     e2e = None
     if not args.no_e2e:
-        tab = lay.run_table("informative")
-        chain = ops.HostChain(n, _lib.SGHMC)
-        stage = torch.empty(n, dtype=torch.float32).pin_memory()
-        stage.copy_(theta)
-        chain.upload(_lib.BUF_THETA, stage)
-        stage.copy_(theta0)
-        chain.upload(_lib.BUF_THETA0, stage)
-        g_host = stage                                       # pinned host gradient (synthetic)
-        g_host.copy_(g)
-        theta_host = torch.empty(n, dtype=torch.float32).pin_memory()
-        Ke = max(3, min(K, args.e2e_steps))
-        for i in range(2):
-            chain.step_host(g_host, theta_host, tab, sc, ops.make_noise(seed=seed, subseq=i))
-        barrier(world)
-        torch.cuda.synchronize()
-        t0 = time.perf_counter()
-        for i in range(Ke):
-            chain.step_host(g_host, theta_host, tab, sc, ops.make_noise(seed=seed, subseq=2 + i))
-        torch.cuda.synchronize()
-        dt = allmax(time.perf_counter() - t0, world, device)
-        assert np.isfinite(theta_host[:1024].numpy()).all()
-        e2e = {"value": world * n_dense * Ke / dt, "unit": "params/s", "h2d_bytes_per_step": 4 * n, "d2h_bytes_per_step": 4 * n,
-               "steps": Ke, "ms_per_step": dt / Ke * 1e3,
-               "api": "bdl_chain_step_host (include/bdl.h): pinned host gradient in, pinned host theta out, "
-                      "theta0/momentum resident in HBM, chunk-pipelined H2D | fused step | D2H"}
-        chain.close()
-        del stage, theta_host, g_host
+        e2e = guarded("e2e", e2e_host_chain, lay, theta, theta0, g, sc, seed, K, args, world, device)
     t_load_end = time.time()
     if rank == 0:
         sampler.stop()
@@ -260,16 +245,16 @@ def run_ours(args):
     if not args.no_train_step:
         del theta, g, theta0, v
         torch.cuda.empty_cache()
-        extras["train_step"] = train_step_extra(device, rank, world)
+        extras["train_step"] = guarded("train_step", train_step_extra, device, rank, world)
     if not args.no_ensemble:
         torch.cuda.empty_cache()
-        extras["ensemble"] = ensemble_extra(device, rank, world, args)
+        extras["ensemble"] = guarded("ensemble", ensemble_extra, device, rank, world, args)
     if rank == 0 and world == 1 and not args.no_eager_gpu:
         torch.cuda.empty_cache()
-        extras["reference_eager_gpu"] = eager_gpu_rate(lay, device)
+        extras["reference_eager_gpu"] = guarded("reference_eager_gpu", eager_gpu_rate, lay, device)
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        cpu_baseline = cpu_port_rate(lay, seconds=args.cpu_seconds, with_eager=True)
+        cpu_baseline = guarded("cpu_baseline", cpu_port_rate, lay, seconds=args.cpu_seconds, with_eager=True)
 
     if rank == 0:
         line = {
@@ -294,6 +279,38 @@ def run_ours(args):
 
 
 # ------------------------------------------------------------------------------------------------------------
+def e2e_host_chain(lay, theta, theta0, g, sc, seed, K, args, world, device):
+    """The same update through the host-buffer C ABI: pinned host gradient in, pinned host theta out, every step."""
+    from bayesdll_b200 import _lib, ops
+    n, n_dense = lay.n_padded, lay.n_dense
+    tab = lay.run_table("informative")
+    chain = ops.HostChain(n, _lib.SGHMC)
+    stage = torch.empty(n, dtype=torch.float32).pin_memory()
+    stage.copy_(theta)
+    chain.upload(_lib.BUF_THETA, stage)
+    stage.copy_(theta0)
+    chain.upload(_lib.BUF_THETA0, stage)
+    g_host = stage                                       # pinned host gradient (synthetic)
+    g_host.copy_(g)
+    theta_host = torch.empty(n, dtype=torch.float32).pin_memory()
+    Ke = max(3, min(K, args.e2e_steps))
+    for i in range(2):
+        chain.step_host(g_host, theta_host, tab, sc, ops.make_noise(seed=seed, subseq=i))
+    barrier(world)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for i in range(Ke):
+        chain.step_host(g_host, theta_host, tab, sc, ops.make_noise(seed=seed, subseq=2 + i))
+    torch.cuda.synchronize()
+    dt = allmax(time.perf_counter() - t0, world, device)
+    assert np.isfinite(theta_host[:1024].numpy()).all()
+    chain.close()
+    return {"value": world * n_dense * Ke / dt, "unit": "params/s", "h2d_bytes_per_step": 4 * n, "d2h_bytes_per_step": 4 * n,
+            "steps": Ke, "ms_per_step": dt / Ke * 1e3,
+            "api": "bdl_chain_step_host (include/bdl.h): pinned host gradient in, pinned host theta out, "
+                   "theta0/momentum resident in HBM, chunk-pipelined H2D | fused step | D2H"}
+
+
 def variant_rates(lay, theta, g, theta0, v, runs_dev, nruns, device, world, peak, seed, steps=30):
     """params/s and roofline fraction of every other fused update rule at ViT-L/32 size (one chain per GPU)."""
     from bayesdll_b200 import _lib, ops
