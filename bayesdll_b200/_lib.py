@@ -11,7 +11,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libbdl.so")
 
 # ---- enums / constants (include/bdl.h) -------------------------------------------------------
-BDL_ABI_VERSION = 1
+BDL_ABI_VERSION = 2
 SGLD, SGHMC, CSGHMC, ADAM_SGHMC, ADAM_CSGHMC = range(5)
 VARIANT_NAMES = {SGLD: "sgld", SGHMC: "sghmc", CSGHMC: "csghmc", ADAM_SGHMC: "adam_sghmc",
                  ADAM_CSGHMC: "adam_csghmc"}
@@ -64,6 +64,8 @@ SIGNATURES = {
     "bdl_lse_rescale": [_P, _P, _P, _U64, _P],
     "bdl_lse_finalize": [_P, _P, _U32, _U32, _F, _F, _I32, _P, _P],
     "bdl_calibrate": [_P, _P, _U64, _U32, _D, _I32, _P, _U32, _P, _P, _P, _P, _P, _P, _P],
+    "bdl_bma_mean": [_P, _U32, _U32, _U32, _P, _P],
+    "bdl_nll_temperature": [_P, _P, _U64, _U32, _D, _P, _P, _P],
     "bdl_chain_create": [_U64, _I32, _I32, _U64, C.POINTER(_P)],
     "bdl_chain_destroy": [_P],
     "bdl_chain_upload": [_P, _I32, _P],

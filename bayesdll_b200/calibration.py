@@ -7,9 +7,9 @@ and return values; the binning / ECE / MCE / NLL reductions run as one CUDA kern
     draw_reliability_plot(...)                                                               :70
 
 Inputs are the numpy arrays the Runners produce (``targets [N] int64``, ``logits [N,K] f32``); CUDA tensors are
-accepted too and avoid the upload.  The reliability plot and the temperature optimiser are host-side
-presentation / scalar optimisation (out of scope for the GPU path); the plot is drawn
-only when matplotlib is importable, exactly the reference's dependency.
+accepted too and avoid the upload.  The temperature optimiser keeps scipy's scalar BFGS driver on the host and
+evaluates its objective on the device (bdl_nll_temperature).  The plots are presentation (SURVEY.md section 2.1
+row 8) and are drawn only when matplotlib is importable, exactly the reference's dependency.
 """
 import numpy as np
 import torch
@@ -132,17 +132,20 @@ def draw_reliability_plot(bins, bin_accs, fig_name, title=None, ece=None, mce=No
 
 
 def find_optimal_temperature(labels, logits, plot_save_path, max_iter=10000):
-    """Temperature scaling on the validation set (calibration.py:123-212): scipy BFGS over the scalar T of the
-    validation NLL.  Host-side scalar optimisation, kept as in the reference (returns the fp64 array ``result.x``)."""
+    """Temperature scaling on the validation set (calibration.py:123-212): scipy's BFGS over the scalar T, exactly the
+    reference's driver (``minimize(fun, np.ones(1), options={'maxiter': max_iter}, callback=...)``, numerical gradient),
+    but every objective evaluation ``mean(logsumexp(logits/T) - (logits/T)[y])`` is ONE fp64 device reduction
+    (bdl_nll_temperature) over logits uploaded once, instead of three host passes over [N,K] per evaluation.
+    Returns ``(result.x, result.success)``: ``result.x`` is the fp64 array the reference returns."""
     import scipy.optimize
-    import scipy.special
-    labels = np.asarray(labels)
-    logits = np.asarray(logits)
-    idx = np.arange(len(labels))
+    lg = _to_dev(logits, torch.float32)
+    lb = _to_dev(labels, torch.int64)
+    row = torch.empty(lg.shape[0], dtype=torch.float64, device=lg.device)
+    out = torch.empty(1, dtype=torch.float64, device=lg.device)
 
     def fun(T):
-        z = logits / T
-        return np.mean(scipy.special.logsumexp(z, axis=1) - z[idx, labels])
+        ops.nll_temperature(lg, lb, float(np.asarray(T, dtype=np.float64).reshape(-1)[0]), row, out)
+        return out.item()
 
     temps, losses = [], []
 
@@ -151,4 +154,34 @@ def find_optimal_temperature(labels, logits, plot_save_path, max_iter=10000):
         losses.append(fun(x))
 
     result = scipy.optimize.minimize(fun, np.ones(1), options={"maxiter": max_iter}, callback=callback)
-    return result.x, result.success
+    success = result.success
+    try:
+        Topt = result.x
+        _draw_temperature_curve(temps, losses, plot_save_path)
+    except Exception:
+        Topt = 1
+    return Topt, success
+
+
+def _draw_temperature_curve(temps, losses, plot_save_path):
+    """Optimisation curve (calibration.py:196-208).  Presentation only; skipped when matplotlib is absent."""
+    if plot_save_path is None:
+        return False
+    try:
+        import matplotlib
+        matplotlib.use("Agg", force=False)
+        import matplotlib.pyplot as plt
+    except Exception:
+        return False
+    fig = plt.figure()
+    plt.subplot(121)
+    plt.plot(list(range(len(temps))), [float(np.asarray(t).reshape(-1)[0]) for t in temps])
+    plt.gca().set_title("Temperature T")
+    plt.gca().set_xlabel("Iterations")
+    plt.subplot(122)
+    plt.plot(list(range(len(losses))), losses)
+    plt.gca().set_title("NLL on validation set")
+    plt.gca().set_xlabel("Iterations")
+    fig.savefig(plot_save_path)
+    plt.close(fig)
+    return True

@@ -145,6 +145,14 @@ class ChainState:
         self.step_count += 1
         self.sgd_steps += 1
 
+    def snapshot(self, flat=None):
+        """Device-side copy of a flat buffer (default theta) taken with ONE TMA ring-copy launch (8 B/param): what
+        checkpoint / cycle-state / raw-sample writers hold while training carries on."""
+        src = self.theta if flat is None else flat
+        out = torch.empty_like(src)
+        ops.capture_ring(src, out.view(1, -1), 0)
+        return out
+
     def reset_momenta(self):
         for t in (self.v, self.m, self.s):
             if t is not None:
@@ -169,11 +177,14 @@ class SampleRing:
     def capacity(self):
         return self.buf.shape[0]
 
-    def capture(self, theta_flat, key, store):
-        """Copy ``theta_flat`` into the next slot; ``store[key]`` becomes the dense view of that slot."""
+    def capture(self, theta_flat, key, store, before_overwrite=None):
+        """Copy ``theta_flat`` into the next slot; ``store[key]`` becomes the dense view of that slot.
+        ``before_overwrite(old_key)`` runs before a wrapped slot is reused (e.g. wait for its spill to disk)."""
         slot = self.count % self.capacity
         old = self.keys[slot]
         if old is not None:
+            if before_overwrite is not None:
+                before_overwrite(old)
             store.pop(old, None)
         ops.capture_ring(theta_flat, self.buf, slot)
         self.keys[slot] = key

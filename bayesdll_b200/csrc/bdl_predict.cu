@@ -262,6 +262,56 @@ calibrate_kernel(const float* __restrict__ logits, const int64_t* __restrict__ l
     }
 }
 
+// -------------------------------------------------------------------------------------------
+// Bayesian model average over stored raw samples (methods/csghmc_fs.py:349-377): logits are summed model by
+// model in fp32 (numpy `all_logits_sum += model_logits`) and divided once by the model count (IEEE).
+// -------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kPredThreads)
+bma_mean_kernel(const float* __restrict__ L, uint32_t total, uint32_t S, float S_f, float* __restrict__ out) {
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+        const float* x = L + static_cast<size_t>(i) * S;
+        float acc = x[0];
+        for (uint32_t s = 1; s < S; ++s) acc = __fadd_rn(acc, x[s]);
+        out[i] = __fdiv_rn(acc, S_f);
+    }
+}
+
+// -------------------------------------------------------------------------------------------
+// Temperature-scaling objective (calibration.py:178-184): nll(T) = mean_i( logsumexp_k(l_ik / T) - l_iy / T ), all in
+// fp64 (T is an fp64 ndarray in the reference, so `logits / T` promotes).  Two launches with a fixed reduction order,
+// so the value is reproducible run to run -- the scipy BFGS driver differentiates it numerically with a 1.5e-8 step.
+// -------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kPredThreads)
+nll_rows_kernel(const float* __restrict__ logits, const int64_t* __restrict__ labels, uint32_t N, uint32_t K, double temp,
+                double* __restrict__ row_nll) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (uint32_t r = blockIdx.x * kPredWarps + warp; r < N; r += gridDim.x * kPredWarps) {
+        const float* row = logits + static_cast<size_t>(r) * K;
+        double mx = -CUDART_INF;
+        for (uint32_t k = lane; k < K; k += 32) mx = fmax(mx, static_cast<double>(row[k]) / temp);
+        mx = warp_max(mx);
+        double sum = 0.0;
+        for (uint32_t k = lane; k < K; k += 32) sum += exp(static_cast<double>(row[k]) / temp - mx);
+        sum = warp_sum(sum);                               // xor-butterfly: same value in every lane, fixed order
+        if (lane == 0) row_nll[r] = (log(sum) + mx) - static_cast<double>(row[labels[r]]) / temp;
+    }
+}
+
+constexpr int kSumThreads = 1024;
+__global__ void __launch_bounds__(kSumThreads)
+mean_f64_kernel(const double* __restrict__ x, uint32_t N, double* __restrict__ out) {
+    __shared__ double s[kSumThreads];
+    double acc = 0.0;
+    for (uint32_t i = threadIdx.x; i < N; i += kSumThreads) acc += x[i];
+    s[threadIdx.x] = acc;
+    __syncthreads();
+    for (int o = kSumThreads / 2; o > 0; o >>= 1) {
+        if (static_cast<int>(threadIdx.x) < o) s[threadIdx.x] += s[threadIdx.x + o];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) out[0] = s[0] / static_cast<double>(N);
+}
+
 static uint32_t rows_grid(uint32_t rows) {
     uint32_t need = (rows + kPredWarps - 1) / kPredWarps;
     uint32_t cap = static_cast<uint32_t>(num_sms() * 4);
@@ -353,4 +403,29 @@ extern "C" int bdl_calibrate(const float* logits, const int64_t* labels, uint64_
                                                                static_cast<float>(temperature), edges, M, bin_size,
                                                                acc_sum, conf_sum, nll_sum, near_edge, binned);
     return check_cuda(cudaGetLastError(), "calibrate_kernel launch");
+}
+
+extern "C" int bdl_bma_mean(const float* logits_all, uint32_t B, uint32_t K, uint32_t S, float* out, void* stream) {
+    using namespace bdl;
+    BDL_REQUIRE(logits_all && out, BDL_ERR_INVALID, "bdl_bma_mean: null pointer");
+    BDL_REQUIRE(K >= 1 && S >= 1, BDL_ERR_INVALID, "bdl_bma_mean: K and S must be >= 1");
+    const uint64_t total = static_cast<uint64_t>(B) * K;
+    BDL_REQUIRE(total < 0xFFFFFFFFull, BDL_ERR_INVALID, "bdl_bma_mean: B*K too large");
+    if (total == 0) return BDL_OK;
+    bma_mean_kernel<<<flat_grid(total), kPredThreads, 0, static_cast<cudaStream_t>(stream)>>>(
+        logits_all, static_cast<uint32_t>(total), S, static_cast<float>(S), out);
+    return check_cuda(cudaGetLastError(), "bma_mean_kernel launch");
+}
+
+extern "C" int bdl_nll_temperature(const float* logits, const int64_t* labels, uint64_t N, uint32_t K, double temperature,
+                                   double* row_nll, double* out_mean, void* stream) {
+    using namespace bdl;
+    BDL_REQUIRE(logits && labels && row_nll && out_mean, BDL_ERR_INVALID, "bdl_nll_temperature: null pointer");
+    BDL_REQUIRE(K >= 1 && N >= 1 && N < 0xFFFFFFFFull, BDL_ERR_INVALID, "bdl_nll_temperature: bad N/K");
+    BDL_REQUIRE(temperature == temperature && temperature != 0.0, BDL_ERR_INVALID, "bdl_nll_temperature: temperature is 0 or NaN");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    nll_rows_kernel<<<rows_grid(static_cast<uint32_t>(N)), kPredThreads, 0, st>>>(logits, labels, static_cast<uint32_t>(N), K,
+                                                                                temperature, row_nll);
+    mean_f64_kernel<<<1, kSumThreads, 0, st>>>(row_nll, static_cast<uint32_t>(N), out_mean);
+    return check_cuda(cudaGetLastError(), "nll_temperature launch");
 }

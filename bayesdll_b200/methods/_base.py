@@ -27,6 +27,7 @@ from tqdm import tqdm
 from .. import _lib, calibration, ops
 from ..chain import ChainState, SampleRing
 from ..flat import adopt_parameters, alloc_flat
+from ..writer import AsyncWriter, FlatBackedStateDict
 from .cyclical import CyclicalSGMCMC
 
 
@@ -219,6 +220,13 @@ class _RunnerCommon:
         self.model.configure(sgd_momentum=mu, seed=self.seed, noise=self.noise_mode,
                              grad_mode=str(hp.get("grad", "table")), div_mode=self.div_mode, optimizer=self.optimizer)
         self._eval_calls = 0
+        # checkpoint / sample writers: 'async' (default) overlaps D2H + serialisation with training, 'sync' behaves like
+        # the reference's in-line torch.save (file complete when save_ckpt returns)
+        self._writer = AsyncWriter(args.device, mode=str(hp.get("io", "async")))
+
+    def flush_io(self):
+        """Block until every checkpoint / sample file submitted so far is on disk."""
+        self._writer.flush()
 
     def _build_model(self, hp):
         raise NotImplementedError
@@ -249,8 +257,18 @@ class _RunnerCommon:
         return fname
 
     def _state_dict_copy(self):
-        """Independent tensors (the live state_dict entries are views of the flat buffer)."""
-        return {k: v.detach().clone() for k, v in self.net.state_dict().items()}
+        """``copy.deepcopy(self.net.state_dict())`` (methods/csgld.py:311) as ONE TMA copy of the flat parameter buffer
+        plus clones of the few buffers (BatchNorm statistics); entries are views of that snapshot."""
+        ch = self._chain()
+        return FlatBackedStateDict.snapshot(self.net, ch.layout, ch.names, ch.snapshot())
+
+    def _dense_for_save(self, flat, mutable):
+        """Dense ``parameters_to_vector``-ordered vector for a writer: a view when the padded layout only differs from
+        the dense one by tail padding and the buffer will not change any more, else a copy."""
+        L = self._chain().layout
+        if not mutable and all(sg.begin == sg.dense_begin for sg in L.segments):
+            return flat[:L.n_dense]
+        return L.to_dense(flat)
 
     def _calibrate_and_log(self, targets_test, logits_test, val, fmt_topt):
         args, logger = self.args, self.logger
@@ -358,6 +376,7 @@ class BurninRunner(_RunnerCommon):
                 if loss_now < best_loss:
                     best_loss = loss_now
                     self._on_best(ep, loss_now, val, test, fmt_topt=lambda T: float(np.asarray(T).reshape(-1)[0]), save_ckpt=True)
+        self.flush_io()
         toc0 = time.time()
         logger.info("Training done! Total time = %f (average per epoch = %f) seconds" %
                     (toc0 - tic0, (toc0 - tic0) / args.epochs))
@@ -461,20 +480,38 @@ class BurninRunner(_RunnerCommon):
         if self.CKPT_HAS_LAST_THETA:
             ck["last_theta"] = self._state_dict_copy()
         ck.update({
-            "post_theta_mom1": self.post_theta_mom1.clone(),
-            "post_theta_mom2": self.post_theta_mom2.clone() if self.nst > 0 else None,
+            "post_theta_mom1": self.post_theta_mom1,       # the property hands out a fresh dense copy (a snapshot)
+            "post_theta_mom2": self.post_theta_mom2 if self.nst > 0 else None,
             "post_theta_cnt": self.post_theta_cnt,
             "prior_sig": self.model.prior_sig,
-            "optimizer": self.optimizer.state_dict(),
+            "optimizer": self._optimizer_state_snapshot(),
         })
         ck.update(self._ckpt_extra())
         ck["epoch"] = epoch
-        torch.save(ck, fname)
+        self._writer.submit(fname, ck)
         return fname
+
+    def _optimizer_state_snapshot(self):
+        """``optimizer.state_dict()`` whose momentum buffers are snapshots (the live ones are views the kernel updates)."""
+        sd = self.optimizer.state_dict()
+        ch = self._chain()
+        if ch.buf is None:
+            return sd
+        snap = ch.layout.views(ch.snapshot(ch.buf))
+        index = {id(p): i for i, p in enumerate(ch.params)}
+        order = [index[id(p)] for g in self.optimizer.param_groups for p in g["params"]]
+        state = {}
+        for k, st in sd["state"].items():
+            st = dict(st)
+            if st.get("momentum_buffer") is not None:
+                st["momentum_buffer"] = snap[order[k]]
+            state[k] = st
+        return {"state": state, "param_groups": sd["param_groups"]}
 
     def load_ckpt(self, ckpt_path):
         """Mirrors the reference incl. its quirk: theta is not restored and the sample count is overwritten with the
         epoch number (Appendix B.11)."""
+        self.flush_io()
         ckpt = torch.load(ckpt_path, map_location=self.args.device, weights_only=False)
         self.post_theta_mom1 = ckpt["post_theta_mom1"]
         if ckpt["post_theta_mom2"] is not None:
@@ -573,6 +610,7 @@ class CyclicalRunner(_RunnerCommon):
                 if loss_now < best_loss:
                     best_loss = loss_now
                     self._on_best(ep, loss_now, val, test, fmt_topt=lambda T: T[0], save_ckpt=False)
+        self.flush_io()
         toc0 = time.time()
         logger.info(f"Training done! Total time = {toc0 - tic0:.4f} (average per epoch = "
                     f"{(toc0 - tic0) / args.epochs:.4f}) seconds")
@@ -660,7 +698,7 @@ class CyclicalRunner(_RunnerCommon):
                         logger.info(f"Cycle {cycle_number} full batch likelihood: {likelihood.mean():.6e}")
                         self.save_ckpt(epoch=sched.current_epoch)
                         if self.STORE_ALL_SAMPLES and getattr(args, "full_sample", False):
-                            torch.save(self.all_samples, "all_samples_TEST.ckpt")   # csgld.py:328-329
+                            self._writer.submit("all_samples_TEST.ckpt", dict(self.all_samples))   # csgld.py:328-329
                         self._after_cycle_completed(cycle_number)
         loss, error = loss_acc.item(), err_acc.item()
         return loss / nb_samples, error / nb_samples, cycle_updated
@@ -818,20 +856,23 @@ class CyclicalRunner(_RunnerCommon):
     # ---- checkpoints (methods/csgld.py:470-506) ----------------------------------------------------------------
     def save_ckpt(self, epoch):
         fname = os.path.join(self.args.log_dir, f"{self.current_cycle}_ckpt.pt")
-        last = self._dense(self._chain().theta).clone() if self.LAST_THETA_AS_VECTOR else self._state_dict_copy()
-        torch.save({
+        last = self._dense(self._chain().theta) if self.LAST_THETA_AS_VECTOR else self._state_dict_copy()
+        # moments of finished cycles never change again: only the newest cycle's buffers are snapshotted
+        newest = max(self._cyc1) if self._cyc1 else None
+        self._writer.submit(fname, {
             "last_theta": last,
-            "cycle_theta_mom1": {c: t.clone() for c, t in self.cycle_theta_mom1.items()},
-            "cycle_theta_mom2": {c: t.clone() for c, t in self.cycle_theta_mom2.items()},
-            "cycle_likelihoods": self.cycle_likelihoods,
-            "cycle_states": self.cycle_states,
+            "cycle_theta_mom1": {c: self._dense_for_save(t, c == newest) for c, t in self._cyc1.items()},
+            "cycle_theta_mom2": {c: self._dense_for_save(t, c == newest) for c, t in self._cyc2.items()},
+            "cycle_likelihoods": dict(self.cycle_likelihoods),
+            "cycle_states": dict(self.cycle_states),
             "epoch": epoch,
             "current_cycle": self.current_cycle,
-            "samples_per_cycle": self.samples_per_cycle,
-        }, fname)
+            "samples_per_cycle": dict(self.samples_per_cycle),
+        })
         return fname
 
     def load_ckpt(self, ckpt_path):
+        self.flush_io()
         ckpt = torch.load(ckpt_path, map_location=self.args.device, weights_only=False)
         self.cycle_theta_mom1 = ckpt.get("cycle_theta_mom1", {})
         self.cycle_theta_mom2 = ckpt.get("cycle_theta_mom2", {})

@@ -14,7 +14,8 @@ from . import _lib
 from ._lib import ADAM_SGHMC, CSGHMC, DIV_RECIP, SGHMC, SGLD, STREAM_STEP, STREAM_USER, BdlError, Noise, Scalars
 
 __all__ = ["make_scalars", "upload_runs", "step", "philox_normal", "moments_avg", "moments_welford",
-           "capture_ring", "draw", "ensemble", "ce_err", "lse_accum", "lse_rescale", "lse_finalize", "calibrate",
+           "capture_ring", "draw", "ensemble", "ce_err", "lse_accum", "lse_rescale", "lse_finalize", "calibrate", "bma_mean",
+           "nll_temperature",
            "set_launch_config"]
 
 
@@ -220,6 +221,24 @@ def calibrate(logits, labels, edges, temperature=1.0, use_f64=False, want_binned
         near.data_ptr(), None if binned is None else binned.data_ptr(), _stream())
     _lib.check(rc, "bdl_calibrate")
     return stats[:M], stats[M:2 * M], stats[2 * M:3 * M], stats[3 * M:], near, binned
+
+
+def bma_mean(logits_all, out):
+    """logits_all [B,K,S] -> out [B,K]: fp32 running sum over S in order, divided by fp32(S) (see bdl_bma_mean)."""
+    B, K, S = logits_all.shape
+    rc = _lib.load().bdl_bma_mean(_ptr(logits_all, "logits_all"), B, K, S, _ptr(out, "out"), _stream())
+    _lib.check(rc, "bdl_bma_mean")
+    return out
+
+
+def nll_temperature(logits, labels, temperature, row_nll, out_mean):
+    """out_mean[0] = mean_i(logsumexp(logits[i]/T) - logits[i,y_i]/T) in fp64 (see bdl_nll_temperature)."""
+    N, K = logits.shape
+    rc = _lib.load().bdl_nll_temperature(_ptr(logits, "logits"), _ptr(labels, "labels", torch.int64), N, K,
+                                         float(temperature), _ptr(row_nll, "row_nll", torch.float64),
+                                         _ptr(out_mean, "out_mean", torch.float64), _stream())
+    _lib.check(rc, "bdl_nll_temperature")
+    return out_mean
 
 
 class HostChain:

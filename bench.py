@@ -242,6 +242,8 @@ def run_ours(args):
 
     # ---- extras --------------------------------------------------------------------------------------------
     extras = {}
+    if rank == 0 and not args.no_sample_store:
+        extras["sample_store"] = guarded("sample_store", sample_store_extra, lay, theta, step, device, peak)
     if not args.no_train_step:
         del theta, g, theta0, v
         torch.cuda.empty_cache()
@@ -346,6 +348,66 @@ def variant_rates(lay, theta, g, theta0, v, runs_dev, nruns, device, world, peak
         out[name] = {"params_per_s": world * n_dense / (ms * 1e-3), "ms_per_step": ms, "bytes_per_param": bpp,
                      "achieved_gbs_per_gpu": gbs, "frac_of_measured_peak": gbs / peak}
     return out
+
+
+def sample_store_extra(lay, theta, step, device, peak, reps=20):
+    """SURVEY 8f rows 2-3 at ViT-L/32 size: (i) raw-sample capture into the HBM ring (TMA bulk copy, 8 B/param);
+    (ii) a 1.2 GB checkpoint vector written the reference's way (clone + synchronous torch.save: the training stream
+    waits for all of it) vs through the asynchronous writer (snapshot launch + submit; D2H and the pickler run on a
+    side stream / thread while sampler steps keep launching)."""
+    from bayesdll_b200 import ops
+    from bayesdll_b200.writer import AsyncWriter
+    n, n_dense = lay.n_padded, lay.n_dense
+    ring = torch.empty((2, n), dtype=torch.float32, device=device)
+    for i in range(3):
+        ops.capture_ring(theta, ring, i & 1)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(reps):
+        ops.capture_ring(theta, ring, i & 1)
+    e1.record()
+    torch.cuda.synchronize()
+    cap_ms = e0.elapsed_time(e1) / reps
+    cap_gbs = 8 * n_dense / (cap_ms * 1e-3) / 1e9
+    tmp = tempfile.mkdtemp(prefix="bdl_bench_store_")
+    try:
+        # reference way: the loop blocks until the file is written
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        torch.save({"last_theta": theta[:n_dense].clone()}, os.path.join(tmp, "sync.pt"))
+        sync_s = time.perf_counter() - t0
+        # asynchronous writer: stall = snapshot launch + submit; then sampler steps overlap the spill
+        w = AsyncWriter(device)
+        w.submit(os.path.join(tmp, "warm.pt"), {"x": theta[:1024].clone()})
+        w.flush()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        ops.capture_ring(theta, ring, 0)
+        w.submit(os.path.join(tmp, "async.pt"), {"last_theta": ring[0, :n_dense]})
+        stall_s = time.perf_counter() - t0
+        e0.record()
+        k = 0
+        while w.is_pending(os.path.join(tmp, "async.pt")) and k < 20000:
+            step(10_000 + k)
+            k += 1
+            if k % 50 == 0:
+                torch.cuda.current_stream().synchronize()
+        e1.record()
+        torch.cuda.synchronize()
+        w.flush()
+        total_s = time.perf_counter() - t0
+        overlapped_ms = e0.elapsed_time(e1) / max(k, 1)
+        same = torch.equal(torch.load(os.path.join(tmp, "async.pt"))["last_theta"], ring[0, :n_dense].cpu())
+        w.close()
+    finally:
+        import shutil
+        shutil.rmtree(tmp, ignore_errors=True)
+    return {"capture_ms": cap_ms, "capture_gbs": cap_gbs, "capture_frac_of_measured_peak": cap_gbs / peak,
+            "capture_kernel": "bdl::ring_copy_kernel (cp.async.bulk global->shared->global), 8 B/param",
+            "bytes": 4 * n_dense, "sync_torch_save_stall_s": sync_s, "async_stall_s": stall_s,
+            "async_complete_s": total_s, "sampler_steps_overlapped": k, "overlapped_step_ms": overlapped_ms,
+            "file_identical": bool(same)}
 
 
 def train_step_extra(device, rank, world, steps=6, batch=64):
@@ -547,6 +609,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-eager-gpu", action="store_true")
     ap.add_argument("--no-variants", action="store_true")
+    ap.add_argument("--no-sample-store", action="store_true")
     args = ap.parse_args()
     world = env_int("WORLD_SIZE", 1)
     if args.gpus != world and args.impl == "ours" and world == 1 and args.gpus > 1:

@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define BDL_ABI_VERSION 1
+#define BDL_ABI_VERSION 2
 
 typedef enum {
     BDL_OK = 0,
@@ -207,6 +207,18 @@ int bdl_calibrate(const float* logits_dev, const int64_t* labels_dev, uint64_t N
                   int use_f64, const double* edges_dev, uint32_t M, double* bin_size_dev, double* acc_sum_dev,
                   double* conf_sum_dev, double* nll_sum_dev, unsigned long long* near_edge_dev,
                   int32_t* binned_dev, void* stream);
+
+/* (section 8f row 2) Bayesian model average over stored raw samples, one test batch
+ * (methods/csghmc_fs.py:349-377): logits_all [B,K,S] fp32 (S fastest; S = models in sorted file order) ->
+ *   out[B,K] = (((l_0 + l_1) + l_2) + ...) / fp32(S)      fp32 running sum in model order, one IEEE division. */
+int bdl_bma_mean(const float* logits_all_dev, uint32_t B, uint32_t K, uint32_t S, float* out_logits_dev, void* stream);
+
+/* (section 8f row 4) Temperature-scaling objective of find_optimal_temperature (calibration.py:178-184):
+ *   row_nll[i] = logsumexp_k(logits[i,k] / T) - logits[i,y_i] / T   (fp64; `logits / T` promotes in the reference)
+ *   out_mean[0] = mean_i row_nll[i]                                  (fixed reduction order: reproducible)
+ * row_nll_dev: caller scratch of N doubles (also an output).  The scalar optimiser (scipy BFGS) stays on the host. */
+int bdl_nll_temperature(const float* logits_dev, const int64_t* labels_dev, uint64_t N, uint32_t K, double temperature,
+                        double* row_nll_dev, double* out_mean_dev, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Host-buffer form: a chain whose state is resident in HBM, stepped from HOST memory.

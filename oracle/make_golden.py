@@ -238,6 +238,29 @@ def make_calibration_golden():
     save("calibration", **out)
 
 
+def make_temperature_golden():
+    """calibration.find_optimal_temperature (the reference's own function, scipy BFGS) on the calibration data sets, plus
+    values of its objective at fixed temperatures computed with the reference's expression (calibration.py:179-183)."""
+    import scipy.special
+    cal = refshim.load("calibration")
+    z = np.load(os.path.join(GOLDEN_DIR, "calibration.npz"))
+    out = {}
+    Ts = np.array([0.25, 0.7, 1.0, 1.37, 2.5, 9.0])
+    for tag in "abcd":
+        logits, labels = z[tag + "_logits"], z[tag + "_labels"]
+        Topt, ok = cal.find_optimal_temperature(labels, logits, os.path.join(tempfile.gettempdir(), "t.png"))
+        out[tag + "_Topt"] = np.asarray(Topt, dtype=np.float64)
+        out[tag + "_success"] = bool(ok)
+        vals = []
+        for T in Ts:
+            lg = logits / np.array([T])
+            vals.append(np.mean(scipy.special.logsumexp(lg, axis=1) - lg[np.arange(len(labels)), labels]))
+        out[tag + "_fun"] = np.array(vals, dtype=np.float64)
+        print(f"  temperature {tag}: Topt = {np.asarray(Topt).reshape(-1)[0]:.6f} success={ok}")
+    out["Ts"] = Ts
+    save("temperature", **out)
+
+
 if __name__ == "__main__":
     torch.set_num_threads(1)
     which = sys.argv[1:] or ["step", "cyclical", "calibration", "runner"]
@@ -250,3 +273,8 @@ if __name__ == "__main__":
     if "runner" in which:
         from oracle import make_golden_runner
         make_golden_runner.main(save)
+    if "runner_fs" in which:                  # only the full-sample-store cases (methods/csghmc_fs.py)
+        from oracle import make_golden_runner
+        make_golden_runner.main(save, only=make_golden_runner.FS_CASES)
+    if "temperature" in which:
+        make_temperature_golden()

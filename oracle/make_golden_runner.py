@@ -230,10 +230,27 @@ def n_params():
     return sum(int(np.prod(s)) for s in SHAPES.values())
 
 
+# Full-sample store + Bayesian model average (methods/csghmc_fs.py).  L = epochs // num_cycles = 3, so epochs 0, 1, 3, 4
+# dump a state_dict and each dump is followed by a BMA over every file written so far (csghmc_fs.py:176-181).
+FS_CASES = {
+    "csghmc_fs": ("csghmc_fs", dict(prior_sig=0.05, Ninflate=5.0, nd=0.6, burnin=0, thin=1, nst=2, bias="informative",
+                                    momentum_decay=0.18), dict(momentum=0.0, epochs=6, num_cycles=2)),
+}
+FS_SEEDS = {"csghmc_fs": 700}
+
+
+def case_seed(name):
+    return FS_SEEDS[name] if name in FS_SEEDS else 500 + sorted(CASES).index(name)
+
+
+def case_spec(name):
+    return FS_CASES[name] if name in FS_CASES else CASES[name]
+
+
 def run_reference_case(name):
-    method, hp, over = CASES[name]
+    method, hp, over = case_spec(name)
     mod = refshim.load(f"methods.{method}")
-    seed = 500 + sorted(CASES).index(name)
+    seed = case_seed(name)
     rng = np.random.default_rng(seed)
     loaders = make_loaders(seed)
     steps = over["epochs"] * len(loaders[0])
@@ -259,6 +276,15 @@ def run_reference_case(name):
         evals.append(res)
         return res
     runner.evaluate = recording_eval
+    bmas = []
+    if hasattr(runner, "evaluate_full_samples"):
+        orig_bma = runner.evaluate_full_samples
+
+        def recording_bma(*a, **k):
+            res = orig_bma(*a, **k)
+            bmas.append((res, sorted(f for f in os.listdir(log_dir) if f.startswith("full_samples_net_ep"))))
+            return res
+        runner.evaluate_full_samples = recording_bma
 
     cwd = os.getcwd()
     os.chdir(log_dir)
@@ -275,6 +301,26 @@ def run_reference_case(name):
     for i, (loss, err, targets, logits, logits_all) in enumerate(evals):
         rec[f"eval{i}_loss"], rec[f"eval{i}_err"] = loss, err
         rec[f"eval{i}_targets"], rec[f"eval{i}_logits"], rec[f"eval{i}_logits_all"] = targets, logits, logits_all
+    if bmas:
+        rec["n_bma"] = len(bmas)
+        for i, (res, files) in enumerate(bmas):
+            rec[f"bma{i}_files"] = np.array(files)
+            for ds in ("train", "val", "test"):
+                r = res[ds]
+                for k in ("loss", "error", "num_models", "individual_avg_loss", "individual_avg_error"):
+                    rec[f"bma{i}_{ds}_{k}"] = np.float64(r[k])
+                if i == len(bmas) - 1 or ds == "test":
+                    rec[f"bma{i}_{ds}_targets"], rec[f"bma{i}_{ds}_logits"] = r["targets"], r["logits"]
+                    rec[f"bma{i}_{ds}_logits_all"] = r["logits_all"]
+        # on-disk contract of the sample store and of the BMA outputs
+        sd = torch.load(os.path.join(log_dir, bmas[-1][1][-1]), map_location="cpu")
+        rec["fs_state_keys"] = np.array(list(sd.keys()))
+        rec["fs_last_sample"] = torch.cat([sd[n].reshape(-1) for n, _ in runner.net.named_parameters()]).numpy()
+        import pickle
+        with open(os.path.join(log_dir, "bma_evaluation_results.pkl"), "rb") as f:
+            pk = pickle.load(f)
+        rec["bma_pkl_keys"] = np.array(sorted(pk["test"].keys()))
+        rec["bma_files_in_logdir"] = np.array(sorted(f for f in os.listdir(log_dir) if "bma" in f))
     if hasattr(runner, "post_theta_mom1"):
         rec["post_theta_mom1"] = runner.post_theta_mom1.numpy()
         if hasattr(runner, "post_theta_mom2"):
@@ -308,12 +354,22 @@ def run_reference_case(name):
     return rec
 
 
-def main(save):
+def main(save, only=None):
     torch.set_num_threads(1)
+    if only is not None:
+        for name in only:
+            rec = run_reference_case(name)
+            save(f"runner_{name}", **rec)
+            print(f"  {name}: tape used {rec['tape_used']}, evaluate() calls {rec['n_evals']}, BMA calls {rec.get('n_bma', 0)}")
+        return
     for name in CASES:
         rec = run_reference_case(name)
         save(f"runner_{name}", **rec)
         print(f"  {name}: tape used {rec['tape_used']}, evaluate() calls {rec['n_evals']}")
+    for name in FS_CASES:
+        rec = run_reference_case(name)
+        save(f"runner_{name}", **rec)
+        print(f"  {name}: tape used {rec['tape_used']}, evaluate() calls {rec['n_evals']}, BMA calls {rec['n_bma']}")
     for name in REAL_CASES:
         rec = run_reference_real_case(name)
         save(f"runner_{name}", **rec)

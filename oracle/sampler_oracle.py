@@ -358,3 +358,35 @@ def analyze(labels, logits, num_bins, temperature=1):
     lse = np.log(np.exp(lg - mx).sum(axis=1)) + mx[:, 0]
     nll = np.mean(lse - lg[np.arange(len(labels)), labels])
     return ece, mce, nll
+
+
+# ----------------------------------------------------------------------------------------------
+# (8f row 4) temperature scaling   calibration.py:123-212 (objective :178-184, driver :196)
+# ----------------------------------------------------------------------------------------------
+def nll_temperature(labels, logits, T):
+    """fun(T) of find_optimal_temperature: mean(logsumexp(logits/T, axis=1) - (logits/T)[i, y_i]).  ``T`` is the fp64
+    ndarray scipy hands to the objective, so ``logits / T`` is fp64 even for fp32 logits."""
+    z = np.asarray(logits) / np.asarray(T, dtype=np.float64)
+    mx = z.max(axis=1, keepdims=True)
+    lse = np.log(np.exp(z - mx).sum(axis=1)) + mx[:, 0]
+    return float(np.mean(lse - z[np.arange(len(labels)), labels]))
+
+
+def find_optimal_temperature(labels, logits, max_iter=10000):
+    """scipy BFGS (numerical gradient) from T = 1, as calibration.py:196.  -> (result.x, result.success)"""
+    import scipy.optimize
+    res = scipy.optimize.minimize(lambda T: nll_temperature(labels, logits, T), np.ones(1), options={"maxiter": max_iter})
+    return res.x, res.success
+
+
+# ----------------------------------------------------------------------------------------------
+# (8f row 2) Bayesian model average over stored raw samples   methods/csghmc_fs.py:349-377
+# ----------------------------------------------------------------------------------------------
+def bma_mean(logits_all):
+    """logits_all [N,K,S] fp32 (S = models in sorted file order) -> [N,K]: ``all_logits_sum += model_logits`` model by
+    model in fp32, then ``/ num_models`` (numpy: fp32 array / python int -> IEEE fp32 division)."""
+    la = np.asarray(logits_all, f32)
+    acc = la[:, :, 0].copy()
+    for m in range(1, la.shape[2]):
+        acc += la[:, :, m]
+    return (acc / la.shape[2]).astype(f32)

@@ -187,3 +187,50 @@ def test_calibration_edge_cases(cuda_device):
         e1, m1, n1 = calibration.analyze(lb, lg, 15, None)
         e2, m2, n2 = so.analyze(lb, lg, 15)
         assert abs(e1 - e2) < 1e-6 and abs(m1 - m2) < 1e-6 and abs(n1 - n2) < 1e-6
+
+
+@pytest.mark.parametrize("B,K,S", [(4, 4, 1), (16, 37, 4), (64, 37, 16), (3669, 37, 12), (1, 1, 3)])
+def test_bma_mean_bit_exact(cuda_device, B, K, S):
+    """bdl_bma_mean == the reference's `all_logits_sum += model_logits` ... `/ num_models` (csghmc_fs.py:349-377)."""
+    from bayesdll_b200 import ops
+    rng = np.random.default_rng(B * 131 + K * 7 + S)
+    la = (rng.standard_normal((B, K, S)) * 20).astype(np.float32)
+    out = torch.empty(B, K, dtype=torch.float32, device=cuda_device)
+    ops.bma_mean(torch.from_numpy(la).to(cuda_device), out)
+    want = so.bma_mean(la)
+    assert np.array_equal(out.cpu().numpy().view(np.uint32), want.view(np.uint32))
+
+
+@pytest.mark.parametrize("tag", ["a", "b", "c", "d"])
+def test_temperature_objective_and_optimum(cuda_device, tag):
+    """bdl_nll_temperature vs the reference's objective values, and the drop-in find_optimal_temperature vs the
+    reference's own optimum (tests/golden/temperature.npz): NLL rel 1e-13, Topt rel 1e-5, same success flag."""
+    from bayesdll_b200 import calibration, ops
+    z = np.load(gu.golden_path("calibration"))
+    t = np.load(gu.golden_path("temperature"))
+    logits, labels = z[f"{tag}_logits"], z[f"{tag}_labels"]
+    lg = torch.from_numpy(logits).to(cuda_device)
+    lb = torch.from_numpy(labels).to(cuda_device)
+    row = torch.empty(len(labels), dtype=torch.float64, device=cuda_device)
+    out = torch.empty(1, dtype=torch.float64, device=cuda_device)
+    for T, want in zip(t["Ts"], t[f"{tag}_fun"]):
+        ops.nll_temperature(lg, lb, float(T), row, out)
+        got = out.item()
+        assert abs(got - want) <= 1e-13 * abs(want), (T, got, want)
+        zz = logits.astype(np.float64) / T                     # per-row values too
+        mx = zz.max(1)
+        ref_rows = np.log(np.exp(zz - mx[:, None]).sum(1)) + mx - zz[np.arange(len(labels)), labels]
+        np.testing.assert_allclose(row.cpu().numpy(), ref_rows, rtol=1e-12, atol=1e-13)
+    # reproducible: same bits on a second evaluation (fixed reduction order)
+    ops.nll_temperature(lg, lb, 1.37, row, out)
+    a = out.item()
+    ops.nll_temperature(lg, lb, 1.37, row, out)
+    assert out.item() == a
+    Topt, ok = calibration.find_optimal_temperature(labels, logits, None)
+    assert bool(ok) == bool(t[f"{tag}_success"])
+    assert isinstance(Topt, np.ndarray) and Topt.dtype == np.float64 and Topt.shape == (1,)
+    np.testing.assert_allclose(Topt, t[f"{tag}_Topt"], rtol=1e-5)
+    # and the calibrated metrics downstream agree with the reference's Topt
+    e1 = calibration.analyze(labels, logits, 15, None, temperature=Topt)
+    e2 = calibration.analyze(labels, logits, 15, None, temperature=t[f"{tag}_Topt"])
+    assert all(abs(x - y) <= 1e-5 * max(1.0, abs(y)) for x, y in zip(e1, e2))

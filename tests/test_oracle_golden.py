@@ -68,3 +68,29 @@ def test_calibration_oracle(tag, tname):
     ece, mce, nll = so.analyze(labels, logits, M, T)
     assert ece == z[pre + "ece"] and mce == z[pre + "mce"]
     assert abs(nll - z[pre + "nll"]) <= 1e-6 * abs(z[pre + "nll"])
+
+
+@pytest.mark.parametrize("tag", ["a", "b", "c", "d"])
+def test_temperature_oracle(tag):
+    """Oracle objective and driver vs the reference's own find_optimal_temperature (tests/golden/temperature.npz)."""
+    z = np.load(gu.golden_path("calibration"))
+    t = np.load(gu.golden_path("temperature"))
+    logits, labels = z[f"{tag}_logits"], z[f"{tag}_labels"]
+    for T, want in zip(t["Ts"], t[f"{tag}_fun"]):
+        got = so.nll_temperature(labels, logits, np.array([T]))
+        assert abs(got - want) <= 4e-15 * abs(want)          # scipy's logsumexp vs the explicit form: last-ulp only
+    Topt, ok = so.find_optimal_temperature(labels, logits)
+    assert bool(ok) == bool(t[f"{tag}_success"])
+    np.testing.assert_allclose(Topt, t[f"{tag}_Topt"], rtol=1e-6)
+
+
+def test_bma_mean_oracle_order():
+    """fp32 running sum in model order then one division: not the same as a pairwise / fp64 mean."""
+    rng = np.random.default_rng(3)
+    la = (rng.standard_normal((50, 7, 9)) * 30).astype(np.float32)
+    got = so.bma_mean(la)
+    acc = np.zeros((50, 7), np.float32)
+    for m in range(9):
+        acc = (acc + la[:, :, m]).astype(np.float32)
+    assert np.array_equal(got, (acc / np.float32(9)).astype(np.float32))
+    assert got.dtype == np.float32

@@ -16,8 +16,8 @@ import golden_util as gu
 
 pytestmark = pytest.mark.gpu
 
-CASES = ["sgld", "sghmc", "adam_sghmc", "sgld_nst0", "csgld", "csghmc", "adam_csghmc"]
-BIT_EXACT = {"sgld", "sghmc", "sgld_nst0", "csgld", "csghmc"}
+CASES = ["sgld", "sghmc", "adam_sghmc", "sgld_nst0", "csgld", "csghmc", "adam_csghmc", "csghmc_fs"]
+BIT_EXACT = {"sgld", "sghmc", "sgld_nst0", "csgld", "csghmc", "csghmc_fs"}
 
 
 def _logger():
@@ -32,9 +32,9 @@ def _run(name, device, tmp_path, extra_hp=None):
     from oracle import make_golden_runner as mgr
     from oracle import refshim
     z = np.load(gu.golden_path(f"runner_{name}"), allow_pickle=False)
-    method, hp, over = mgr.CASES[name]
+    method, hp, over = mgr.case_spec(name)
     hp = dict(hp, noise="torch", div="ieee", **(extra_hp or {}))
-    seed = 500 + sorted(mgr.CASES).index(name)
+    seed = mgr.case_seed(name)
     net, net0 = mgr.InjectNet(seed, z["G"]), mgr.InjectNet(seed + 1)
     assert np.array_equal(torch.cat([p.detach().reshape(-1) for p in net.parameters()]).numpy(), z["theta_init"])
     args = mgr.make_args(hp, str(tmp_path), device, **over)
@@ -49,6 +49,15 @@ def _run(name, device, tmp_path, extra_hp=None):
         evals.append(r)
         return r
     runner.evaluate = rec
+    runner._bma_calls = []
+    if hasattr(runner, "evaluate_full_samples"):
+        orig_bma = runner.evaluate_full_samples
+
+        def rec_bma(*a, **k):
+            r = orig_bma(*a, **k)
+            runner._bma_calls.append((r, runner._full_sample_files()))
+            return r
+        runner.evaluate_full_samples = rec_bma
     loaders = mgr.loaders_from_arrays(z)
     cwd = os.getcwd()
     os.chdir(tmp_path)
@@ -75,6 +84,8 @@ def test_runner_train_matches_reference(cuda_device, tmp_path, name):
     z, runner, evals, ret, tape = _run(name, cuda_device, tmp_path)
     # every recorded draw was consumed, in order, and none beyond
     assert tape.pos == int(z["tape_used"])
+    if "n_bma" in z.files:
+        _check_bma(z, runner, tmp_path)
     dense = lambda flat: runner._dense(flat).cpu().numpy()
     _close(name, dense(runner.model.chain.theta), z["theta_final"], "theta_final")
     if "v_final" in z.files:
@@ -119,6 +130,80 @@ def test_runner_train_matches_reference(cuda_device, tmp_path, name):
         if kind == "vector":
             assert ck["last_theta"].shape == (n_dense,)
         assert os.path.exists(os.path.join(tmp_path, "logits_test.pkl"))
+
+
+def _check_bma(z, runner, tmp_path):
+    """Bayesian model average over the stored raw samples vs the reference's evaluate_full_samples recordings."""
+    import pickle
+    calls = runner._bma_calls
+    assert len(calls) == int(z["n_bma"])
+    for i, (res, files) in enumerate(calls):
+        assert files == z[f"bma{i}_files"].tolist()
+        for ds in ("train", "val", "test"):
+            r = res[ds]
+            assert r["num_models"] == int(z[f"bma{i}_{ds}_num_models"])
+            assert r["error"] == float(z[f"bma{i}_{ds}_error"])
+            assert r["individual_avg_error"] == float(z[f"bma{i}_{ds}_individual_avg_error"])
+            for k in ("loss", "individual_avg_loss"):
+                want = float(z[f"bma{i}_{ds}_{k}"])
+                assert abs(r[k] - want) <= 1e-5 * max(1.0, abs(want)), (i, ds, k, r[k], want)
+            if f"bma{i}_{ds}_logits" in z.files:
+                assert np.array_equal(r["targets"], z[f"bma{i}_{ds}_targets"]) and r["targets"].dtype == np.int64
+                assert r["logits_all"].shape == z[f"bma{i}_{ds}_logits_all"].shape and r["logits"].dtype == np.float32
+                np.testing.assert_allclose(r["logits_all"], z[f"bma{i}_{ds}_logits_all"], atol=1e-5, rtol=1e-5)
+                np.testing.assert_allclose(r["logits"], z[f"bma{i}_{ds}_logits"], atol=1e-5, rtol=1e-5)
+                # the average itself is bit-exact given the per-model logits: fp32 running sum in file order / S
+                la = r["logits_all"]
+                acc = la[:, :, 0].copy()
+                for m in range(1, la.shape[2]):
+                    acc += la[:, :, m]
+                assert np.array_equal((acc / la.shape[2]).view(np.uint32), r["logits"].view(np.uint32))
+    # on-disk contract: same files, a loadable state_dict with the reference's keys, the stored sample bit-exact
+    assert sorted(f for f in os.listdir(tmp_path) if "bma" in f) == z["bma_files_in_logdir"].tolist()
+    last = calls[-1][1][-1]
+    sd = torch.load(os.path.join(tmp_path, last), map_location="cpu")
+    assert list(sd.keys()) == z["fs_state_keys"].tolist()
+    names = [n for n, _ in runner.net.named_parameters()]
+    got = torch.cat([sd[n].reshape(-1) for n in names]).numpy()
+    assert np.array_equal(got.view(np.uint32), z["fs_last_sample"].view(np.uint32))
+    with open(os.path.join(tmp_path, "bma_evaluation_results.pkl"), "rb") as f:
+        assert sorted(pickle.load(f)["test"].keys()) == z["bma_pkl_keys"].tolist()
+
+
+@pytest.mark.parametrize("extra", [dict(), dict(fs_ring_slots=2), dict(io="sync")],
+                         ids=["resident", "evicting-ring", "sync-io"])
+def test_csghmc_fs_sample_store_and_bma(cuda_device, tmp_path, extra):
+    """csghmc_fs: raw samples go to the HBM ring (TMA copy) and are spilled asynchronously; the BMA runs on the resident
+    slots.  A 2-slot ring forces eviction, so older samples are re-read from the spilled files: same results."""
+    z, runner, evals, ret, tape = _run("csghmc_fs", cuda_device, tmp_path, extra_hp=extra)
+    assert tape.pos == int(z["tape_used"])
+    got = runner._dense(runner.model.chain.theta).cpu().numpy()
+    assert np.array_equal(got.view(np.uint32), z["theta_final"].view(np.uint32))
+    _check_bma(z, runner, tmp_path)
+    cap = runner._fs_ring.capacity
+    assert cap == (2 if "fs_ring_slots" in extra else 4)
+    assert len(runner._fs_resident) == cap
+
+
+def test_async_and_sync_checkpoints_are_identical(cuda_device, tmp_path):
+    """io=async (side-stream D2H + writer thread) writes byte-for-byte the tensors io=sync writes."""
+    outs = {}
+    for mode in ("async", "sync"):
+        d = tmp_path / mode
+        d.mkdir()
+        _, runner, _, _, _ = _run("adam_sghmc", cuda_device, d, extra_hp=dict(io=mode))
+        assert runner._writer.stats["jobs"] >= 1
+        outs[mode] = torch.load(os.path.join(d, "ckpt.pt"), map_location="cpu", weights_only=False)
+
+    def same(a, b):
+        if torch.is_tensor(a):
+            return torch.equal(a, b)
+        if isinstance(a, dict):
+            return a.keys() == b.keys() and all(same(a[k], b[k]) for k in a)
+        if isinstance(a, (list, tuple)):
+            return len(a) == len(b) and all(same(x, y) for x, y in zip(a, b))
+        return a == b
+    assert same(outs["async"], outs["sync"])
 
 
 def test_runner_flat_gradient_mode_is_identical(cuda_device, tmp_path):
