@@ -204,11 +204,11 @@ ring_copy_kernel(const char* __restrict__ src, char* __restrict__ dst, uint64_t 
 extern "C" int bdl_moments_avg(const float* theta, float* mom1, float* mom2, uint64_t n, float cnt, float cntp1,
                                int init, int div_mode, void* stream) {
     using namespace bdl;
+    if (n == 0) return BDL_OK;                     // empty state: a no-op, pointers may be null
     BDL_REQUIRE(theta && mom1, BDL_ERR_INVALID, "bdl_moments_avg: null theta/mom1");
     BDL_REQUIRE(n % 4 == 0 && (n >> 2) < 0xFFFFFFFFull, BDL_ERR_INVALID, "bdl_moments_avg: bad n");
     BDL_REQUIRE(aligned16(theta) && aligned16(mom1) && aligned16(mom2), BDL_ERR_ALIGN, "bdl_moments_avg: unaligned pointer");
     BDL_REQUIRE(div_mode == BDL_DIV_IEEE || div_mode == BDL_DIV_RECIP, BDL_ERR_INVALID, "bdl_moments_avg: bad div_mode");
-    if (n == 0) return BDL_OK;
     const uint32_t n4 = static_cast<uint32_t>(n >> 2);
     const uint32_t grid = ew_grid(n4, 4);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
@@ -229,11 +229,11 @@ extern "C" int bdl_moments_avg(const float* theta, float* mom1, float* mom2, uin
 extern "C" int bdl_moments_welford(const float* theta, float* mean, float* M2, uint64_t n, float nf, int init,
                                    int div_mode, void* stream) {
     using namespace bdl;
+    if (n == 0) return BDL_OK;                     // empty state: a no-op, pointers may be null
     BDL_REQUIRE(theta && mean && M2, BDL_ERR_INVALID, "bdl_moments_welford: null pointer");
     BDL_REQUIRE(n % 4 == 0 && (n >> 2) < 0xFFFFFFFFull, BDL_ERR_INVALID, "bdl_moments_welford: bad n");
     BDL_REQUIRE(aligned16(theta) && aligned16(mean) && aligned16(M2), BDL_ERR_ALIGN, "bdl_moments_welford: unaligned pointer");
     BDL_REQUIRE(div_mode == BDL_DIV_IEEE || div_mode == BDL_DIV_RECIP, BDL_ERR_INVALID, "bdl_moments_welford: bad div_mode");
-    if (n == 0) return BDL_OK;
     const uint32_t n4 = static_cast<uint32_t>(n >> 2);
     const uint32_t grid = ew_grid(n4, 4);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
@@ -254,10 +254,10 @@ extern "C" int bdl_set_ring_config(int chunks_per_cta) {
 
 extern "C" int bdl_capture_ring(const float* theta, float* ring, uint64_t slot, uint64_t n, void* stream) {
     using namespace bdl;
+    if (n == 0) return BDL_OK;                     // empty state: a no-op, pointers may be null
     BDL_REQUIRE(theta && ring, BDL_ERR_INVALID, "bdl_capture_ring: null pointer");
     BDL_REQUIRE(n % 4 == 0, BDL_ERR_INVALID, "bdl_capture_ring: n must be a multiple of 4");
     BDL_REQUIRE(aligned16(theta) && aligned16(ring), BDL_ERR_ALIGN, "bdl_capture_ring: unaligned pointer");
-    if (n == 0) return BDL_OK;
     const int smem_bytes = kRingStages * kRingChunk;
     BDL_CUDA(cudaFuncSetAttribute(ring_copy_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
     const uint64_t bytes = n * sizeof(float);

@@ -323,10 +323,10 @@ static uint32_t rows_grid(uint32_t rows) {
 extern "C" int bdl_ensemble(const float* logits_all, uint32_t B, uint32_t K, uint32_t S, float log_S, float weight,
                             int mode, float* out, void* stream) {
     using namespace bdl;
+    if (B == 0) return BDL_OK;                     // empty batch: a no-op, pointers may be null
     BDL_REQUIRE(logits_all && out, BDL_ERR_INVALID, "bdl_ensemble: null pointer");
     BDL_REQUIRE(K >= 1 && S >= 1, BDL_ERR_INVALID, "bdl_ensemble: K and S must be >= 1");
     BDL_REQUIRE(mode >= 0 && mode <= 2, BDL_ERR_INVALID, "bdl_ensemble: mode must be 0,1,2");
-    if (B == 0) return BDL_OK;
     const size_t smem = static_cast<size_t>(kPredWarps) * 2 * S * sizeof(float);
     BDL_REQUIRE(smem <= 48 * 1024, BDL_ERR_UNSUPPORTED, "bdl_ensemble: S=%u too large", S);
     ensemble_kernel<<<rows_grid(B), kPredThreads, smem, static_cast<cudaStream_t>(stream)>>>(logits_all, B, K, S, log_S,
@@ -337,9 +337,9 @@ extern "C" int bdl_ensemble(const float* logits_all, uint32_t B, uint32_t K, uin
 extern "C" int bdl_ce_err(const float* logits, const int64_t* y, uint32_t B, uint32_t K, double* loss_sum,
                           int32_t* err_count, void* stream) {
     using namespace bdl;
+    if (B == 0) return BDL_OK;                     // empty batch: a no-op, pointers may be null
     BDL_REQUIRE(logits && y && loss_sum && err_count, BDL_ERR_INVALID, "bdl_ce_err: null pointer");
     BDL_REQUIRE(K >= 1, BDL_ERR_INVALID, "bdl_ce_err: K must be >= 1");
-    if (B == 0) return BDL_OK;
     ce_err_kernel<<<1, kPredThreads, 0, static_cast<cudaStream_t>(stream)>>>(logits, y, B, K, loss_sum, err_count);
     return check_cuda(cudaGetLastError(), "ce_err_kernel launch");
 }
@@ -352,9 +352,9 @@ static uint32_t flat_grid(uint64_t total) {
 
 extern "C" int bdl_lse_accum(const float* logits, uint32_t B, uint32_t K, float* m, float* s, void* stream) {
     using namespace bdl;
+    if (B == 0) return BDL_OK;                     // empty batch: a no-op, pointers may be null
     BDL_REQUIRE(logits && m && s, BDL_ERR_INVALID, "bdl_lse_accum: null pointer");
     BDL_REQUIRE(K >= 1, BDL_ERR_INVALID, "bdl_lse_accum: K must be >= 1");
-    if (B == 0) return BDL_OK;
     lse_accum_kernel<<<rows_grid(B), kPredThreads, 0, static_cast<cudaStream_t>(stream)>>>(logits, B, K, m, s);
     return check_cuda(cudaGetLastError(), "lse_accum_kernel launch");
 }
@@ -387,12 +387,12 @@ extern "C" int bdl_calibrate(const float* logits, const int64_t* labels, uint64_
                              double* conf_sum, double* nll_sum, unsigned long long* near_edge, int32_t* binned,
                              void* stream) {
     using namespace bdl;
+    if (N == 0) return BDL_OK;                     // empty batch: a no-op, pointers may be null
     BDL_REQUIRE(logits && labels && edges && bin_size && acc_sum && conf_sum && nll_sum, BDL_ERR_INVALID,
                 "bdl_calibrate: null pointer");
     BDL_REQUIRE(M >= 1 && M <= static_cast<uint32_t>(kMaxBins), BDL_ERR_UNSUPPORTED, "bdl_calibrate: num_bins=%u not in [1,%d]", M, kMaxBins);
     BDL_REQUIRE(K >= 1 && N < 0xFFFFFFFFull, BDL_ERR_INVALID, "bdl_calibrate: bad N/K");
     BDL_REQUIRE(temperature > 0.0, BDL_ERR_INVALID, "bdl_calibrate: temperature must be > 0");
-    if (N == 0) return BDL_OK;
     const uint32_t grid = rows_grid(static_cast<uint32_t>(N));
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     if (use_f64)
@@ -407,8 +407,9 @@ extern "C" int bdl_calibrate(const float* logits, const int64_t* labels, uint64_
 
 extern "C" int bdl_bma_mean(const float* logits_all, uint32_t B, uint32_t K, uint32_t S, float* out, void* stream) {
     using namespace bdl;
-    BDL_REQUIRE(logits_all && out, BDL_ERR_INVALID, "bdl_bma_mean: null pointer");
     BDL_REQUIRE(K >= 1 && S >= 1, BDL_ERR_INVALID, "bdl_bma_mean: K and S must be >= 1");
+    if (B == 0) return BDL_OK;                     // empty batch: a no-op, pointers may be null
+    BDL_REQUIRE(logits_all && out, BDL_ERR_INVALID, "bdl_bma_mean: null pointer");
     const uint64_t total = static_cast<uint64_t>(B) * K;
     BDL_REQUIRE(total < 0xFFFFFFFFull, BDL_ERR_INVALID, "bdl_bma_mean: B*K too large");
     if (total == 0) return BDL_OK;

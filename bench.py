@@ -347,6 +347,33 @@ def variant_rates(lay, theta, g, theta0, v, runs_dev, nruns, device, world, peak
         gbs = bpp * n_dense / (ms * 1e-3) / 1e9
         out[name] = {"params_per_s": world * n_dense / (ms * 1e-3), "ms_per_step": ms, "bytes_per_param": bpp,
                      "achieved_gbs_per_gpu": gbs, "frac_of_measured_peak": gbs / peak}
+    # the shape Runner.train() actually launches: one run per tensor, each row pointing at that tensor's own
+    # (separately allocated) autograd gradient -- no flat gradient buffer, no gather pass
+    del m, s2, buf
+    grads = [torch.randn(sg.numel, device=device) * 1e-2 for sg in lay.segments]
+    ok = all(t.data_ptr() % 16 == 0 for t in grads)
+    tab = lay.run_table("informative", grad_ptrs=[t.data_ptr() for t in grads])
+    rd, nr = ops.upload_runs(tab, device)
+    sc = make_scalars(_lib.SGHMC)
+
+    def one_ptr(i):
+        ops.step(_lib.SGHMC, theta, None, theta0, v, None, None, None, rd, nr, sc, ops.make_noise(seed=seed, subseq=2000 + i))
+    for i in range(3):
+        one_ptr(i)
+    barrier(world)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(steps):
+        one_ptr(3 + i)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = allmax(e0.elapsed_time(e1), world, device) / steps
+    gbs = 24 * n_dense / (ms * 1e-3) / 1e9
+    out["sghmc_per_tensor_gradient_pointers"] = {
+        "params_per_s": world * n_dense / (ms * 1e-3), "ms_per_step": ms, "bytes_per_param": 24, "achieved_gbs_per_gpu": gbs,
+        "frac_of_measured_peak": gbs / peak, "runs": nr, "aligned": ok,
+        "note": "run table with one row per tensor carrying that tensor's p.grad address (the training-loop launch)"}
     return out
 
 

@@ -275,6 +275,6 @@ if __name__ == "__main__":
         make_golden_runner.main(save)
     if "runner_fs" in which:                  # only the full-sample-store cases (methods/csghmc_fs.py)
         from oracle import make_golden_runner
-        make_golden_runner.main(save, only=make_golden_runner.FS_CASES)
+        make_golden_runner.main(save, only=list(make_golden_runner.FS_CASES) + ["real_csghmc_fs"])
     if "temperature" in which:
         make_temperature_golden()

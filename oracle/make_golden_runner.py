@@ -108,13 +108,17 @@ REAL_CASES = {
     "real_adam_csghmc": ("adam_csghmc", dict(prior_sig=1.0, Ninflate=10.0, nd=0.3, burnin=0, thin=1, nst=2,
                                              bias="uninformative", momentum_decay=0.1, beta1=0.9, beta2=0.99,
                                              epsilon=1e-3, temperature=1.0), dict(momentum=0.0, epochs=4, num_cycles=2)),
+    # raw-sample store with BatchNorm buffers in every stored state_dict (methods/csghmc_fs.py)
+    "real_csghmc_fs": ("csghmc_fs", dict(prior_sig=0.05, Ninflate=5.0, nd=0.3, burnin=0, thin=1, nst=2,
+                                         bias="informative", momentum_decay=0.18), dict(momentum=0.0, epochs=6, num_cycles=2)),
 }
+REAL_SEEDS = {"real_adam_csghmc": 900, "real_csghmc": 901, "real_sghmc": 902, "real_csghmc_fs": 903}
 
 
 def run_reference_real_case(name):
     method, hp, over = REAL_CASES[name]
     mod = refshim.load(f"methods.{method}")
-    seed = 900 + sorted(REAL_CASES).index(name)
+    seed = REAL_SEEDS[name]
     rng = np.random.default_rng(seed)
     loaders = make_loaders(seed)
     tape = rng.standard_normal(200_000).astype(np.float32)
@@ -133,6 +137,15 @@ def run_reference_real_case(name):
         evals.append(res)
         return res
     runner.evaluate = recording_eval
+    bmas = []
+    if hasattr(runner, "evaluate_full_samples"):
+        orig_bma = runner.evaluate_full_samples
+
+        def recording_bma(*a, **k):
+            res = orig_bma(*a, **k)
+            bmas.append((res, sorted(f for f in os.listdir(log_dir) if f.startswith("full_samples_net_ep"))))
+            return res
+        runner.evaluate_full_samples = recording_bma
     cwd = os.getcwd()
     os.chdir(log_dir)
     try:
@@ -141,7 +154,22 @@ def run_reference_real_case(name):
             used = tp.pos
     finally:
         os.chdir(cwd)
-    rec = dict(tape=tape[:used], tape_used=used, n_evals=len(evals), method=np.array(method),
+    extra = {}
+    if bmas:
+        extra["n_bma"] = len(bmas)
+        res, files = bmas[-1]
+        extra["bma_files"] = np.array(files)
+        for ds in ("train", "val", "test"):
+            r = res[ds]
+            for k in ("loss", "error", "num_models", "individual_avg_loss", "individual_avg_error"):
+                extra[f"bma_{ds}_{k}"] = np.float64(r[k])
+            extra[f"bma_{ds}_logits"], extra[f"bma_{ds}_logits_all"] = r["logits"], r["logits_all"]
+        for i, f in enumerate(files):          # BatchNorm statistics differ from sample to sample
+            sd = torch.load(os.path.join(log_dir, f), map_location="cpu")
+            extra[f"fs{i}_bn_mean"] = sd["features.1.running_mean"].numpy()
+            extra[f"fs{i}_theta"] = torch.cat([sd[n].reshape(-1) for n, _ in runner.net.named_parameters()]).numpy()
+        extra["fs_state_keys"] = np.array(list(sd.keys()))
+    rec = dict(tape=tape[:used], tape_used=used, n_evals=len(evals), method=np.array(method), **extra,
                theta_final=torch.cat([p.detach().reshape(-1) for p in runner.net.parameters()]).numpy(),
                bn_mean=runner.net.features[1].running_mean.numpy().copy(),
                bn_var=runner.net.features[1].running_var.numpy().copy(), **loaders_to_arrays(loaders))
@@ -358,7 +386,7 @@ def main(save, only=None):
     torch.set_num_threads(1)
     if only is not None:
         for name in only:
-            rec = run_reference_case(name)
+            rec = run_reference_real_case(name) if name in REAL_CASES else run_reference_case(name)
             save(f"runner_{name}", **rec)
             print(f"  {name}: tape used {rec['tape_used']}, evaluate() calls {rec['n_evals']}, BMA calls {rec.get('n_bma', 0)}")
         return

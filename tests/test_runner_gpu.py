@@ -313,7 +313,7 @@ def test_csgld_full_sample_uses_hbm_ring(cuda_device, tmp_path):
     assert np.array_equal(got.view(np.uint32), z["theta_final"].view(np.uint32))
 
 
-@pytest.mark.parametrize("name", ["real_sghmc", "real_csghmc", "real_adam_csghmc"])
+@pytest.mark.parametrize("name", ["real_sghmc", "real_csghmc", "real_adam_csghmc", "real_csghmc_fs"])
 def test_runner_real_network_end_to_end(cuda_device, tmp_path, name):
     """A real conv + BatchNorm network trained through ordinary autograd: the reference on CPU (recorded) vs the drop-in
     on the GPU, both fed the same noise tape.  Gradients come from different conv implementations (1e-7-level
@@ -323,7 +323,7 @@ def test_runner_real_network_end_to_end(cuda_device, tmp_path, name):
     from oracle import refshim
     z = np.load(gu.golden_path(f"runner_{name}"), allow_pickle=False)
     method, hp, over = mgr.REAL_CASES[name]
-    seed = 900 + sorted(mgr.REAL_CASES).index(name)
+    seed = mgr.REAL_SEEDS[name]
     net, net0 = mgr.RealNet(seed), mgr.RealNet(seed + 1)
     args = mgr.make_args(dict(hp, noise="torch", div="ieee"), str(tmp_path), cuda_device, lr=2e-2, lr_head=5e-2, **over)
     runner = importlib.import_module(f"bayesdll_b200.methods.{method}").Runner(net, net0, args, _logger())
@@ -335,6 +335,15 @@ def test_runner_real_network_end_to_end(cuda_device, tmp_path, name):
         evals.append(r)
         return r
     runner.evaluate = rec
+    bmas = []
+    if hasattr(runner, "evaluate_full_samples"):
+        orig_bma = runner.evaluate_full_samples
+
+        def rec_bma(*a, **k):
+            r = orig_bma(*a, **k)
+            bmas.append(r)
+            return r
+        runner.evaluate_full_samples = rec_bma
     cwd = os.getcwd()
     os.chdir(tmp_path)
     try:
@@ -345,6 +354,28 @@ def test_runner_real_network_end_to_end(cuda_device, tmp_path, name):
     assert tape.pos == int(z["tape_used"])
     theta = runner._dense(runner.model.chain.theta).cpu().numpy()
     assert gu.max_rel(theta, z["theta_final"]) <= 2e-4, gu.max_rel(theta, z["theta_final"])
+    if "n_bma" in z.files:
+        # raw-sample store on a network with BatchNorm: every stored state_dict carries the statistics of ITS epoch
+        assert len(bmas) == int(z["n_bma"])
+        files = z["bma_files"].tolist()
+        assert runner._full_sample_files() == files
+        names = [n for n, _ in runner.net.named_parameters()]
+        for i, f in enumerate(files):
+            sd = torch.load(os.path.join(tmp_path, f), map_location="cpu")
+            assert list(sd.keys()) == z["fs_state_keys"].tolist()
+            np.testing.assert_allclose(sd["features.1.running_mean"].numpy(), z[f"fs{i}_bn_mean"], rtol=1e-4, atol=1e-6)
+            got = torch.cat([sd[n].reshape(-1) for n in names]).numpy()
+            assert gu.max_rel(got, z[f"fs{i}_theta"]) <= 2e-4
+            res = runner._fs_resident[f]           # the resident copy evaluates with the same buffers the file holds
+            assert torch.equal(res.net.features[1].running_mean.cpu(), sd["features.1.running_mean"])
+        assert not np.allclose(z["fs0_bn_mean"], z[f"fs{len(files) - 1}_bn_mean"])
+        for ds in ("train", "val", "test"):
+            r = bmas[-1][ds]
+            assert r["num_models"] == int(z[f"bma_{ds}_num_models"])
+            np.testing.assert_allclose(r["logits_all"], z[f"bma_{ds}_logits_all"], atol=5e-3, rtol=5e-3)
+            np.testing.assert_allclose(r["logits"], z[f"bma_{ds}_logits"], atol=5e-3, rtol=5e-3)
+            for k in ("loss", "individual_avg_loss"):
+                assert abs(r[k] - float(z[f"bma_{ds}_{k}"])) <= 5e-3
     # BatchNorm running statistics are buffers: updated by the forward passes, never sampled (Appendix B.12)
     np.testing.assert_allclose(runner.net.features[1].running_mean.cpu().numpy(), z["bn_mean"], rtol=1e-4, atol=1e-6)
     np.testing.assert_allclose(runner.net.features[1].running_var.cpu().numpy(), z["bn_var"], rtol=1e-4, atol=1e-6)

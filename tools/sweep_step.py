@@ -108,6 +108,19 @@ def main():
             continue
         med, mn = timeit(stepper(variant, bpp, **kw), a.iters)
         report(tag, bpp, med, mn)
+    tag = "SGHMC philox per-tensor gradient pointers (%d runs)" % len(lay.segments)
+    if want(tag):
+        grads = [torch.randn(sg.numel, device=dev) * 1e-2 for sg in lay.segments]
+        rd, nr = ops.upload_runs(lay.run_table("informative", grad_ptrs=[t.data_ptr() for t in grads]), dev)
+        sc = ops.make_scalars(_lib.SGHMC, lr_body=1e-4, lr_head=1e-2, ND=3680, Ninflate=1e3, prior_sig=1.0, nd=1.0, alpha=0.18)
+
+        def fn_ptr():
+            step_no[0] += 1
+            ops.step(_lib.SGHMC, buf["theta"], None, buf["theta0"], buf["v"], None, None, None, rd, nr, sc,
+                     ops.make_noise(seed=42, subseq=step_no[0]))
+        med, mn = timeit(fn_ptr, a.iters)
+        report(tag, 24, med, mn)
+        del grads
     if a.full:
         for threads in (64, 128, 256):
             for unroll in (1,):
