@@ -11,7 +11,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libbdl.so")
 
 # ---- enums / constants (include/bdl.h) -------------------------------------------------------
-BDL_ABI_VERSION = 2
+BDL_ABI_VERSION = 3
 SGLD, SGHMC, CSGHMC, ADAM_SGHMC, ADAM_CSGHMC = range(5)
 VARIANT_NAMES = {SGLD: "sgld", SGHMC: "sghmc", CSGHMC: "csghmc", ADAM_SGHMC: "adam_sghmc",
                  ADAM_CSGHMC: "adam_csghmc"}
@@ -42,6 +42,14 @@ class Noise(C.Structure):
                 ("stream_id", C.c_uint32), ("reserved", C.c_uint32)]
 
 
+class Capture(C.Structure):
+    _fields_ = [("kind", C.c_int32), ("init", C.c_int32), ("first_dev", C.c_uint64), ("second_dev", C.c_uint64),
+                ("cnt", C.c_float), ("cnt_plus_1", C.c_float)]
+
+
+CAPTURE_NONE, CAPTURE_AVG, CAPTURE_WELFORD = 0, 1, 2
+
+assert C.sizeof(Capture) == 32
 assert C.sizeof(Run) == 40 and C.sizeof(Noise) == 32 and C.sizeof(Scalars) == 88
 
 _P = C.c_void_p
@@ -52,6 +60,8 @@ _U64, _U32, _I32, _F, _D = C.c_uint64, C.c_uint32, C.c_int, C.c_float, C.c_doubl
 SIGNATURES = {
     "bdl_set_launch_config": [_I32, _I32, _I32],
     "bdl_step": [_I32, _P, _P, _P, _P, _P, _P, _P, _U64, _P, _U32, _P, C.POINTER(Scalars), C.POINTER(Noise), _P],
+    "bdl_step_capture": [_I32, _P, _P, _P, _P, _P, _P, _P, _U64, _P, _U32, _P, C.POINTER(Scalars), C.POINTER(Noise),
+                         C.POINTER(Capture), _P],
     "bdl_philox_normal": [_P, _U64, _U64, _U32, _U64, _P],
     "bdl_moments_avg": [_P, _P, _P, _U64, _F, _F, _I32, _I32, _P],
     "bdl_moments_welford": [_P, _P, _P, _U64, _F, _I32, _I32, _P],

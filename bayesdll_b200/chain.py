@@ -129,8 +129,9 @@ class ChainState:
         raise ValueError(f"unknown noise mode {self.noise_mode!r} (philox | torch)")
 
     # ---- the fused update --------------------------------------------------------------------
-    def update(self, scalars):
-        """Apply one fused update using the gradients currently held in ``p.grad``."""
+    def update(self, scalars, capture=None):
+        """Apply one fused update using the gradients currently held in ``p.grad``.  ``capture`` (ops.make_capture)
+        folds the new theta into running moments in the same launch."""
         if self.grad_mode == "table":
             runs_dev, nruns = self._gradient_table()
             g = self.g_flat
@@ -141,7 +142,7 @@ class ChainState:
         if self.buf is not None:
             scalars.first_step = int(self.sgd_steps == 0)
         ops.step(self.variant, self.theta, g, self.theta0, self.v, self.m, self.s, self.buf, runs_dev, nruns,
-                 scalars, self._noise())
+                 scalars, self._noise(), capture=capture)
         self.step_count += 1
         self.sgd_steps += 1
 

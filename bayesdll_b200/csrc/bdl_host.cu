@@ -124,7 +124,7 @@ extern "C" int bdl_chain_step_host(bdl_chain* c, const float* g_host, float* the
         BDL_CUDA(cudaStreamWaitEvent(c->s_cmp, c->ev_h2d[k], 0));
         const int rc = step_range(c->variant, c->buf[BDL_BUF_THETA], c->buf[kGrad], c->buf[BDL_BUF_THETA0], c->buf[BDL_BUF_V],
                                   c->buf[BDL_BUF_M], c->buf[BDL_BUF_S], c->buf[BDL_BUF_SGD], c->n, off >> 2, (off + len) >> 2,
-                                  c->runs_dev, nruns, runs_host, sc, nz, c->s_cmp);
+                                  c->runs_dev, nruns, runs_host, sc, nz, nullptr, c->s_cmp);
         if (rc != BDL_OK) return rc;
         BDL_CUDA(cudaEventRecord(c->ev_cmp[k], c->s_cmp));
         BDL_CUDA(cudaStreamWaitEvent(c->s_d2h, c->ev_cmp[k], 0));

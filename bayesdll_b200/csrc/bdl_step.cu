@@ -45,6 +45,11 @@ struct StepParams {
     float oma, sig2, inv_sig2, N, inv_N, mu;
     float b1, omb1, b2, omb2, bc1, inv_bc1, bc2, inv_bc2, eps, two_alpha, nd, T, inv_T;
     int first_step, add_noise;
+    // fused sample capture (kCap != 0): running moments of the NEW theta, same arithmetic as bdl_capture.cu
+    float* cap1;               // mom1 (avg) / mean (Welford)
+    float* cap2;               // mom2 (avg, may be null: nst == 0) / M2 (Welford)
+    float cap_a, cap_b, cap_inv;   // avg: cnt, cnt+1, 1/(cnt+1);  Welford: n, -, 1/n
+    int cap_init, cap_kind;
     NoiseKey key;
 };
 
@@ -151,11 +156,11 @@ constexpr int kDefaultUnroll = 1;
 
 // Resident CTAs per SM the kernel is compiled for: 16 data registers per stream per unroll step plus ~28 registers of
 // addressing / Philox state, rounded to the allocation granule, against the 64K-entry register file.
-template <int kVariant, bool kHasBuf, bool kPhilox, int kU, int kT>
+template <int kVariant, bool kHasBuf, bool kPhilox, int kU, int kT, int kCap = 0>
 constexpr int min_blocks() {
     int streams = (kVariant == BDL_SGLD) ? 3 : (kVariant == BDL_SGHMC) ? 4 : (kVariant == BDL_CSGHMC) ? 3 : 6;
-    streams += (kHasBuf ? 1 : 0) + (kPhilox ? 0 : 1);
-    int regs = 4 * kU * streams + 28;
+    streams += (kHasBuf ? 1 : 0) + (kPhilox ? 0 : 1) + (kCap ? 2 : 0);
+    int regs = 4 * kU * streams + 28 + (kCap ? 12 : 0);   // capture: moment arithmetic temporaries live across the update
     regs = (regs + 7) / 8 * 8;
     int blocks = 65536 / (kT * regs);
     const int cap = 2048 / kT > 32 ? 32 : 2048 / kT;   // 64 warps and 32 CTAs per SM
@@ -190,8 +195,11 @@ __device__ __forceinline__ uint32_t cursor_find_warp(const StepParams& p, uint32
 // beats a persistent grid-stride grid by ~8 % (6.87 vs 6.35 TB/s on the SGHMC step): in-order dispatch keeps the set
 // of DRAM pages being streamed compact, whereas persistent CTAs drift apart and scatter the access window.  The
 // tile loop remains for capped grids (bdl_set_launch_config) and for > 2^31 tiles.
-template <int kVariant, bool kHasBuf, bool kPhilox, int kDiv, int kU, int kT>
-__global__ void __launch_bounds__(kT, (min_blocks<kVariant, kHasBuf, kPhilox, kU, kT>()))
+// kCap: 0 = plain step; 1 = also fold the new theta into running moments (bdl_moments_avg arithmetic); 2 = Welford
+// (bdl_moments_welford arithmetic).  Fusing saves the capture kernel's re-read of theta: 40 instead of 44 B/param for
+// SGHMC + moments, which is every step after burn-in when thin = 1 (BASELINE.json configs[2]).
+template <int kVariant, bool kHasBuf, bool kPhilox, int kDiv, int kU, int kT, int kCap = 0>
+__global__ void __launch_bounds__(kT, (min_blocks<kVariant, kHasBuf, kPhilox, kU, kT, kCap>()))
 step_kernel(const StepParams p) {
     using U = Uses<kVariant>;
     constexpr uint32_t tile_groups = kT * kU;
@@ -201,17 +209,24 @@ step_kernel(const StepParams p) {
 
     for (uint32_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         const uint32_t q0 = p.q_begin + tile * tile_groups + threadIdx.x;
-        float4 th[kU], g[kU], th0[kU], v[kU], m[kU], s[kU], b[kU], xi[kU];
+        float4 th[kU], g[kU], th0[kU], v[kU], m[kU], s[kU], b[kU], xi[kU], c1[kU], c2[kU];
         uint32_t cls[kU];
-        bool act[kU];
+        bool act[kU], inr[kU];
         // ---- 1. every load that does not depend on the run table (kU * #streams independent 128-bit requests) ----
 #pragma unroll
         for (int u = 0; u < kU; ++u) {
             const uint32_t q = q0 + u * kT;
             act[u] = q < p.n4;
+            inr[u] = act[u];
             if (act[u]) {
                 const uint64_t i = static_cast<uint64_t>(q) << 2;
                 th[u] = ld_stream(p.theta + i);
+                if constexpr (kCap != 0) {
+                    if (!p.cap_init) {
+                        c1[u] = ld_stream(p.cap1 + i);
+                        if (kCap == 2 || p.cap2) c2[u] = ld_stream(p.cap2 + i);
+                    }
+                }
                 if constexpr (U::theta0) th0[u] = ld_stream(p.theta0 + i);
                 if constexpr (U::v) v[u] = ld_stream(p.v + i);
                 if constexpr (U::adam) {
@@ -282,6 +297,40 @@ step_kernel(const StepParams p) {
                 if constexpr (kHasBuf) st_stream(p.buf + i, b[u]);
                 st_stream(p.theta + i, th[u]);
             }
+            if constexpr (kCap != 0) {
+                if (inr[u]) {                              // also for skipped tensors: their (unchanged) theta is a sample too
+                    const uint64_t i = static_cast<uint64_t>(q) << 2;
+                    const float t[4] = {th[u].x, th[u].y, th[u].z, th[u].w};
+                    float a[4] = {c1[u].x, c1[u].y, c1[u].z, c1[u].w};
+                    float bb[4] = {c2[u].x, c2[u].y, c2[u].z, c2[u].w};
+                    const bool has2 = kCap == 2 || p.cap2 != nullptr;
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        if constexpr (kCap == 1) {
+                            if (p.cap_init) {
+                                a[k] = __fmul_rn(t[k], 1.0f);                      // theta_vec*1.0
+                                bb[k] = __fmul_rn(t[k], t[k]);                     // theta_vec**2
+                            } else {                                               // (theta^k + cnt*mom) / (cnt+1)
+                                a[k] = div_scalar<kDiv>(__fadd_rn(t[k], __fmul_rn(p.cap_a, a[k])), p.cap_b, p.cap_inv);
+                                if (has2)
+                                    bb[k] = div_scalar<kDiv>(__fadd_rn(__fmul_rn(t[k], t[k]), __fmul_rn(p.cap_a, bb[k])), p.cap_b, p.cap_inv);
+                            }
+                        } else {
+                            if (p.cap_init) {
+                                a[k] = t[k];                                       // mean = theta.clone()
+                                bb[k] = 0.0f;                                      // M2 = zeros_like
+                            } else {
+                                const float d = __fsub_rn(t[k], a[k]);             // delta
+                                a[k] = __fadd_rn(a[k], div_scalar<kDiv>(d, p.cap_a, p.cap_inv));
+                                const float d2 = __fsub_rn(t[k], a[k]);            // delta2
+                                bb[k] = __fadd_rn(bb[k], __fmul_rn(d, d2));
+                            }
+                        }
+                    }
+                    st_stream(p.cap1 + i, make_float4(a[0], a[1], a[2], a[3]));
+                    if (has2) st_stream(p.cap2 + i, make_float4(bb[0], bb[1], bb[2], bb[3]));
+                }
+            }
         }
     }
 }
@@ -293,7 +342,7 @@ static int g_ctas_per_sm = 0;   // 0 = one tile per CTA (default); > 0 = persist
 static int g_unroll = 0;        // 0 = default
 static int g_threads = 0;       // 0 = default
 
-template <int kVariant, bool kHasBuf, bool kPhilox, int kDiv, int kU, int kT>
+template <int kVariant, bool kHasBuf, bool kPhilox, int kDiv, int kU, int kT, int kCap = 0>
 static int launch_shape(const StepParams& p, cudaStream_t st) {
     constexpr uint32_t tile_groups = kT * kU;
     const uint32_t ntiles = (p.n4 - p.q_begin + tile_groups - 1) / tile_groups;
@@ -304,7 +353,7 @@ static int launch_shape(const StepParams& p, cudaStream_t st) {
     }
     if (grid > 0x7FFFFFFFull) grid = 0x7FFFFFFFull;
     if (grid == 0) return BDL_OK;
-    step_kernel<kVariant, kHasBuf, kPhilox, kDiv, kU, kT><<<static_cast<uint32_t>(grid), kT, 0, st>>>(p);
+    step_kernel<kVariant, kHasBuf, kPhilox, kDiv, kU, kT, kCap><<<static_cast<uint32_t>(grid), kT, 0, st>>>(p);
     return check_cuda(cudaGetLastError(), "step_kernel launch");
 }
 
@@ -316,6 +365,12 @@ static int launch_u(const StepParams& p, cudaStream_t st) {
     constexpr int kStreams = ((kVariant == BDL_SGLD) ? 3 : (kVariant == BDL_SGHMC) ? 4 : (kVariant == BDL_CSGHMC) ? 3 : 6) +
                              (kHasBuf ? 1 : 0);
     constexpr int kAutoThreads = kStreams >= 4 ? 64 : (kVariant == BDL_SGLD ? 256 : 128);
+    if (p.cap1) {
+        // fused capture: two more streams per element -> always >= 5, i.e. the 64-thread shape; the launch-shape knobs
+        // of bdl_set_launch_config do not apply (one instantiation per variant keeps the binary small)
+        return p.cap_kind == BDL_CAPTURE_WELFORD ? launch_shape<kVariant, kHasBuf, kPhilox, kDiv, 1, 64, 2>(p, st)
+                               : launch_shape<kVariant, kHasBuf, kPhilox, kDiv, 1, 64, 1>(p, st);
+    }
     const int unroll = g_unroll ? g_unroll : kDefaultUnroll;
     const int threads = g_threads ? g_threads : kAutoThreads;
 #define BDL_SHAPE(UU, TT) if (unroll == UU && threads == TT) return launch_shape<kVariant, kHasBuf, kPhilox, kDiv, UU, TT>(p, st)
@@ -356,7 +411,7 @@ namespace bdl {
 // so Philox counters and the run table keep their absolute indexing (results do not depend on chunking).
 int step_range(int variant, float* theta, const float* g, const float* theta0, float* v, float* m, float* s, float* buf,
                uint64_t n, uint64_t q_begin, uint64_t q_end, const bdl_run* runs, uint32_t nruns, const bdl_run* runs_host,
-               const bdl_scalars* sc, const bdl_noise* nz, cudaStream_t st) {
+               const bdl_scalars* sc, const bdl_noise* nz, const bdl_capture* cap, cudaStream_t st) {
     BDL_REQUIRE(variant >= BDL_SGLD && variant <= BDL_ADAM_CSGHMC, BDL_ERR_INVALID, "bdl_step: unknown variant %d", variant);
     if (n == 0 || q_begin >= q_end) return BDL_OK;   // empty state / empty range: nothing to do (pointers may be null)
     BDL_REQUIRE(theta && (runs || runs_host) && sc && nz, BDL_ERR_INVALID, "bdl_step: null theta/runs/scalars/noise");
@@ -373,7 +428,16 @@ int step_range(int variant, float* theta, const float* g, const float* theta0, f
     BDL_REQUIRE(!adam || (m && s), BDL_ERR_INVALID, "bdl_step: Adam moments m,s required");
     BDL_REQUIRE(!has_buf || buf, BDL_ERR_INVALID, "bdl_step: SGD momentum buffer required when mu != 0");
     BDL_REQUIRE(sc->div_mode == BDL_DIV_IEEE || sc->div_mode == BDL_DIV_RECIP, BDL_ERR_INVALID, "bdl_step: bad div_mode");
-    const void* ptrs[] = {theta, g, theta0, v, m, s, buf, nz->xi_dev};
+    const bool capture = cap != nullptr && cap->kind != BDL_CAPTURE_NONE;
+    if (capture) {
+        BDL_REQUIRE(cap->kind == BDL_CAPTURE_AVG || cap->kind == BDL_CAPTURE_WELFORD, BDL_ERR_INVALID,
+                    "bdl_step_capture: unknown capture kind %d", cap->kind);
+        BDL_REQUIRE(cap->first_dev, BDL_ERR_INVALID, "bdl_step_capture: first-moment buffer required");
+        BDL_REQUIRE(cap->kind == BDL_CAPTURE_AVG || cap->second_dev, BDL_ERR_INVALID, "bdl_step_capture: Welford needs the M2 buffer");
+        BDL_REQUIRE(q_begin == 0 && q_end == (n >> 2), BDL_ERR_UNSUPPORTED, "bdl_step_capture: capture needs the whole range");
+    }
+    const void* ptrs[] = {theta, g, theta0, v, m, s, buf, nz->xi_dev, capture ? cap->first_dev : nullptr,
+                          capture ? cap->second_dev : nullptr};
     for (const void* q : ptrs) BDL_REQUIRE(aligned16(q), BDL_ERR_ALIGN, "bdl_step: pointer %p is not 16-byte aligned", q);
 
     StepParams p{};
@@ -407,6 +471,12 @@ int step_range(int variant, float* theta, const float* g, const float* theta0, f
     p.eps = sc->eps; p.two_alpha = sc->two_alpha; p.nd = sc->nd;
     p.T = sc->temperature; p.inv_T = 1.0f / sc->temperature;
     p.first_step = sc->first_step; p.add_noise = sc->add_noise;
+    if (capture) {
+        p.cap1 = cap->first_dev; p.cap2 = cap->second_dev; p.cap_kind = cap->kind; p.cap_init = cap->init != 0;
+        p.cap_a = cap->cnt;
+        p.cap_b = cap->cnt_plus_1;
+        p.cap_inv = 1.0f / (cap->kind == BDL_CAPTURE_AVG ? cap->cnt_plus_1 : cap->cnt);
+    }
     p.key = host_noise_key(nz->seed, nz->stream_id, nz->subseq);
 
     const bool philox = nz->xi_dev == nullptr;
@@ -431,6 +501,14 @@ int step_range(int variant, float* theta, const float* g, const float* theta0, f
 extern "C" int bdl_step(int variant, float* theta, const float* g, const float* theta0, float* v, float* m,
                         float* s, float* buf, uint64_t n, const bdl_run* runs, uint32_t nruns, const bdl_run* runs_host,
                         const bdl_scalars* sc, const bdl_noise* nz, void* stream) {
-    return bdl::step_range(variant, theta, g, theta0, v, m, s, buf, n, 0, n >> 2, runs, nruns, runs_host, sc, nz,
+    return bdl::step_range(variant, theta, g, theta0, v, m, s, buf, n, 0, n >> 2, runs, nruns, runs_host, sc, nz, nullptr,
+                           static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int bdl_step_capture(int variant, float* theta, const float* g, const float* theta0, float* v, float* m,
+                                float* s, float* buf, uint64_t n, const bdl_run* runs, uint32_t nruns,
+                                const bdl_run* runs_host, const bdl_scalars* sc, const bdl_noise* nz,
+                                const bdl_capture* capture, void* stream) {
+    return bdl::step_range(variant, theta, g, theta0, v, m, s, buf, n, 0, n >> 2, runs, nruns, runs_host, sc, nz, capture,
                            static_cast<cudaStream_t>(stream));
 }

@@ -120,8 +120,10 @@ class FusedModel(nn.Module):
                                 mu=self._opts["sgd_momentum"], beta1=self.beta1, beta2=self.beta2, eps=self.epsilon,
                                 temperature=self.temperature, t=max(self.t, 1), add_noise=should_sample)
 
-    def step_async(self, x, y, net, net0, criterion, lrs, Ninflate=1.0, nd=1.0, should_sample=False):
-        """``forward`` without the host sync: returns (loss tensor, detached logits)."""
+    def step_async(self, x, y, net, net0, criterion, lrs, Ninflate=1.0, nd=1.0, should_sample=False, capture=None):
+        """``forward`` without the host sync: returns (loss tensor, detached logits).  ``capture``: a callable returning
+        an ops.make_capture spec, evaluated once the flat state exists; the sample capture that follows this step in
+        the reference's loop then rides in the same kernel."""
         chain = self._ensure_chain(net, net0)
         if self.VARIANT in (_lib.ADAM_SGHMC, _lib.ADAM_CSGHMC):
             self.t += 1                                   # methods/adam_sghmc.py:494
@@ -129,7 +131,7 @@ class FusedModel(nn.Module):
         loss = criterion(out, y)
         net.zero_grad()                                   # grads -> None; autograd hands us fresh tensors
         loss.backward()
-        chain.update(self._scalars(lrs, Ninflate, nd, should_sample))
+        chain.update(self._scalars(lrs, Ninflate, nd, should_sample), capture=None if capture is None else capture())
         return loss.detach(), out.detach()
 
     def forward(self, x, y, net, net0, criterion, lrs, Ninflate=1.0, nd=1.0, should_sample=False):
@@ -220,6 +222,9 @@ class _RunnerCommon:
         self.model.configure(sgd_momentum=mu, seed=self.seed, noise=self.noise_mode,
                              grad_mode=str(hp.get("grad", "table")), div_mode=self.div_mode, optimizer=self.optimizer)
         self._eval_calls = 0
+        # fuse=1 (default): the moment capture that follows a sampler step runs inside the step kernel; fuse=0: separate
+        # launch right after it, like the reference's statement order (bit-identical either way)
+        self.fuse_capture = str(hp.get("fuse", "1")).lower() not in ("0", "false", "no")
         # checkpoint / sample writers: 'async' (default) overlaps D2H + serialisation with training, 'sync' behaves like
         # the reference's in-line torch.save (file complete when save_ckpt returns)
         self._writer = AsyncWriter(args.device, mode=str(hp.get("io", "async")))
@@ -402,18 +407,24 @@ class BurninRunner(_RunnerCommon):
         with tqdm(train_loader, unit="batch") as tepoch:
             for x, y in tepoch:
                 x, y = x.to(dev, non_blocking=True), y.to(dev, non_blocking=True)
+                captures = collect and (bi + 1) % self.thin == 0
+                spec = None
+                if captures and self.fuse_capture:
+                    spec = lambda: ops.make_capture("avg", self._mom1, self._mom2 if self.nst > 0 else None,
+                                                    self.post_theta_cnt)
                 loss_, out = self.model.step_async(x, y, self.net, self.net0, self.criterion, self._lrs(),
-                                                   self.Ninflate, self.nd)
+                                                   self.Ninflate, self.nd, capture=spec)
                 self.optimizer.step()                     # no-op: the update is part of the fused kernel
                 loss_acc += loss_.double() * len(y)
                 err_acc += out.argmax(dim=1).ne(y).sum()
                 nb_samples += len(y)
                 bi += 1
-                if collect and bi % self.thin == 0:
+                if captures:
                     logger.info("(post-burnin) accumulate posterior samples")
-                    ch = self._chain()
-                    ops.moments_avg(ch.theta, self._mom1, self._mom2 if self.nst > 0 else None, self.post_theta_cnt,
-                                    div_mode=self.div_mode)
+                    if spec is None:
+                        ch = self._chain()
+                        ops.moments_avg(ch.theta, self._mom1, self._mom2 if self.nst > 0 else None, self.post_theta_cnt,
+                                        div_mode=self.div_mode)
                     self.post_theta_cnt += 1
         loss, error = loss_acc.item(), err_acc.item()      # the only host sync of the epoch
         return loss / nb_samples, error / nb_samples, bi
@@ -666,6 +677,10 @@ class CyclicalRunner(_RunnerCommon):
 
                 x, y = x.to(dev, non_blocking=True), y.to(dev, non_blocking=True)
                 kw = dict(should_sample=should_sample) if self.PASS_SHOULD_SAMPLE else {}
+                fused = should_sample and self.fuse_capture
+                if fused:
+                    cyc = sched.get_cycle_number(**pos)
+                    kw["capture"] = lambda: self._capture_spec(cyc)
                 loss_, out = self.model.step_async(x, y, self.net, self.net0, self.criterion, self._lrs(),
                                                    self.Ninflate, self.nd, **kw)
                 self.optimizer.step()                     # no-op (see FusedSGD)
@@ -677,7 +692,7 @@ class CyclicalRunner(_RunnerCommon):
                     cycle_number = sched.get_cycle_number(**pos)
                     if batch_idx % 50 == 0:
                         logger.info(f"Sampling phase: collecting posterior sample at lr={current_lr:.6f}")
-                    self._capture(cycle_number, sched.current_epoch, batch_idx)
+                    self._capture(cycle_number, sched.current_epoch, batch_idx, already_fused=fused)
                     self.samples_collected += 1
                     self.samples_per_cycle[cycle_number] = self.samples_per_cycle.get(cycle_number, 0) + 1
                 elif batch_idx % 50 == 0:
@@ -710,31 +725,38 @@ class CyclicalRunner(_RunnerCommon):
         pass
 
     # ---- per-cycle capture ------------------------------------------------------------------------------------
-    def _capture(self, cycle, epoch, batch_idx):
+    def _capture_spec(self, cycle):
+        """ops.make_capture spec for folding the sample of this step into cycle ``cycle``'s moments; allocates the buffers
+        on the first sample of a cycle.  Called exactly once per captured sample -- by the fused step, or by ``_capture``
+        when the capture runs as its own launch; ``_capture`` then does the bookkeeping."""
         ch = self._chain()
         n = ch.layout.n_padded
-        first = cycle not in self._cyc1
+        first = self._capture_first = cycle not in self._cyc1
         if first:
             self._cyc1[cycle] = alloc_flat(n, ch.device, zero=False)
             self._cyc2[cycle] = alloc_flat(n, ch.device, zero=False)
+        if self.CAPTURE == "avg":
+            cnt = 0 if first else self.samples_per_cycle.get(cycle, 0)          # cycle_count - 1 (csgld.py:286-290)
+            return ops.make_capture("avg", self._cyc1[cycle], self._cyc2[cycle], cnt, init=first)
+        n_w = 1 if first else self.samples_per_cycle.get(cycle, 0) + 1          # Welford's n (csghmc.py:339)
+        return ops.make_capture("welford", self._cyc1[cycle], self._cyc2[cycle], n_w, init=first)
+
+    def _capture(self, cycle, epoch, batch_idx, already_fused=False):
+        """Per-cycle capture (csgld.py:276-293, csghmc.py:327-348).  ``already_fused``: the moment update was part of
+        the step kernel; only the bookkeeping (and the optional raw-sample store) remains."""
+        ch = self._chain()
+        if not already_fused:
+            spec = self._capture_spec(cycle)
+            launch = ops.moments_avg if self.CAPTURE == "avg" else ops.moments_welford
+            launch(ch.theta, self._cyc1[cycle], self._cyc2[cycle], int(spec.cnt), init=bool(spec.init), div_mode=self.div_mode)
+        first = self._capture_first
         if self.CAPTURE == "avg":
             if self.STORE_ALL_SAMPLES and getattr(self.args, "full_sample", False):            # csgld.py:278-279
                 if self._ring is None:
                     self._ring = SampleRing(ch.layout, ch.device, self._expected_samples())
                 self._ring.capture(ch.theta, f"{epoch}_{batch_idx}", self.all_samples)
-            if first:
-                ops.moments_avg(ch.theta, self._cyc1[cycle], self._cyc2[cycle], 0, init=True)
-            else:
-                cycle_count = self.samples_per_cycle.get(cycle, 0) + 1
-                ops.moments_avg(ch.theta, self._cyc1[cycle], self._cyc2[cycle], cycle_count - 1, div_mode=self.div_mode)
         else:   # Welford with the reference's double-counted n (Appendix B.3): n runs 3, 5, 7, ...
-            if first:
-                ops.moments_welford(ch.theta, self._cyc1[cycle], self._cyc2[cycle], 1, init=True)
-                self.samples_per_cycle[cycle] = 1
-            else:
-                n_w = self.samples_per_cycle.get(cycle, 0) + 1
-                ops.moments_welford(ch.theta, self._cyc1[cycle], self._cyc2[cycle], n_w, div_mode=self.div_mode)
-                self.samples_per_cycle[cycle] = n_w
+            self.samples_per_cycle[cycle] = 1 if first else self.samples_per_cycle.get(cycle, 0) + 1
 
     def _expected_samples(self):
         """Number of captures the schedule will make over the whole run (host arithmetic, sizes the ring)."""

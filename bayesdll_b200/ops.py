@@ -13,7 +13,7 @@ import torch
 from . import _lib
 from ._lib import ADAM_SGHMC, CSGHMC, DIV_RECIP, SGHMC, SGLD, STREAM_STEP, STREAM_USER, BdlError, Noise, Scalars
 
-__all__ = ["make_scalars", "upload_runs", "step", "philox_normal", "moments_avg", "moments_welford",
+__all__ = ["make_scalars", "upload_runs", "step", "make_capture", "philox_normal", "moments_avg", "moments_welford",
            "capture_ring", "draw", "ensemble", "ce_err", "lse_accum", "lse_rescale", "lse_finalize", "calibrate", "bma_mean",
            "nll_temperature",
            "set_launch_config"]
@@ -109,19 +109,39 @@ def make_noise(xi=None, seed=0, subseq=0, stream_id=STREAM_STEP):
 # ----------------------------------------------------------------------------------------------
 # kernels
 # ----------------------------------------------------------------------------------------------
-def step(variant, theta, g, theta0, v, m, s, buf, runs_dev, nruns, scalars, noise):
+def make_capture(kind, first, second, cnt, init=False):
+    """Capture spec for the fused step (bdl_capture).  kind 'avg': running moments, ``cnt`` = samples averaged so far
+    (the argument of moments_avg); kind 'welford': ``cnt`` = n of moments_welford.  ``second`` may be None for 'avg'."""
+    cap = _lib.Capture()
+    cap.kind = {"avg": _lib.CAPTURE_AVG, "welford": _lib.CAPTURE_WELFORD}[kind]
+    cap.init = int(bool(init))
+    cap.first_dev = _ptr(first, "capture first")
+    cap.second_dev = _ptr(second, "capture second", allow_none=(kind == "avg")) or 0
+    cap.cnt = float(cnt)
+    cap.cnt_plus_1 = float(cnt + 1)
+    cap._keep = (first, second)
+    return cap
+
+
+def step(variant, theta, g, theta0, v, m, s, buf, runs_dev, nruns, scalars, noise, capture=None):
     """One fused sampler update (bdl_step).  Tensors are padded-flat fp32 CUDA buffers; unused state may be
-    None.  ``noise`` from make_noise(); ``runs_dev`` from upload_runs()."""
+    None.  ``noise`` from make_noise(); ``runs_dev`` from upload_runs().  ``capture`` (make_capture) additionally folds
+    the new theta into running moments in the same pass (bdl_step_capture)."""
     n = theta.numel()
     for name, t in (("g", g), ("theta0", theta0), ("v", v), ("m", m), ("s", s), ("buf", buf)):
         if t is not None and t.numel() != n:
             raise BdlError(f"{name}: length {t.numel()} != theta length {n}")
-    rc = _lib.load().bdl_step(
-        int(variant), _ptr(theta, "theta"), _ptr(g, "g", allow_none=True), _ptr(theta0, "theta0", allow_none=True),
-        _ptr(v, "v", allow_none=True), _ptr(m, "m", allow_none=True), _ptr(s, "s", allow_none=True),
-        _ptr(buf, "buf", allow_none=True), n, _ptr(runs_dev, "runs", torch.uint8), nruns,
-        getattr(runs_dev, "_bdl_host", None), C.byref(scalars), C.byref(noise), _stream())
-    _lib.check(rc, "bdl_step")
+    args = (int(variant), _ptr(theta, "theta"), _ptr(g, "g", allow_none=True), _ptr(theta0, "theta0", allow_none=True),
+            _ptr(v, "v", allow_none=True), _ptr(m, "m", allow_none=True), _ptr(s, "s", allow_none=True),
+            _ptr(buf, "buf", allow_none=True), n, _ptr(runs_dev, "runs", torch.uint8), nruns,
+            getattr(runs_dev, "_bdl_host", None), C.byref(scalars), C.byref(noise))
+    if capture is None:
+        _lib.check(_lib.load().bdl_step(*args, _stream()), "bdl_step")
+        return
+    for t in capture._keep:
+        if t is not None and t.numel() != n:
+            raise BdlError(f"capture buffer length {t.numel()} != theta length {n}")
+    _lib.check(_lib.load().bdl_step_capture(*args, C.byref(capture), _stream()), "bdl_step_capture")
 
 
 def philox_normal(out, seed, stream_id=STREAM_USER, subseq=0):

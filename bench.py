@@ -347,6 +347,38 @@ def variant_rates(lay, theta, g, theta0, v, runs_dev, nruns, device, world, peak
         gbs = bpp * n_dense / (ms * 1e-3) / 1e9
         out[name] = {"params_per_s": world * n_dense / (ms * 1e-3), "ms_per_step": ms, "bytes_per_param": bpp,
                      "achieved_gbs_per_gpu": gbs, "frac_of_measured_peak": gbs / peak}
+    # post-burn-in steady state of BASELINE.json configs[2] (thin = 1): every step is followed by a moment capture.
+    # Fused (bdl_step_capture, 40 B/param) vs the two launches it replaces (24 + 20 = 44 B/param).
+    sc = make_scalars(_lib.SGHMC)
+    mom1, mom2 = m, s2
+
+    def timed(fn):
+        for i in range(3):
+            fn(i)
+        barrier(world)
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for i in range(steps):
+            fn(3 + i)
+        b.record()
+        torch.cuda.synchronize()
+        return allmax(a.elapsed_time(b), world, device) / steps
+
+    def fused(i):
+        ops.step(_lib.SGHMC, theta, g, theta0, v, None, None, None, runs_dev, nruns, sc,
+                 ops.make_noise(seed=seed, subseq=3000 + i), capture=ops.make_capture("avg", mom1, mom2, 7 + i))
+
+    def separate(i):
+        ops.step(_lib.SGHMC, theta, g, theta0, v, None, None, None, runs_dev, nruns, sc, ops.make_noise(seed=seed, subseq=3000 + i))
+        ops.moments_avg(theta, mom1, mom2, 7 + i)
+    ms_f, ms_s = timed(fused), timed(separate)
+    gbs = 40 * n_dense / (ms_f * 1e-3) / 1e9
+    out["sghmc_step_with_fused_moment_capture"] = {
+        "params_per_s": world * n_dense / (ms_f * 1e-3), "ms_per_step": ms_f, "bytes_per_param": 40,
+        "achieved_gbs_per_gpu": gbs, "frac_of_measured_peak": gbs / peak, "separate_launches_ms": ms_s,
+        "speedup_vs_separate": ms_s / ms_f,
+        "note": "bdl_step_capture: step + running-moment update of the new theta in one pass (thin=1 steady state)"}
     # the shape Runner.train() actually launches: one run per tensor, each row pointing at that tensor's own
     # (separately allocated) autograd gradient -- no flat gradient buffer, no gather pass
     del m, s2, buf

@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define BDL_ABI_VERSION 2
+#define BDL_ABI_VERSION 3
 
 typedef enum {
     BDL_OK = 0,
@@ -132,6 +132,30 @@ int bdl_step(int variant, float* theta_dev, const float* g_dev, const float* the
              float* v_dev, float* m_dev, float* s_dev, float* buf_dev, uint64_t n,
              const bdl_run* runs_dev, uint32_t nruns, const bdl_run* runs_host, const bdl_scalars* scalars,
              const bdl_noise* noise, void* stream);
+
+/* Fused step + sample capture.  After burn-in (or in the sampling phase of a cycle) the reference folds the NEW theta
+ * into its running moments right after the optimizer step (methods/sghmc.py:242-249, methods/csgld.py:276-293,
+ * methods/csghmc.py:327-348) -- with thin = 1 that is every step.  bdl_step_capture does both in one pass: the new
+ * theta never leaves the registers, which saves the capture kernel's re-read (SGHMC + moments: 40 instead of
+ * 24 + 20 = 44 B/param).  Arithmetic is exactly bdl_step followed by bdl_moments_avg / bdl_moments_welford on the
+ * same stream (bit-identical; division semantics = scalars->div_mode).  Tensors skipped by BDL_CLS_SKIP are still
+ * captured (their unchanged theta is part of the sample), as parameters_to_vector does. */
+#define BDL_CAPTURE_NONE 0
+#define BDL_CAPTURE_AVG 1       /* bdl_moments_avg:     first = mom1, second = mom2 (may be NULL: nst == 0)      */
+#define BDL_CAPTURE_WELFORD 2   /* bdl_moments_welford: first = mean, second = M2                                */
+typedef struct {
+    int32_t kind;          /* BDL_CAPTURE_*                                                                     */
+    int32_t init;          /* != 0: first sample (avg: mom1 = theta*1.0, mom2 = theta**2; Welford: mean = theta, M2 = 0) */
+    float* first_dev;
+    float* second_dev;
+    float cnt;             /* avg: fp32(cnt) ; Welford: fp32(n)                                                 */
+    float cnt_plus_1;      /* avg: fp32(cnt + 1) ; Welford: unused                                              */
+} bdl_capture;
+/* capture == NULL or kind == BDL_CAPTURE_NONE: identical to bdl_step. */
+int bdl_step_capture(int variant, float* theta_dev, const float* g_dev, const float* theta0_dev,
+                     float* v_dev, float* m_dev, float* s_dev, float* buf_dev, uint64_t n,
+                     const bdl_run* runs_dev, uint32_t nruns, const bdl_run* runs_host, const bdl_scalars* scalars,
+                     const bdl_noise* noise, const bdl_capture* capture, void* stream);
 
 /* Fill out[0..n) with exactly the N(0,1) stream the step / draw kernels use for (seed, stream_id,
  * subseq).  Test and diagnostics entry (KS / moment tests; external-vs-in-kernel equivalence). */

@@ -206,6 +206,23 @@ def test_async_and_sync_checkpoints_are_identical(cuda_device, tmp_path):
     assert same(outs["async"], outs["sync"])
 
 
+@pytest.mark.parametrize("name", ["sghmc", "csgld", "csghmc", "sgld_nst0"])
+def test_unfused_capture_is_identical(cuda_device, tmp_path, name):
+    """fuse=0 launches the moment capture as its own kernel after the step (the reference's statement order); the default
+    folds it into the step kernel.  Same trajectory, same moments, bit for bit."""
+    z, runner, _, _, tape = _run(name, cuda_device, tmp_path, extra_hp=dict(fuse=0))
+    assert not runner.fuse_capture and tape.pos == int(z["tape_used"])
+    got = runner._dense(runner.model.chain.theta).cpu().numpy()
+    assert np.array_equal(got.view(np.uint32), z["theta_final"].view(np.uint32))
+    if "post_theta_mom1" in z.files:
+        assert np.array_equal(runner.post_theta_mom1.cpu().numpy().view(np.uint32), z["post_theta_mom1"].view(np.uint32))
+        assert runner.post_theta_cnt == int(z["post_theta_cnt"])
+    if "cycles" in z.files:
+        for c in z["cycles"].tolist():
+            assert runner.samples_per_cycle[c] == int(z[f"cyc{c}_count"])
+            assert np.array_equal(runner.cycle_theta_mom1[c].cpu().numpy().view(np.uint32), z[f"cyc{c}_mom1"].view(np.uint32))
+
+
 def test_runner_flat_gradient_mode_is_identical(cuda_device, tmp_path):
     """grad=flat (gather into the flat buffer) and grad=table (read p.grad in place) give the same trajectory."""
     z, runner, _, _, _ = _run("sghmc", cuda_device, tmp_path, extra_hp=dict(grad="flat"))
@@ -292,8 +309,8 @@ def test_csgld_full_sample_uses_hbm_ring(cuda_device, tmp_path):
     captured = {}
     orig = runner._capture
 
-    def spy(cycle, epoch, batch_idx):
-        orig(cycle, epoch, batch_idx)
+    def spy(cycle, epoch, batch_idx, **kw):
+        orig(cycle, epoch, batch_idx, **kw)
         captured[f"{epoch}_{batch_idx}"] = runner._dense(runner.model.chain.theta).clone()
     runner._capture = spy
     cwd = os.getcwd()

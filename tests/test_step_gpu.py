@@ -185,3 +185,93 @@ def test_inline_run_table_equals_device_run_table(cuda_device, bias_mode):
                  ops.make_noise(seed=5, subseq=2))
         outs.append(st)
     assert torch.equal(outs[0]["theta"], outs[1]["theta"]) and torch.equal(outs[0]["v"], outs[1]["v"])
+
+
+@pytest.mark.parametrize("variant_name", ["sgld", "sghmc", "csghmc", "adam_sghmc", "adam_csghmc"])
+@pytest.mark.parametrize("kind", ["avg", "avg_nomom2", "welford"])
+@pytest.mark.parametrize("own_g", [False, True])
+def test_fused_capture_equals_step_then_moments(cuda_device, variant_name, kind, own_g):
+    """bdl_step_capture == bdl_step followed by bdl_moments_avg / bdl_moments_welford, bit for bit: first sample (init)
+    and later samples, both division modes, in-kernel Philox, ragged layout, a tensor without gradient (BDL_CLS_SKIP:
+    left untouched by the step, still part of the captured sample) and -- via the oracle -- the reference arithmetic."""
+    from bayesdll_b200 import _lib, ops
+    rng = np.random.default_rng(abs(hash((variant_name, kind, own_g))) % 2**32)
+    lay = _random_layout(rng, 23, 4000)
+    n = lay.n_padded
+    dev = cuda_device
+    variant = dict(sgld=_lib.SGLD, sghmc=_lib.SGHMC, csghmc=_lib.CSGHMC, adam_sghmc=_lib.ADAM_SGHMC,
+                   adam_csghmc=_lib.ADAM_CSGHMC)[variant_name]
+    mu = 0.5 if variant_name in ("sgld", "adam_sghmc") else 0.0
+    adam = variant_name.startswith("adam")
+    f = lambda scale=1.0: torch.from_numpy((rng.standard_normal(n) * scale).astype(np.float32)).to(dev)
+    init_state = dict(theta=f(0.1), v=f(0.01), m=f(0.01), s=f(1e-3).abs() + 1e-6, buf=f(0.01))
+    theta0, g = f(0.1), f(0.05)
+    keep, ptrs = [], None
+    if own_g:
+        ptrs = []
+        for sg in lay.segments:
+            t = torch.full((sg.numel + 8,), float("nan"), device=dev)
+            t[:sg.numel] = g[sg.begin:sg.begin + sg.numel]
+            keep.append(t)
+            ptrs.append(t.data_ptr())
+    tab = lay.run_table("uninformative", grad_ptrs=ptrs if own_g else [0] * len(lay.segments))
+    skip_idx = 5
+    tab[skip_idx].cls |= _lib.CLS_SKIP                                  # this tensor has p.grad None
+    runs_dev, nruns = ops.upload_runs(tab, dev)
+    for div in (_lib.DIV_IEEE, _lib.DIV_RECIP):
+        sc = ops.make_scalars(variant, lr_body=1e-3, lr_head=1e-2, ND=1840, Ninflate=3.0, prior_sig=0.9, nd=0.7, alpha=0.18,
+                              mu=mu, t=4, first_step=False, add_noise=True, div_mode=div)
+        A = {k: t.clone() for k, t in init_state.items()}               # fused
+        B = {k: t.clone() for k, t in init_state.items()}               # step, then capture
+        capA = [torch.full((n,), 7.0, device=dev), torch.full((n,), 7.0, device=dev)]
+        capB = [t.clone() for t in capA]
+        second = None if kind == "avg_nomom2" else 1
+
+        def run(S, cap, fused, cnt, init, subseq):
+            spec = None
+            if fused:
+                spec = ops.make_capture("welford" if kind == "welford" else "avg", cap[0],
+                                        None if second is None else cap[1], cnt, init=init)
+            ops.step(variant, S["theta"], None if own_g else g, None if variant_name == "csghmc" else theta0,
+                     None if variant_name == "sgld" else S["v"], S["m"] if adam else None, S["s"] if adam else None,
+                     S["buf"] if mu else None, runs_dev, nruns, sc, ops.make_noise(seed=9, subseq=subseq), capture=spec)
+            if not fused:
+                if kind == "welford":
+                    ops.moments_welford(S["theta"], cap[0], cap[1], cnt, init=init, div_mode=div)
+                else:
+                    ops.moments_avg(S["theta"], cap[0], None if second is None else cap[1], cnt, init=init, div_mode=div)
+
+        seg = lay.segments[skip_idx]
+        before = A["theta"][seg.begin:seg.end].clone()
+        for step_no, (cnt, init) in enumerate([(1 if kind == "welford" else 0, True), (3, False), (5, False)]):
+            run(A, capA, True, cnt, init, step_no)
+            run(B, capB, False, cnt, init, step_no)
+        torch.cuda.synchronize()
+        for k in A:
+            assert torch.equal(A[k], B[k]), f"{variant_name} {k}: fused step differs from the plain step (div={div})"
+        assert torch.equal(capA[0], capB[0]), f"{variant_name}/{kind}: first moment differs (div={div})"
+        if second is not None:
+            assert torch.equal(capA[1], capB[1]), f"{variant_name}/{kind}: second moment differs (div={div})"
+        else:
+            assert torch.equal(capA[1], torch.full((n,), 7.0, device=dev))          # untouched
+        assert torch.isfinite(capA[0]).all()
+        assert torch.equal(A["theta"][seg.begin:seg.end], before)                  # skipped tensor left untouched ...
+        assert not torch.equal(capA[0][seg.begin:seg.end], torch.full((seg.end - seg.begin,), 7.0, device=dev))  # ... but captured
+
+
+def test_fused_capture_argument_errors(cuda_device):
+    from bayesdll_b200 import _lib, ops
+    from bayesdll_b200.flat import FlatLayout
+    lay = FlatLayout([("a.weight", (64,))], "classifier")
+    runs_dev, nruns = ops.upload_runs(lay.run_table("informative"), cuda_device)
+    sc = ops.make_scalars(_lib.SGHMC, lr_body=1e-3, lr_head=1e-3, ND=10)
+    z = lambda n: torch.zeros(n, device=cuda_device)
+    with pytest.raises(_lib.BdlError, match="length"):
+        ops.step(_lib.SGHMC, z(64), z(64), z(64), z(64), None, None, None, runs_dev, nruns, sc, ops.make_noise(seed=1),
+                 capture=ops.make_capture("avg", z(32), None, 1))
+    with pytest.raises(_lib.BdlError, match="tensor required"):
+        ops.make_capture("welford", z(64), None, 1)
+    cap = ops.make_capture("avg", z(64), z(64), 1)
+    cap.kind = 9
+    with pytest.raises(_lib.BdlError, match="capture kind"):
+        ops.step(_lib.SGHMC, z(64), z(64), z(64), z(64), None, None, None, runs_dev, nruns, sc, ops.make_noise(seed=1), capture=cap)
