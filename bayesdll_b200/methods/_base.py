@@ -317,7 +317,7 @@ class _RunnerCommon:
             logger.info(f"Logits on val set saved at {self.save_logits(*val, suffix='val')}")
         logger.info(f"Logits on test set saved at {self.save_logits(*test, suffix='test')}")
         if save_ckpt:
-            logger.info(f"Checkpoint saved at {self.save_ckpt(ep)}")
+            logger.info(f"Checkpoint saved at {self.save_ckpt(ep, wait=False)}")
         self._calibrate_and_log(test[0], test[1], None if val is None else val[:2], fmt_topt)
 
 
@@ -485,7 +485,9 @@ class BurninRunner(_RunnerCommon):
     def _ckpt_extra(self):
         return {}
 
-    def save_ckpt(self, epoch):
+    def save_ckpt(self, epoch, wait=True):
+        """Same file, keys and layout as methods/sghmc.py:370-388.  Called directly it returns once the file is complete,
+        like the reference; the training loop passes ``wait=False`` and lets the writer thread finish it."""
         fname = os.path.join(self.args.log_dir, "ckpt.pt")
         ck = {}
         if self.CKPT_HAS_LAST_THETA:
@@ -500,6 +502,8 @@ class BurninRunner(_RunnerCommon):
         ck.update(self._ckpt_extra())
         ck["epoch"] = epoch
         self._writer.submit(fname, ck)
+        if wait:
+            self._writer.flush()
         return fname
 
     def _optimizer_state_snapshot(self):
@@ -711,7 +715,7 @@ class CyclicalRunner(_RunnerCommon):
                         likelihood = np.array(self.full_batch_likelihoods(train_loader))
                         self.cycle_likelihoods[cycle_number] = likelihood
                         logger.info(f"Cycle {cycle_number} full batch likelihood: {likelihood.mean():.6e}")
-                        self.save_ckpt(epoch=sched.current_epoch)
+                        self.save_ckpt(epoch=sched.current_epoch, wait=False)
                         if self.STORE_ALL_SAMPLES and getattr(args, "full_sample", False):
                             self._writer.submit("all_samples_TEST.ckpt", dict(self.all_samples))   # csgld.py:328-329
                         self._after_cycle_completed(cycle_number)
@@ -876,7 +880,8 @@ class CyclicalRunner(_RunnerCommon):
         return {c: 1.0 / len(weights) for c in weights}
 
     # ---- checkpoints (methods/csgld.py:470-506) ----------------------------------------------------------------
-    def save_ckpt(self, epoch):
+    def save_ckpt(self, epoch, wait=True):
+        """Same file, keys and layout as methods/csgld.py:470-490; ``wait`` as in BurninRunner.save_ckpt."""
         fname = os.path.join(self.args.log_dir, f"{self.current_cycle}_ckpt.pt")
         last = self._dense(self._chain().theta) if self.LAST_THETA_AS_VECTOR else self._state_dict_copy()
         # moments of finished cycles never change again: only the newest cycle's buffers are snapshotted
@@ -891,6 +896,8 @@ class CyclicalRunner(_RunnerCommon):
             "current_cycle": self.current_cycle,
             "samples_per_cycle": dict(self.samples_per_cycle),
         })
+        if wait:
+            self._writer.flush()
         return fname
 
     def load_ckpt(self, ckpt_path):

@@ -37,6 +37,23 @@ def _stream():
     return torch.cuda.current_stream().cuda_stream
 
 
+def _on_tensor_device(fn):
+    """Run ``fn`` with the CUDA device of its first tensor argument current (the C ABI launches on the calling thread's
+    current device and stream; torch's own ops switch devices implicitly, a ctypes call does not)."""
+    import functools
+
+    @functools.wraps(fn)
+    def wrapper(*args, **kwargs):
+        for a in args:
+            if isinstance(a, torch.Tensor):
+                if a.is_cuda and a.device.index != torch.cuda.current_device():
+                    with torch.cuda.device(a.device):
+                        return fn(*args, **kwargs)
+                break
+        return fn(*args, **kwargs)
+    return wrapper
+
+
 def set_launch_config(ctas_per_sm=0, unroll=0, threads=0):
     _lib.check(_lib.load().bdl_set_launch_config(ctas_per_sm, unroll, threads), "bdl_set_launch_config")
 
@@ -123,6 +140,7 @@ def make_capture(kind, first, second, cnt, init=False):
     return cap
 
 
+@_on_tensor_device
 def step(variant, theta, g, theta0, v, m, s, buf, runs_dev, nruns, scalars, noise, capture=None):
     """One fused sampler update (bdl_step).  Tensors are padded-flat fp32 CUDA buffers; unused state may be
     None.  ``noise`` from make_noise(); ``runs_dev`` from upload_runs().  ``capture`` (make_capture) additionally folds
@@ -144,6 +162,7 @@ def step(variant, theta, g, theta0, v, m, s, buf, runs_dev, nruns, scalars, nois
     _lib.check(_lib.load().bdl_step_capture(*args, C.byref(capture), _stream()), "bdl_step_capture")
 
 
+@_on_tensor_device
 def philox_normal(out, seed, stream_id=STREAM_USER, subseq=0):
     rc = _lib.load().bdl_philox_normal(_ptr(out, "out"), out.numel(), int(seed) & 0xFFFFFFFFFFFFFFFF, int(stream_id),
                                        int(subseq) & 0xFFFFFFFFFFFFFFFF, _stream())
@@ -151,6 +170,7 @@ def philox_normal(out, seed, stream_id=STREAM_USER, subseq=0):
     return out
 
 
+@_on_tensor_device
 def moments_avg(theta, mom1, mom2, cnt, init=False, div_mode=DIV_RECIP):
     """init: mom1 = theta*1.0, mom2 = theta**2.  else mom <- (theta^k + cnt*mom)/(cnt+1)."""
     rc = _lib.load().bdl_moments_avg(_ptr(theta, "theta"), _ptr(mom1, "mom1"), _ptr(mom2, "mom2", allow_none=True),
@@ -158,6 +178,7 @@ def moments_avg(theta, mom1, mom2, cnt, init=False, div_mode=DIV_RECIP):
     _lib.check(rc, "bdl_moments_avg")
 
 
+@_on_tensor_device
 def moments_welford(theta, mean, M2, n, init=False, div_mode=DIV_RECIP):
     rc = _lib.load().bdl_moments_welford(_ptr(theta, "theta"), _ptr(mean, "mean"), _ptr(M2, "M2"), theta.numel(),
                                          float(n), int(init), div_mode, _stream())
@@ -168,6 +189,7 @@ def set_ring_config(chunks_per_cta=4):
     _lib.check(_lib.load().bdl_set_ring_config(int(chunks_per_cta)), "bdl_set_ring_config")
 
 
+@_on_tensor_device
 def capture_ring(theta, ring, slot):
     n = theta.numel()
     if ring.dim() != 2 or ring.shape[1] != n or not (0 <= slot < ring.shape[0]):
@@ -179,6 +201,7 @@ def capture_ring(theta, ring, slot):
 VAR_FROM_MOMENTS, VAR_FROM_WELFORD, VAR_TINY, VAR_GIVEN = 0, 1, 2, 3
 
 
+@_on_tensor_device
 def draw(mean, second, out, var_mode, scale, noise, div_mode=DIV_RECIP, center=None):
     """out = (center or mean) + sqrt(var(mean, second)) * eps   (see bdl_draw)."""
     rc = _lib.load().bdl_draw(_ptr(mean, "mean"), _ptr(second, "second", allow_none=True),
@@ -187,6 +210,7 @@ def draw(mean, second, out, var_mode, scale, noise, div_mode=DIV_RECIP, center=N
     _lib.check(rc, "bdl_draw")
 
 
+@_on_tensor_device
 def ensemble(logits_all, out, nst, weight=1.0, mode=0):
     """logits_all [B,K,S] -> out [B,K] (see bdl_ensemble).  nst == 0 -> no '- log S'."""
     B, K, S = logits_all.shape
@@ -197,6 +221,7 @@ def ensemble(logits_all, out, nst, weight=1.0, mode=0):
     return out
 
 
+@_on_tensor_device
 def ce_err(logits, y, loss_sum, err_count):
     B, K = logits.shape
     rc = _lib.load().bdl_ce_err(_ptr(logits, "logits"), _ptr(y, "y", torch.int64), B, K,
@@ -205,6 +230,7 @@ def ce_err(logits, y, loss_sum, err_count):
     _lib.check(rc, "bdl_ce_err")
 
 
+@_on_tensor_device
 def lse_accum(logits, m, s):
     """Running logsumexp over samples of log_softmax(logits): (m, s) <- combine((m, s), log_softmax(logits))."""
     B, K = logits.shape
@@ -212,11 +238,13 @@ def lse_accum(logits, m, s):
     _lib.check(rc, "bdl_lse_accum")
 
 
+@_on_tensor_device
 def lse_rescale(m_local, m_global, s):
     rc = _lib.load().bdl_lse_rescale(_ptr(m_local, "m_local"), _ptr(m_global, "m_global"), _ptr(s, "s"), s.numel(), _stream())
     _lib.check(rc, "bdl_lse_rescale")
 
 
+@_on_tensor_device
 def lse_finalize(m, s, out, n_samples, weight=1.0, mode=0):
     B, K = out.shape
     log_S = float(np.float32(np.log(n_samples))) if n_samples > 0 else 0.0
@@ -226,6 +254,7 @@ def lse_finalize(m, s, out, n_samples, weight=1.0, mode=0):
     return out
 
 
+@_on_tensor_device
 def calibrate(logits, labels, edges, temperature=1.0, use_f64=False, want_binned=False):
     """Returns device tensors (bin_size[M], acc_sum[M], conf_sum[M], nll_sum[1], near_edge[1], binned|None)."""
     N, K = logits.shape
@@ -243,6 +272,7 @@ def calibrate(logits, labels, edges, temperature=1.0, use_f64=False, want_binned
     return stats[:M], stats[M:2 * M], stats[2 * M:3 * M], stats[3 * M:], near, binned
 
 
+@_on_tensor_device
 def bma_mean(logits_all, out):
     """logits_all [B,K,S] -> out [B,K]: fp32 running sum over S in order, divided by fp32(S) (see bdl_bma_mean)."""
     B, K, S = logits_all.shape
@@ -251,6 +281,7 @@ def bma_mean(logits_all, out):
     return out
 
 
+@_on_tensor_device
 def nll_temperature(logits, labels, temperature, row_nll, out_mean):
     """out_mean[0] = mean_i(logsumexp(logits[i]/T) - logits[i,y_i]/T) in fp64 (see bdl_nll_temperature)."""
     N, K = logits.shape

@@ -16,14 +16,29 @@ methods/csghmc_fs.py:176-181): the GPU idles while 0.2-20 GB go through a device
 ``net.state_dict()`` looks like after one snapshot launch instead of ~300 per-tensor clones, and it moves to the host
 with one copy.
 """
+import atexit
 import os
 import queue
 import threading
+import weakref
 from collections import OrderedDict
 
 import torch
 
 PIN_LIMIT_BYTES = 4 << 30      # stage through pinned memory up to this much per job; larger jobs use pageable copies
+
+_LIVE_WRITERS = weakref.WeakSet()
+
+
+@atexit.register
+def _close_all_writers():
+    """Join every writer thread before the interpreter starts tearing down: a daemon thread that wakes up during
+    finalisation inside torch / CUDA code aborts the process ('terminate called without an active exception')."""
+    for w in list(_LIVE_WRITERS):
+        try:
+            w.close()
+        except Exception:
+            pass
 
 
 class FlatBackedStateDict(OrderedDict):
@@ -96,13 +111,16 @@ def _atomic_save(obj, path, serializer):
 
 
 class AsyncWriter:
-    """One writer thread + one side stream per runner.  ``mode='sync'`` performs the same work inline (the reference's
-    behaviour: the file exists when ``save_ckpt`` returns)."""
+    """One writer thread (+ one side stream on CUDA devices) per runner.  ``mode='sync'`` performs the same work inline
+    (the reference's behaviour: the file exists when ``save_ckpt`` returns)."""
 
     def __init__(self, device, mode="async"):
         if mode not in ("async", "sync"):
             raise ValueError(f"io mode must be 'async' or 'sync', got {mode!r}")
-        self.device = torch.device(device)
+        device = torch.device(device)
+        if device.type == "cuda" and device.index is None:        # args.device is often a bare 'cuda'
+            device = torch.device("cuda", torch.cuda.current_device())
+        self.device = device
         self.mode = mode
         self._q = None
         self._thread = None
@@ -110,7 +128,7 @@ class AsyncWriter:
         self._error = None
         self.pending_paths = set()
         self._lock = threading.Lock()
-        self.stats = {"jobs": 0, "bytes": 0, "submit_s": 0.0}
+        self.stats = {"jobs": 0, "bytes": 0}
 
     # ---- public -----------------------------------------------------------------------------------------
     def submit(self, path, obj, serializer=torch.save):
@@ -121,29 +139,41 @@ class AsyncWriter:
         nbytes = _nbytes(obj)
         self.stats["jobs"] += 1
         self.stats["bytes"] += nbytes
-        if self.mode == "sync" or self.device.type != "cuda":
+        if self.mode == "sync":
             _atomic_save(to_host(obj), path, serializer)
             return path
         self._start()
-        ev = torch.cuda.Event()
-        ev.record(torch.cuda.current_stream(self.device))
+        ev = None
+        if self.device.type == "cuda":
+            ev = torch.cuda.Event()
+            ev.record(torch.cuda.current_stream(self.device))
         with self._lock:
             self.pending_paths.add(path)
         self._q.put((path, obj, serializer, ev, nbytes))
         return path
 
     def flush(self):
-        if self._q is not None:
-            self._q.join()
+        """Wait for every submitted file; re-raise the first failure.  Never waits on a dead writer thread."""
+        q = self._q
+        if q is not None:
+            with q.all_tasks_done:
+                while q.unfinished_tasks:
+                    if self._thread is None or not self._thread.is_alive():
+                        break
+                    q.all_tasks_done.wait(timeout=0.2)
+            if q.unfinished_tasks and self._error is None:
+                self._error = RuntimeError("writer thread exited with jobs outstanding")
         if self._error is not None:
             self._raise()
 
     def close(self):
         if self._thread is not None:
-            self._q.join()
-            self._q.put(None)
-            self._thread.join()
-            self._thread = self._q = None
+            try:
+                self.flush()
+            finally:
+                self._q.put(None)
+                self._thread.join(timeout=10)
+                self._thread = self._q = None
         if self._error is not None:
             self._raise()
 
@@ -157,39 +187,55 @@ class AsyncWriter:
         raise RuntimeError(f"asynchronous write failed: {err!r}") from err
 
     def _start(self):
-        if self._thread is not None:
+        if self._thread is not None and self._thread.is_alive():
             return
+        if self._thread is not None:                 # a previous thread died: surface that instead of queueing forever
+            self._error = self._error or RuntimeError("writer thread is not running")
+            self._raise()
         self._q = queue.Queue()
-        self._stream = torch.cuda.Stream(self.device)
+        if self.device.type == "cuda":
+            self._stream = torch.cuda.Stream(self.device)
         self._thread = threading.Thread(target=self._run, name="bdl-writer", daemon=True)
         self._thread.start()
+        _LIVE_WRITERS.add(self)
 
     def _run(self):
-        torch.cuda.set_device(self.device)
-        while True:
-            job = self._q.get()
-            if job is None:
-                self._q.task_done()
-                return
-            path, obj, serializer, ev, nbytes = job
-            try:
+        try:
+            if self.device.type == "cuda":
+                torch.cuda.set_device(self.device)
+            while True:
+                job = self._q.get()
+                if job is None:
+                    self._q.task_done()
+                    return
+                self._one(*job)
+        except BaseException as e:                  # anything outside a job: remember it, flush() reports it
+            if self._error is None:
+                self._error = e
+
+    def _one(self, path, obj, serializer, ev, nbytes):
+        try:
+            if self.device.type == "cuda":
                 with torch.cuda.stream(self._stream):
                     self._stream.wait_event(ev)
                     host = to_host(obj, pin=nbytes <= PIN_LIMIT_BYTES)
                     self._stream.synchronize()
-                del obj, job
-                _atomic_save(host, path, serializer)
-            except BaseException as e:          # surfaced by the next submit() / flush()
-                if self._error is None:
-                    self._error = e
-            finally:
-                with self._lock:
-                    self.pending_paths.discard(path)
-                self._q.task_done()
+            else:
+                host = to_host(obj)
+            del obj
+            _atomic_save(host, path, serializer)
+        except BaseException as e:                  # surfaced by the next submit() / flush()
+            if self._error is None:
+                self._error = e
+        finally:
+            with self._lock:
+                self.pending_paths.discard(path)
+            self._q.task_done()
 
     def __del__(self):
         try:
-            if self._thread is not None and self._q is not None:
+            if self._thread is not None and self._q is not None and self._thread.is_alive():
                 self._q.put(None)
+                self._thread.join(timeout=5)
         except Exception:
             pass

@@ -8,6 +8,9 @@ loaders are synthetic tensors of the BASELINE.json shapes (no dataset download) 
     python examples/demo_synthetic.py --backbone resnet101 --method csghmc --num_cycles 2 --epochs 4 \
         --hparams prior_sig=1.0,Ninflate=1.0,nd=0.01,burnin=0,momentum_decay=0.18,thin=2,bias=informative,nst=2 \
         --lr 1e-4 --lr_head 1e-2 --batch_size 16 --train_batches 8 --pretrained synthetic
+    python examples/demo_synthetic.py --backbone resnet101 --method csghmc_fs --num_cycles 2 --epochs 6 \
+        --hparams prior_sig=1.0,Ninflate=1.0,nd=0.01,burnin=0,momentum_decay=0.18,thin=2,bias=informative,nst=2 \
+        --lr 1e-4 --lr_head 1e-2 --batch_size 16 --train_batches 6     # raw samples in the HBM ring + BMA
 """
 import argparse
 import importlib
@@ -23,7 +26,7 @@ import torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from bayesdll_b200 import shapes  # noqa: E402
 
-METHODS = ("sgld", "sghmc", "csgld", "csghmc", "adam_sghmc", "adam_csghmc")
+METHODS = ("sgld", "sghmc", "csgld", "csghmc", "csghmc_fs", "adam_sghmc", "adam_csghmc")
 
 
 def synthetic_loader(n_batches, batch, shape, num_classes, seed):

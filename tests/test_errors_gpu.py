@@ -154,3 +154,33 @@ def test_host_chain_argument_errors(cuda_device):
     assert lib.bdl_chain_upload(h if h else None, 0, None) == INVALID
     ch.close()
     ch.close()                                                                        # idempotent
+
+
+def test_ops_follow_the_tensor_device_not_the_current_one():
+    """Tensors on cuda:1 while cuda:0 is current (args.device='cuda:1' without torch.cuda.set_device): every entry point
+    must launch on the tensors' device.  Needs two GPUs."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 CUDA devices")
+    torch.cuda.set_device(0)
+    n = 4096
+    res = []
+    for dev in (torch.device("cuda:0"), torch.device("cuda:1")):
+        gen = torch.Generator().manual_seed(5)
+        th, g, th0, v = [(torch.randn(n, generator=gen) * 0.1).to(dev) for _ in range(4)]
+        rd, nr = ops.upload_runs(_runs(n), dev)
+        sc = ops.make_scalars(_lib.SGHMC, lr_body=1e-3, lr_head=1e-2, ND=10)
+        m1, m2 = torch.empty(n, device=dev), torch.empty(n, device=dev)
+        ops.step(_lib.SGHMC, th, g, th0, v, None, None, None, rd, nr, sc, ops.make_noise(seed=3, subseq=1),
+                 capture=ops.make_capture("avg", m1, m2, 0, init=True))
+        out = torch.empty(n, device=dev)
+        ops.draw(m1, m2, out, ops.VAR_FROM_MOMENTS, 1.5, ops.make_noise(seed=3, subseq=2, stream_id=_lib.STREAM_DRAW))
+        ring = torch.zeros((2, n), device=dev)
+        ops.capture_ring(out, ring, 1)
+        la = torch.randn(8, 5, 3, generator=gen).to(dev)
+        ens = torch.empty(8, 5, device=dev)
+        ops.ensemble(la, ens, 3)
+        torch.cuda.synchronize(dev)
+        assert torch.cuda.current_device() == 0
+        res.append([t.cpu() for t in (th, v, m1, m2, ring[1], ens)])
+    for a, b in zip(*res):
+        assert torch.equal(a, b)

@@ -185,6 +185,14 @@ def test_csghmc_fs_sample_store_and_bma(cuda_device, tmp_path, extra):
     assert len(runner._fs_resident) == cap
 
 
+def test_runner_accepts_bare_cuda_device(cuda_device, tmp_path):
+    """args.device = torch.device('cuda') (no index), as the reference's drivers build it (demo_vision.py:64): the writer
+    thread, the flat state and the BMA must all cope.  (A bare device once killed the writer thread and hung flush().)"""
+    z, runner, _, _, _ = _run("csghmc_fs", torch.device("cuda"), tmp_path)
+    assert runner._writer.device.index is not None
+    _check_bma(z, runner, tmp_path)
+
+
 def test_async_and_sync_checkpoints_are_identical(cuda_device, tmp_path):
     """io=async (side-stream D2H + writer thread) writes byte-for-byte the tensors io=sync writes."""
     outs = {}

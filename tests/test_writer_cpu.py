@@ -59,3 +59,65 @@ def test_writer_rejects_bad_mode():
     import pytest
     with pytest.raises(ValueError):
         AsyncWriter("cpu", mode="later")
+
+
+def test_async_writer_thread_path_on_cpu(tmp_path):
+    """The threaded path (queue, atomic rename, pending set, flush) without CUDA."""
+    w = AsyncWriter("cpu")
+    paths = [w.submit(os.path.join(tmp_path, f"f{i}.pt"), {"i": i, "t": torch.full((1000,), float(i))}) for i in range(8)]
+    w.flush()
+    assert not w.pending_paths
+    for i, p in enumerate(paths):
+        d = torch.load(p)
+        assert d["i"] == i and torch.equal(d["t"], torch.full((1000,), float(i)))
+    assert w.stats["jobs"] == 8
+    w.close()
+    w.close()
+
+
+def test_async_writer_reports_failures_and_never_hangs(tmp_path):
+    import pytest
+
+    def boom(obj, path):
+        raise OSError("disk on fire")
+    w = AsyncWriter("cpu")
+    w.submit(os.path.join(tmp_path, "a.pt"), {"x": 1}, serializer=boom)
+    with pytest.raises(RuntimeError, match="disk on fire"):
+        w.flush()
+    # the writer keeps working after a failed job
+    p = w.submit(os.path.join(tmp_path, "b.pt"), {"x": 2})
+    w.flush()
+    assert torch.load(p)["x"] == 2
+    # a writer thread that dies outside a job (this is what a bare torch.device('cuda') once did in set_device) must make
+    # flush() raise, not wait forever
+    w2 = AsyncWriter("cpu")
+    w2._one = None                                   # makes the thread's loop raise TypeError on the first job
+    w2.submit(os.path.join(tmp_path, "c.pt"), {"x": 3})
+    with pytest.raises(RuntimeError):
+        w2.flush()
+    with pytest.raises(RuntimeError):
+        w2.submit(os.path.join(tmp_path, "d.pt"), {"x": 4})
+
+
+def test_async_writer_resolves_bare_cuda_device():
+    import pytest
+    if not torch.cuda.is_available():
+        pytest.skip("needs CUDA to resolve the current device")
+    assert AsyncWriter(torch.device("cuda")).device.index is not None
+
+
+def test_process_exits_cleanly_with_an_open_writer(tmp_path):
+    """A script that never calls close() must still exit 0 with its file complete (atexit joins the writer thread)."""
+    import subprocess
+    import sys
+    import textwrap
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    code = textwrap.dedent(f"""
+        import os, torch
+        from bayesdll_b200.writer import AsyncWriter
+        w = AsyncWriter("cpu")
+        w.submit(os.path.join({str(tmp_path)!r}, "late.pt"), {{"x": torch.arange(100000)}})
+    """)
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, cwd=root, timeout=120)
+    assert r.returncode == 0, r.stderr[-500:]
+    assert torch.equal(torch.load(os.path.join(tmp_path, "late.pt"))["x"], torch.arange(100000))
