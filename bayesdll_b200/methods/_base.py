@@ -31,6 +31,27 @@ from ..writer import AsyncWriter, FlatBackedStateDict
 from .cyclical import CyclicalSGMCMC
 
 
+def reinitialize_fresh(net, logger):
+    """Cold restart (methods/adam_csghmc.py:102-129, methods/csghmc_fs.py:91-117): Xavier for Linear, Kaiming (fan-in,
+    ReLU) for Conv2d, unit / zero BatchNorm affine, ``reset_parameters`` otherwise -- written in place through the flat
+    views, so the sampler state stays one buffer."""
+    inits = ((nn.Linear, lambda m: nn.init.xavier_uniform_(m.weight)),
+             (nn.Conv2d, lambda m: nn.init.kaiming_uniform_(m.weight, mode="fan_in", nonlinearity="relu")),
+             ((nn.BatchNorm2d, nn.BatchNorm1d), lambda m: m.weight is not None and nn.init.ones_(m.weight)))
+
+    def fresh(m):
+        for kinds, init_weight in inits:
+            if isinstance(m, kinds):
+                init_weight(m)
+                if m.bias is not None:
+                    nn.init.zeros_(m.bias)
+                return
+        if hasattr(m, "reset_parameters"):
+            m.reset_parameters()
+    net.apply(fresh)
+    logger.info("Network parameters re-initialized with fresh random weights for cold restart.")
+
+
 # ================================================================================================
 # optimizer shim
 # ================================================================================================

@@ -4,10 +4,8 @@ update (fused kernel BDL_ADAM_CSGHMC): as Adam-SGHMC with gU = g/T + prior and t
 SGD momentum 0).  Momentum and Adam state are zeroed at every end of cycle (:370-378, :131-143); optional cold
 restarts re-initialise the network (:102-129, :408-410).  hparams add temperature, perform_cold_restarts.
 """
-import torch.nn as nn
-
 from .. import _lib
-from ._base import AdamStateMixin, CyclicalRunner, FusedModel
+from ._base import AdamStateMixin, CyclicalRunner, FusedModel, reinitialize_fresh
 
 
 class Model(AdamStateMixin, FusedModel):
@@ -43,25 +41,7 @@ class Runner(CyclicalRunner):
                      temperature=self.temperature)
 
     def _reinitialize_network_fresh(self):
-        """Fresh random weights for a cold restart (methods/adam_csghmc.py:102-129); in-place on the flat views."""
-        def fresh(m):
-            if isinstance(m, nn.Linear):
-                nn.init.xavier_uniform_(m.weight)
-                if m.bias is not None:
-                    nn.init.zeros_(m.bias)
-            elif isinstance(m, nn.Conv2d):
-                nn.init.kaiming_uniform_(m.weight, mode="fan_in", nonlinearity="relu")
-                if m.bias is not None:
-                    nn.init.zeros_(m.bias)
-            elif isinstance(m, (nn.BatchNorm2d, nn.BatchNorm1d)):
-                if m.weight is not None:
-                    nn.init.ones_(m.weight)
-                if m.bias is not None:
-                    nn.init.zeros_(m.bias)
-            elif hasattr(m, "reset_parameters"):
-                m.reset_parameters()
-        self.net.apply(fresh)
-        self.logger.info("Network parameters re-initialized with fresh random weights for cold restart.")
+        reinitialize_fresh(self.net, self.logger)
 
     def _reset_optimizer_states(self, log=True):
         """v, m, s <- 0 and t <- 0 (methods/adam_csghmc.py:131-143): three memsets on the flat buffers."""

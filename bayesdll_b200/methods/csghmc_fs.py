@@ -22,14 +22,14 @@ import os
 import pickle
 import time
 
-import numpy as np
 import torch
-import torch.nn as nn
 
 from .. import ops
 from ..chain import SampleRing
 from ..flat import adopt_parameters, alloc_flat
+from ..writer import FlatBackedStateDict
 from . import csghmc as _csghmc
+from ._base import reinitialize_fresh
 
 Model = _csghmc.Model            # methods/csghmc_fs.py:908-985 is identical to methods/csghmc.py:673-781
 
@@ -109,25 +109,7 @@ class Runner(_csghmc.Runner):
             self.logger.info("All optimizer states (momentum, m, v, t) reset for new cycle.")
 
     def _reinitialize_network_fresh(self):
-        """Fresh random weights for a cold restart (csghmc_fs.py:91-117); in-place on the flat views."""
-        def fresh(m):
-            if isinstance(m, nn.Linear):
-                nn.init.xavier_uniform_(m.weight)
-                if m.bias is not None:
-                    nn.init.zeros_(m.bias)
-            elif isinstance(m, nn.Conv2d):
-                nn.init.kaiming_uniform_(m.weight, mode="fan_in", nonlinearity="relu")
-                if m.bias is not None:
-                    nn.init.zeros_(m.bias)
-            elif isinstance(m, (nn.BatchNorm2d, nn.BatchNorm1d)):
-                if m.weight is not None:
-                    nn.init.ones_(m.weight)
-                if m.bias is not None:
-                    nn.init.zeros_(m.bias)
-            elif hasattr(m, "reset_parameters"):
-                m.reset_parameters()
-        self.net.apply(fresh)
-        self.logger.info("Network parameters re-initialized with fresh random weights for cold restart.")
+        reinitialize_fresh(self.net, self.logger)
 
     # ---- raw-sample store -----------------------------------------------------------------------------------
     def store_full_sample(self, ep):
@@ -152,7 +134,6 @@ class Runner(_csghmc.Runner):
         sample = _ResidentSample(self.net, ch.layout, self._fs_ring.buf[slot])
         self._fs_resident[name] = sample
         # on-disk contract: a state_dict (parameters from the slot, buffers from the sample's own copies)
-        from ..writer import FlatBackedStateDict
         sd = FlatBackedStateDict.snapshot(sample.net, ch.layout, ch.names, sample.row)
         self._writer.submit(path, sd)
         return path

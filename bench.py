@@ -525,7 +525,8 @@ def cpu_port_rate(lay, seconds=15.0, with_eager=False, n_limit=None, steps=None,
     from bayesdll_b200 import _lib
     from oracle import c_oracle
     c_oracle.build()
-    cores = os.cpu_count()
+    # all host cores, explicitly: torchrun exports OMP_NUM_THREADS=1 to its workers; report what is really used
+    cores = c_oracle.set_threads(len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else os.cpu_count())
     n_full = lay.n_padded
     rng = np.random.default_rng(0)
 

@@ -28,6 +28,22 @@
 
 #include "bdl.h"
 
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+
+/* Thread control for the timed CPU baseline: torchrun exports OMP_NUM_THREADS=1 to its workers, which would silently
+ * turn the "all host cores" baseline into a single-threaded one. */
+int bdl_oracle_set_threads(int n) {
+#ifdef _OPENMP
+    if (n > 0) omp_set_num_threads(n);
+    return omp_get_max_threads();
+#else
+    (void)n;
+    return 1;
+#endif
+}
+
 /* ------------------------------------------------------------------------------------------ */
 static inline void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1,
                                  uint32_t out[4]) {

@@ -29,6 +29,13 @@ def lib():
     return _lib
 
 
+def set_threads(n=0):
+    """Use ``n`` OpenMP threads (0: leave unchanged); returns the thread count the next call will use."""
+    fn = lib().bdl_oracle_set_threads
+    fn.restype = C.c_int
+    return int(fn(C.c_int(int(n))))
+
+
 def _fp(a):
     return None if a is None else a.ctypes.data_as(C.c_void_p)
 
