@@ -1,7 +1,8 @@
 """Torch-eager, per-tensor restatement of the reference's SGHMC update loop + SGD step, as the reference itself
 executes it (methods/sghmc.py:482-510 then torch.optim.SGD.step, :229): ~12 elementwise ops per tensor, one
-``torch.randn_like`` per tensor.  TEST / BASELINE INFRASTRUCTURE ONLY: bench.py times it on the host cores as the
-"what the reference's own structure achieves on this CPU" figure next to the fused C port (oracle/bdl_oracle.c).
+``torch.randn_like`` per tensor.  BASELINE ONLY: bench.py times it on the host cores ("what the reference's own
+structure achieves on this CPU", next to the fused C port oracle/bdl_oracle.c) and on the same B200 ("the number the
+fused kernel replaces").  Nothing under bayesdll_b200/ imports it.
 """
 import numpy as np
 import torch

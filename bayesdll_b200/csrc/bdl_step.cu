@@ -35,6 +35,7 @@ struct StepParams {
     const float* xi;
     const bdl_run* runs;
     uint32_t nruns;
+    uint32_t flat_g;           // 1: no run carries its own gradient pointer (known from the host table): g loads do not wait for the lookup
     uint32_t inl_n;            // > 0: the run table is small and has no gradient pointers -> inlined below (constant bank)
     uint32_t inl_end4[kInlineRuns];
     uint32_t inl_cls[kInlineRuns];
@@ -235,6 +236,7 @@ step_kernel(const StepParams p) {
                 }
                 if constexpr (kHasBuf) b[u] = ld_stream(p.buf + i);
                 if constexpr (!kPhilox) xi[u] = ld_stream(p.xi + i);
+                if (p.flat_g) g[u] = ld_stream(p.g + i);     // no per-run gradient pointers: the load need not wait for the class lookup
             }
         }
         // ---- 2. element class / gradient pointer, then the gradient loads ----
@@ -245,11 +247,14 @@ step_kernel(const StepParams p) {
                 const uint32_t q = q0 + u * kT;
                 if (act[u]) {
                     uint32_t c = p.inl_cls[0];
+                    if (p.inl_n == 2) {                    // body | head, the layout of every BASELINE config: one compare
+                        if (q >= p.inl_end4[0]) c = p.inl_cls[1];
+                    } else {
 #pragma unroll
-                    for (int r = 1; r < kInlineRuns; ++r)
-                        if (r < static_cast<int>(p.inl_n) && q >= p.inl_end4[r - 1]) c = p.inl_cls[r];
+                        for (int r = 1; r < kInlineRuns; ++r)
+                            if (r < static_cast<int>(p.inl_n) && q >= p.inl_end4[r - 1]) c = p.inl_cls[r];
+                    }
                     cls[u] = c;
-                    g[u] = ld_stream(p.g + (static_cast<uint64_t>(q) << 2));
                     act[u] = (c & BDL_CLS_SKIP) == 0;
                 }
             }
@@ -267,7 +272,7 @@ step_kernel(const StepParams p) {
                 cursor_seek(cur, p, q);
                 cls[u] = cur.cls;
                 const uint64_t i = static_cast<uint64_t>(q) << 2;
-                g[u] = ld_stream(cur.gbase + i);
+                if (!p.flat_g) g[u] = ld_stream(cur.gbase + i);
                 if (cur.own_g && i + 4 > cur.valid_end) {  // tail group of a per-run gradient: zero the padding lanes
                     if (i + 0 >= cur.valid_end) g[u].x = 0.f;
                     if (i + 1 >= cur.valid_end) g[u].y = 0.f;
@@ -444,10 +449,12 @@ int step_range(int variant, float* theta, const float* g, const float* theta0, f
     p.theta = theta; p.g = g; p.theta0 = theta0; p.v = v; p.m = m; p.s = s; p.buf = buf;
     p.xi = nz->xi_dev; p.runs = runs; p.nruns = nruns;
     p.inl_n = 0;
-    if (runs_host && nruns <= static_cast<uint32_t>(kInlineRuns) && g) {
+    p.flat_g = 0;
+    if (runs_host && g) {
         bool plain = true;
         for (uint32_t r = 0; r < nruns; ++r) plain = plain && runs_host[r].g_dev == nullptr;
-        if (plain) {
+        p.flat_g = plain ? 1u : 0u;
+        if (plain && nruns <= static_cast<uint32_t>(kInlineRuns)) {
             p.inl_n = nruns;
             for (uint32_t r = 0; r < nruns; ++r) {
                 p.inl_end4[r] = static_cast<uint32_t>(runs_host[r].end >> 2);

@@ -577,7 +577,7 @@ def cpu_port_rate(lay, seconds=15.0, with_eager=False, n_limit=None, steps=None,
 
 def eager_rate(lay, cores, max_params=64 << 20):
     """What the reference's own structure (per-tensor torch eager loop + SGD.step) achieves on these cores."""
-    from oracle import eager_port
+    from baseline import eager_port
     torch.set_num_threads(cores)
     segs, tot = [], 0
     for s in lay.segments:
@@ -600,14 +600,14 @@ def eager_rate(lay, cores, max_params=64 << 20):
     dt = time.perf_counter() - t0
     return {"value": tot * reps / dt, "unit": "params/s", "cores": cores, "kind": "port",
             "sample": f"{reps} per-tensor torch-eager SGHMC steps over the first {len(segs)} ViT-L/32 tensors ({tot} params), "
-                      f"oracle/eager_port.py restating methods/sghmc.py:482-510 + SGD.step"}
+                      f"baseline/eager_port.py restating methods/sghmc.py:482-510 + SGD.step"}
 
 
 def eager_gpu_rate(lay, device, reps=3):
-    """The reference's own structure on the SAME B200: per-tensor eager loop + SGD.step (oracle/eager_port.py restating
+    """The reference's own structure on the SAME B200: per-tensor eager loop + SGD.step (baseline/eager_port.py restating
     methods/sghmc.py:482-510, :229) over all 296 ViT-L/32 tensors.  This is the number the fused kernel replaces
     ('reference on the same B200')."""
-    from oracle import eager_port
+    from baseline import eager_port
     names = [s.name for s in lay.segments]
     gen = torch.Generator(device=device).manual_seed(1)
     mk = lambda sc: [torch.randn(s.shape, device=device, generator=gen) * sc for s in lay.segments]
@@ -627,7 +627,7 @@ def eager_gpu_rate(lay, device, reps=3):
     ms = e0.elapsed_time(e1) / reps
     return {"value": lay.n_dense / (ms * 1e-3), "unit": "params/s", "ms_per_step": ms, "steps": reps,
             "kernel_launches_per_step": "~12 eager kernels x 296 tensors",
-            "sample": "per-tensor torch-eager SGHMC loop + SGD step on cuda:0, all 296 ViT-L/32 tensors (oracle/eager_port.py)"}
+            "sample": "per-tensor torch-eager SGHMC loop + SGD step on cuda:0, all 296 ViT-L/32 tensors (baseline/eager_port.py)"}
 
 
 def run_reference(args):

@@ -121,6 +121,17 @@ def main():
         med, mn = timeit(fn_ptr, a.iters)
         report(tag, 24, med, mn)
         del grads
+    tag = "SGHMC philox + fused moment capture (bdl_step_capture)"
+    if want(tag):
+        rd, nr = runs["informative"]
+        sc = ops.make_scalars(_lib.SGHMC, lr_body=1e-4, lr_head=1e-2, ND=3680, Ninflate=1e3, prior_sig=1.0, nd=1.0, alpha=0.18)
+
+        def fn_cap():
+            step_no[0] += 1
+            ops.step(_lib.SGHMC, buf["theta"], buf["g"], buf["theta0"], buf["v"], None, None, None, rd, nr, sc,
+                     ops.make_noise(seed=42, subseq=step_no[0]), capture=ops.make_capture("avg", buf["m"], buf["s"], 7))
+        med, mn = timeit(fn_cap, a.iters)
+        report(tag, 40, med, mn)
     if a.full:
         for threads in (64, 128, 256):
             for unroll in (1,):
