@@ -11,7 +11,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libbdl.so")
 
 # ---- enums / constants (include/bdl.h) -------------------------------------------------------
-BDL_ABI_VERSION = 3
+BDL_ABI_VERSION = 4
 SGLD, SGHMC, CSGHMC, ADAM_SGHMC, ADAM_CSGHMC = range(5)
 VARIANT_NAMES = {SGLD: "sgld", SGHMC: "sghmc", CSGHMC: "csghmc", ADAM_SGHMC: "adam_sghmc",
                  ADAM_CSGHMC: "adam_csghmc"}
@@ -34,7 +34,9 @@ class Scalars(C.Structure):
                 ("one_minus_beta2", C.c_float), ("bias_corr1", C.c_float), ("bias_corr2", C.c_float),
                 ("eps", C.c_float), ("two_alpha", C.c_float), ("nd", C.c_float), ("temperature", C.c_float),
                 ("first_step", C.c_int32), ("add_noise", C.c_int32), ("div_mode", C.c_int32),
-                ("reserved", C.c_int32)]
+                ("reserved", C.c_int32),
+                ("inv_sig2", C.c_float), ("inv_N", C.c_float), ("inv_bias_corr1", C.c_float),
+                ("inv_bias_corr2", C.c_float), ("inv_temperature", C.c_float), ("reserved2", C.c_int32)]
 
 
 class Noise(C.Structure):
@@ -50,7 +52,7 @@ class Capture(C.Structure):
 CAPTURE_NONE, CAPTURE_AVG, CAPTURE_WELFORD = 0, 1, 2
 
 assert C.sizeof(Capture) == 32
-assert C.sizeof(Run) == 40 and C.sizeof(Noise) == 32 and C.sizeof(Scalars) == 88
+assert C.sizeof(Run) == 40 and C.sizeof(Noise) == 32 and C.sizeof(Scalars) == 112
 
 _P = C.c_void_p
 _U64, _U32, _I32, _F, _D = C.c_uint64, C.c_uint32, C.c_int, C.c_float, C.c_double

@@ -212,7 +212,7 @@ extern "C" int bdl_moments_avg(const float* theta, float* mom1, float* mom2, uin
     const uint32_t n4 = static_cast<uint32_t>(n >> 2);
     const uint32_t grid = ew_grid(n4, 4);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    const float inv = 1.0f / cntp1;
+    const float inv = scalar_reciprocal(cntp1, div_mode);
 #define BDL_LAUNCH_MA(D, I, H) moments_avg_kernel<D, I, H><<<grid, kCapThreads, 0, st>>>(theta, mom1, mom2, n4, cnt, cntp1, inv)
     const bool h = mom2 != nullptr;
     if (init) {
@@ -237,7 +237,7 @@ extern "C" int bdl_moments_welford(const float* theta, float* mean, float* M2, u
     const uint32_t n4 = static_cast<uint32_t>(n >> 2);
     const uint32_t grid = ew_grid(n4, 4);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    const float inv = 1.0f / nf;
+    const float inv = scalar_reciprocal(nf, div_mode);
     if (init) moments_welford_kernel<BDL_DIV_IEEE, true><<<grid, kCapThreads, 0, st>>>(theta, mean, M2, n4, nf, inv);
     else if (div_mode == BDL_DIV_IEEE) moments_welford_kernel<BDL_DIV_IEEE, false><<<grid, kCapThreads, 0, st>>>(theta, mean, M2, n4, nf, inv);
     else moments_welford_kernel<BDL_DIV_RECIP, false><<<grid, kCapThreads, 0, st>>>(theta, mean, M2, n4, nf, inv);

@@ -468,21 +468,25 @@ int step_range(int variant, float* theta, const float* g, const float* theta0, f
         p.neg_lr[h] = -sc->lr[h];
         p.c[h] = sc->noise_scale[h];
     }
+    // Reciprocals.  IEEE mode needs RN(1 / fp32(s)) for the FMA-corrected division; reciprocal mode multiplies by the
+    // factor torch CUDA uses, fp32(1.0 / s_double), supplied by the host (0 -> not supplied -> fp32 reciprocal).
+    const bool recip = sc->div_mode == BDL_DIV_RECIP;
+    auto inv_of = [recip](float s_f, float host_inv) { return (recip && host_inv != 0.0f) ? host_inv : 1.0f / s_f; };
     p.oma = sc->one_minus_alpha;
-    p.sig2 = sc->sig2; p.inv_sig2 = 1.0f / sc->sig2;
-    p.N = sc->N; p.inv_N = 1.0f / sc->N;
+    p.sig2 = sc->sig2; p.inv_sig2 = inv_of(sc->sig2, sc->inv_sig2);
+    p.N = sc->N; p.inv_N = inv_of(sc->N, sc->inv_N);
     p.mu = sc->mu;
     p.b1 = sc->beta1; p.omb1 = sc->one_minus_beta1; p.b2 = sc->beta2; p.omb2 = sc->one_minus_beta2;
-    p.bc1 = sc->bias_corr1; p.inv_bc1 = 1.0f / sc->bias_corr1;
-    p.bc2 = sc->bias_corr2; p.inv_bc2 = 1.0f / sc->bias_corr2;
+    p.bc1 = sc->bias_corr1; p.inv_bc1 = inv_of(sc->bias_corr1, sc->inv_bias_corr1);
+    p.bc2 = sc->bias_corr2; p.inv_bc2 = inv_of(sc->bias_corr2, sc->inv_bias_corr2);
     p.eps = sc->eps; p.two_alpha = sc->two_alpha; p.nd = sc->nd;
-    p.T = sc->temperature; p.inv_T = 1.0f / sc->temperature;
+    p.T = sc->temperature; p.inv_T = inv_of(sc->temperature, sc->inv_temperature);
     p.first_step = sc->first_step; p.add_noise = sc->add_noise;
     if (capture) {
         p.cap1 = cap->first_dev; p.cap2 = cap->second_dev; p.cap_kind = cap->kind; p.cap_init = cap->init != 0;
         p.cap_a = cap->cnt;
         p.cap_b = cap->cnt_plus_1;
-        p.cap_inv = 1.0f / (cap->kind == BDL_CAPTURE_AVG ? cap->cnt_plus_1 : cap->cnt);
+        p.cap_inv = scalar_reciprocal(cap->kind == BDL_CAPTURE_AVG ? cap->cnt_plus_1 : cap->cnt, sc->div_mode);
     }
     p.key = host_noise_key(nz->seed, nz->stream_id, nz->subseq);
 

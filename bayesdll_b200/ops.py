@@ -93,6 +93,14 @@ def make_scalars(variant, *, lr_body, lr_head, ND, Ninflate=1.0, prior_sig=1.0, 
     sc.beta2, sc.one_minus_beta2 = beta2, 1 - beta2
     sc.bias_corr1 = 1 - beta1 ** t
     sc.bias_corr2 = 1 - beta2 ** t
+    # torch CUDA evaluates `tensor / python_scalar` as tensor * fp32(1.0 / s), the reciprocal taken in double
+    # (BinaryDivTrueKernel.cu; probed, tools/probe_torch_div.py): hand the kernel exactly those factors
+    if variant != CSGHMC:
+        sc.inv_sig2 = 1.0 / (prior_sig ** 2)
+    sc.inv_N = 1.0 / N
+    sc.inv_bias_corr1 = 1.0 / (1 - beta1 ** t)
+    sc.inv_bias_corr2 = 1.0 / (1 - beta2 ** t)
+    sc.inv_temperature = 1.0 / temperature
     sc.eps = eps
     sc.two_alpha = 2 * alpha
     sc.nd = nd

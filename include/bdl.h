@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define BDL_ABI_VERSION 3
+#define BDL_ABI_VERSION 4
 
 typedef enum {
     BDL_OK = 0,
@@ -70,7 +70,9 @@ typedef struct {
 #define BDL_MAX_RUNS 2048
 
 /* Division semantics for `tensor / python_scalar` (last row of the table):
- * the reference on CPU divides (IEEE); the reference on CUDA multiplies by the fp32 reciprocal. */
+ * the reference on CPU divides (IEEE); the reference on CUDA multiplies by fp32(1.0 / s) where the reciprocal is taken
+ * in DOUBLE precision from the Python double and rounded once (probed on this torch build: tools/probe_torch_div.py,
+ * profiles/r01_torch_div_probe.log; e.g. s = 1 - 0.99**2 gives a different fp32 factor than 1.0f / fp32(s)). */
 #define BDL_DIV_IEEE 0
 #define BDL_DIV_RECIP 1
 
@@ -93,6 +95,11 @@ typedef struct {
     int32_t add_noise;       /* cSGHMC: should_sample (csghmc.py:769); other variants ignore it        */
     int32_t div_mode;        /* BDL_DIV_IEEE | BDL_DIV_RECIP                                           */
     int32_t reserved;
+    /* BDL_DIV_RECIP factors: fp32(1.0 / s_double), computed by the host in double from the ORIGINAL Python doubles
+     * (prior_sig**2, ND*Ninflate, 1-beta1**t, 1-beta2**t, temperature).  A field left at 0 makes the library use
+     * 1.0f / fp32(s) instead (differs from torch CUDA by one ulp of the factor for a minority of divisors). */
+    float inv_sig2, inv_N, inv_bias_corr1, inv_bias_corr2, inv_temperature;
+    int32_t reserved2;
 } bdl_scalars;
 
 /* Gaussian noise source.  xi_dev != NULL: externally injected N(0,1) draws in the padded flat

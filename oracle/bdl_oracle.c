@@ -90,6 +90,8 @@ int bdl_oracle_philox_normal(float* out, uint64_t n, uint64_t seed, uint32_t str
 
 /* ------------------------------------------------------------------------------------------ */
 static inline float div_s(float x, float s, float inv_s, int mode) { return mode == BDL_DIV_IEEE ? x / s : x * inv_s; }
+/* integer-valued divisors (sample counts): reciprocal mode = fp32(1.0 / s) taken in double, as torch CUDA does */
+static inline float scalar_reciprocal(float s, int mode) { return mode == BDL_DIV_RECIP ? (float)(1.0 / (double)s) : 1.0f / s; }
 
 typedef struct {
     float lr[2], c[2];
@@ -165,10 +167,13 @@ int bdl_oracle_step(int variant, float* theta, const float* g, const float* thet
     if (variant < BDL_SGLD || variant > BDL_ADAM_CSGHMC || !theta || !runs || !sc || !nz || n % 4) return BDL_ERR_INVALID;
     sc_t p;
     for (int h = 0; h < 2; ++h) { p.lr[h] = sc->lr[h]; p.c[h] = sc->noise_scale[h]; }
-    p.oma = sc->one_minus_alpha; p.sig2 = sc->sig2; p.inv_sig2 = 1.0f / sc->sig2; p.N = sc->N; p.inv_N = 1.0f / sc->N;
+    /* reciprocal mode multiplies by the host-supplied fp32(1.0 / s_double) (what torch CUDA uses); 0 = not supplied */
+#define INV_OF(s_f, host_inv) ((sc->div_mode == BDL_DIV_RECIP && (host_inv) != 0.0f) ? (host_inv) : 1.0f / (s_f))
+    p.oma = sc->one_minus_alpha; p.sig2 = sc->sig2; p.inv_sig2 = INV_OF(sc->sig2, sc->inv_sig2); p.N = sc->N; p.inv_N = INV_OF(sc->N, sc->inv_N);
     p.mu = sc->mu; p.b1 = sc->beta1; p.omb1 = sc->one_minus_beta1; p.b2 = sc->beta2; p.omb2 = sc->one_minus_beta2;
-    p.bc1 = sc->bias_corr1; p.inv_bc1 = 1.0f / sc->bias_corr1; p.bc2 = sc->bias_corr2; p.inv_bc2 = 1.0f / sc->bias_corr2;
-    p.eps = sc->eps; p.two_alpha = sc->two_alpha; p.nd = sc->nd; p.T = sc->temperature; p.inv_T = 1.0f / sc->temperature;
+    p.bc1 = sc->bias_corr1; p.inv_bc1 = INV_OF(sc->bias_corr1, sc->inv_bias_corr1); p.bc2 = sc->bias_corr2; p.inv_bc2 = INV_OF(sc->bias_corr2, sc->inv_bias_corr2);
+    p.eps = sc->eps; p.two_alpha = sc->two_alpha; p.nd = sc->nd; p.T = sc->temperature; p.inv_T = INV_OF(sc->temperature, sc->inv_temperature);
+#undef INV_OF
     p.first_step = sc->first_step; p.add_noise = sc->add_noise; p.div = sc->div_mode;
     const int has_buf = (variant == BDL_SGLD || variant == BDL_ADAM_SGHMC) && sc->mu != 0.0f;
     const float* xi = (const float*)(uintptr_t)nz->xi_dev;
@@ -202,7 +207,7 @@ int bdl_oracle_draw(const float* mean, const float* second, const float* center,
                     float scale, int div_mode, const bdl_noise* nz) {
     if (n % 4) return BDL_ERR_INVALID;
     const float* xi = (const float*)(uintptr_t)nz->xi_dev;
-    const float inv = 1.0f / scale;
+    const float inv = scalar_reciprocal(scale, div_mode);
 #pragma omp parallel for schedule(static)
     for (int64_t q = 0; q < (int64_t)(n / 4); ++q) {
         float z[4];
@@ -223,7 +228,7 @@ int bdl_oracle_draw(const float* mean, const float* second, const float* center,
 
 int bdl_oracle_moments_avg(const float* theta, float* mom1, float* mom2, uint64_t n, float cnt, float cntp1, int init,
                            int div_mode) {
-    const float inv = 1.0f / cntp1;
+    const float inv = scalar_reciprocal(cntp1, div_mode);
 #pragma omp parallel for schedule(static)
     for (int64_t i = 0; i < (int64_t)n; ++i) {
         const float t = theta[i];
@@ -239,7 +244,7 @@ int bdl_oracle_moments_avg(const float* theta, float* mom1, float* mom2, uint64_
 }
 
 int bdl_oracle_moments_welford(const float* theta, float* mean, float* M2, uint64_t n, float nf, int init, int div_mode) {
-    const float inv = 1.0f / nf;
+    const float inv = scalar_reciprocal(nf, div_mode);
 #pragma omp parallel for schedule(static)
     for (int64_t i = 0; i < (int64_t)n; ++i) {
         const float t = theta[i];

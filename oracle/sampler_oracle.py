@@ -44,11 +44,12 @@ def _fma(a, b, c):
 
 def _div_scalar(x, s, div_mode):
     """tensor / python_scalar.  'true': IEEE divide by fp32(s) (torch CPU);
-    'recip': multiply by the fp32 reciprocal of fp32(s) (torch CUDA)."""
+    'recip': multiply by fp32(1.0 / s) with the reciprocal taken in DOUBLE from the Python double (torch CUDA,
+    BinaryDivTrueKernel.cu; pinned by tools/probe_torch_div.py and tests/test_cuda_eager_parity_gpu.py)."""
     if div_mode == "true":
         return x / f32(s)
     if div_mode == "recip":
-        return x * (f32(1.0) / f32(s))
+        return x * f32(1.0 / float(s))
     raise ValueError(div_mode)
 
 

@@ -34,12 +34,31 @@ def test_library_exports_every_declared_symbol():
     assert set(_lib.SIGNATURES) | {"bdl_abi_version", "bdl_last_error"} == set(_declared_functions())
 
 
-def test_struct_layouts_match_header():
+def test_struct_layouts_match_header(tmp_path):
+    """sizeof / offsetof of every struct of include/bdl.h, as the C compiler sees them, against the ctypes mirrors."""
+    import subprocess
     from bayesdll_b200 import _lib
-    assert ctypes.sizeof(_lib.Run) == 40
-    assert _lib.Run.g_dev.offset == 24 and _lib.Run.cls.offset == 32
-    assert ctypes.sizeof(_lib.Scalars) == 88 and _lib.Scalars.first_step.offset == 72
-    assert ctypes.sizeof(_lib.Noise) == 32 and _lib.Noise.stream_id.offset == 24
+    mirrors = {"bdl_run": _lib.Run, "bdl_scalars": _lib.Scalars, "bdl_noise": _lib.Noise, "bdl_capture": _lib.Capture}
+    lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "bdl.h"', 'int main(void) {']
+    for cname, cls in mirrors.items():
+        lines.append(f'  printf("{cname} size %zu\\n", sizeof({cname}));')
+        for fname, _ in cls._fields_:
+            lines.append(f'  printf("{cname} {fname} %zu\\n", offsetof({cname}, {fname}));')
+    lines += ['  return 0;', '}']
+    src = tmp_path / "layout.c"
+    src.write_text("\n".join(lines))
+    exe = tmp_path / "layout"
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    subprocess.check_call(["gcc", "-I", os.path.join(root, "include"), str(src), "-o", str(exe)])
+    got = {}
+    for ln in subprocess.check_output([str(exe)], text=True).splitlines():
+        cname, field, val = ln.split()
+        got[(cname, field)] = int(val)
+    for cname, cls in mirrors.items():
+        assert got[(cname, "size")] == ctypes.sizeof(cls), cname
+        for fname, _ in cls._fields_:
+            assert got[(cname, fname)] == getattr(cls, fname).offset, (cname, fname)
+    assert ctypes.sizeof(_lib.Scalars) == 112 and ctypes.sizeof(_lib.Run) == 40
 
 
 def test_missing_library_fails_loudly(monkeypatch, tmp_path):
