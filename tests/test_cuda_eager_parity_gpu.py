@@ -119,3 +119,72 @@ def test_fused_kernel_equals_torch_cuda_eager(cuda_device, variant_name, bias):
                 assert rel <= 1e-6, f"{variant_name}/{bias} step {t} {key}[{n_}]: rel {rel:.2e}"
     print(f"{variant_name}/{bias}: max ulp distance to torch CUDA eager {worst}")
     assert all(u == 0 for u in worst.values()), worst       # every state vector of every update rule: bit-identical
+
+
+@pytest.mark.parametrize("n", [4, 100_004, 1_000_000])
+def test_capture_and_draw_equal_torch_cuda_eager(cuda_device, n):
+    """Running moments (methods/sgld.py:95-102,239-246), Welford with the reference's n = 3, 5, 7 ... (methods/csghmc.py:
+    327-348), variance + posterior draw (methods/sgld.py:292-297,338-348; methods/csghmc.py:451-459) written in torch CUDA
+    eager ops vs the kernels in the default division mode: bit-identical."""
+    from bayesdll_b200 import _lib, ops
+    dev = cuda_device
+    gen = torch.Generator().manual_seed(n)
+    thetas = [(torch.randn(n, generator=gen) * 0.3).to(dev) for _ in range(6)]
+    # --- running average ---
+    mom1, mom2, cnt = thetas[0] * 1.0, thetas[0] ** 2, 1
+    k1, k2 = torch.empty(n, device=dev), torch.empty(n, device=dev)
+    ops.moments_avg(thetas[0], k1, k2, 0, init=True)
+    for th in thetas[1:]:
+        mom1 = (th + cnt * mom1) / (cnt + 1)
+        mom2 = (th ** 2 + cnt * mom2) / (cnt + 1)
+        ops.moments_avg(th, k1, k2, cnt)                                   # default: DIV_RECIP
+        cnt += 1
+    assert torch.equal(k1, mom1) and torch.equal(k2, mom2)
+    # --- Welford, double-counted sample count ---
+    mean, M2, count = thetas[0].clone(), torch.zeros(n, device=dev), 1
+    w1, w2 = torch.empty(n, device=dev), torch.empty(n, device=dev)
+    ops.moments_welford(thetas[0], w1, w2, 1, init=True)
+    count += 1
+    for th in thetas[1:]:
+        nn_ = count + 1
+        delta = th - mean
+        mean = mean + delta / nn_
+        delta2 = th - mean
+        M2 = M2 + delta * delta2
+        ops.moments_welford(th, w1, w2, nn_)
+        count = nn_ + 1
+    assert torch.equal(w1, mean) and torch.equal(w2, M2)
+    # --- variance + draw ---
+    eps = torch.randn(n, generator=gen).to(dev)
+    ratio = cnt / (cnt - 1)
+    var = ratio * (mom2 - mom1 ** 2)
+    var.clamp_(min=1e-12)
+    want = mom1 + var.sqrt() * eps
+    out = torch.empty(n, device=dev)
+    ops.draw(k1, k2, out, ops.VAR_FROM_MOMENTS, ratio, ops.make_noise(xi=eps))
+    assert torch.equal(out, want)
+    var_w = (M2 / (count - 1)).clamp(min=1e-12)
+    want_w = mean + var_w.sqrt() * eps
+    ops.draw(w1, w2, out, ops.VAR_FROM_WELFORD, float(count - 1), ops.make_noise(xi=eps))
+    assert torch.equal(out, want_w)
+
+
+@pytest.mark.parametrize("B,K,S", [(16, 37, 5), (64, 37, 40), (7, 10, 1)])
+def test_ensemble_and_ce_close_to_torch_cuda_eager(cuda_device, B, K, S):
+    """logsumexp_S(log_softmax_K) - log S, CE and error count (methods/sgld.py:299-306) vs torch CUDA eager: these go
+    through exp / log whose last bits differ between implementations -> abs/rel 1e-5 (SURVEY 8c iii); errors exact."""
+    from bayesdll_b200 import ops
+    dev = cuda_device
+    gen = torch.Generator().manual_seed(B * S)
+    la = (torch.randn(B, K, S, generator=gen) * 3).to(dev)
+    y = torch.randint(0, K, (B,), generator=gen).to(dev)
+    want = la.log_softmax(dim=1).logsumexp(-1) - np.log(S)
+    out = torch.empty(B, K, device=dev)
+    ops.ensemble(la, out, S)
+    torch.testing.assert_close(out, want.float(), atol=1e-5, rtol=1e-5)
+    loss = torch.zeros(1, dtype=torch.float64, device=dev)
+    err = torch.zeros(1, dtype=torch.int32, device=dev)
+    ops.ce_err(out, y, loss, err)
+    ref_loss = torch.nn.functional.cross_entropy(want.float(), y).item()
+    assert abs(loss.item() / B - ref_loss) <= 1e-5 * max(1.0, abs(ref_loss))
+    assert err.item() == want.argmax(1).ne(y).sum().item()
