@@ -188,3 +188,42 @@ def test_ensemble_and_ce_close_to_torch_cuda_eager(cuda_device, B, K, S):
     ref_loss = torch.nn.functional.cross_entropy(want.float(), y).item()
     assert abs(loss.item() / B - ref_loss) <= 1e-5 * max(1.0, abs(ref_loss))
     assert err.item() == want.argmax(1).ne(y).sum().item()
+
+
+def test_noise_torch_mode_reproduces_reference_rng_stream(cuda_device):
+    """hparams noise=torch: the chain draws ``torch.randn_like`` per tensor in named_parameters() order, exactly the calls
+    the reference makes (methods/sghmc.py:501).  After the same ``torch.manual_seed`` both consume the same CUDA
+    generator stream, so a seeded reference run on a GPU is reproduced bit for bit -- noise included."""
+    from bayesdll_b200 import _lib, ops
+    from bayesdll_b200.chain import ChainState
+    dev = cuda_device
+    gen = torch.Generator().manual_seed(3)
+    ref, ref0 = _Net(gen).to(dev), _Net(gen).to(dev)
+    net, net0 = _Net(gen).to(dev), _Net(gen).to(dev)
+    net.load_state_dict(ref.state_dict())
+    net0.load_state_dict(ref0.state_dict())
+    chain = ChainState(net, net0, variant=_lib.SGHMC, bias_mode="informative", noise="torch", seed=0)
+    named = list(ref.named_parameters())
+    p0s = [p for _, p in ref0.named_parameters()]
+    opt = er.make_sgd([p for n, p in named if READOUT not in n], [p for n, p in named if READOUT in n], HP["lr_body"],
+                      HP["lr_head"], 0.0)
+    vs = {n: torch.zeros_like(p) for n, p in named}
+    N = HP["ND"] * HP["Ninflate"]
+    for t in range(3):
+        grads = [(torch.randn(p.shape, generator=gen) * 0.05).to(dev) for _, p in named]
+        for (_, p), g in zip(named, grads):
+            p.grad = g.clone()
+        torch.manual_seed(100 + t)
+        xis = [torch.randn_like(p) for _, p in named]                      # what the reference's loop would draw
+        er.sghmc(named, p0s, xis, vs, READOUT, lr_body=HP["lr_body"], lr_head=HP["lr_head"], N=N, prior_sig=HP["prior_sig"],
+                 nd=HP["nd"], alpha=HP["alpha"], bias="informative")
+        opt.step()
+        for p, g in zip(chain.params, grads):
+            p.grad = g.clone()
+        torch.manual_seed(100 + t)
+        chain.update(ops.make_scalars(_lib.SGHMC, lr_body=HP["lr_body"], lr_head=HP["lr_head"], ND=HP["ND"],
+                                      Ninflate=HP["Ninflate"], prior_sig=HP["prior_sig"], nd=HP["nd"], alpha=HP["alpha"]))
+    torch.cuda.synchronize()
+    for (n_, p), view, vview in zip(named, chain.layout.views(chain.theta), chain.layout.views(chain.v)):
+        assert torch.equal(view, p.data), n_
+        assert torch.equal(vview, vs[n_]), n_
