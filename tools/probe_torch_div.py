@@ -1,3 +1,10 @@
+"""How does torch CUDA evaluate ``tensor / python_scalar``?  (run under gpurun; output: profiles/r01_torch_div_probe.log)
+
+Compares ``x_cuda / s`` bit for bit with four candidates over 2 M random fp32 values per divisor:
+x * fp32(1/fp32(s)) (fp32 reciprocal), x * fp32(1.0/s) (reciprocal in double, rounded once), x / fp32(s) and x / s (IEEE).
+Result on torch 2.11.0+cu128 / B200: always and only the second one matches -- the semantics of the library's default
+``BDL_DIV_RECIP`` mode (include/bdl.h: bdl_scalars.inv_*).
+"""
 import numpy as np, torch
 torch.manual_seed(0)
 dev = torch.device("cuda:0")
