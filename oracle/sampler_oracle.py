@@ -19,7 +19,10 @@ from "one rounding per op":
     ``p.add_(grad, alpha=-lr)``) is a fused multiply-add on CPU (vec::fmadd) and on
     CUDA (compiler contraction inside the functor); restated by ``_fma``.
   * ``div_mode='recip'`` restates torch-CUDA semantics where ``tensor / python_scalar``
-    is evaluated as ``tensor * (1.0f / (float)scalar)`` (BinaryDivTrueKernel.cu).
+    is evaluated as ``tensor * (float)(1.0 / scalar)``, the reciprocal taken in double
+    (BinaryDivTrueKernel.cu).  Pinned on the GPU box against torch CUDA itself:
+    tools/probe_torch_div.py and tests/test_cuda_eager_parity_gpu.py (the kernels in this
+    mode are bit-identical to the reference's statements run in torch CUDA eager ops).
     ``div_mode='true'`` is IEEE division, what the reference does on CPU and what
     the golden vectors pin.
 
