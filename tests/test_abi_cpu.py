@@ -74,3 +74,16 @@ def test_cpu_tensors_are_rejected():
     from bayesdll_b200 import _lib, ops
     with pytest.raises(_lib.BdlError, match="CUDA tensor"):
         ops.philox_normal(torch.zeros(8), seed=1)
+
+
+def test_library_depends_only_on_the_cuda_runtime():
+    """The drop-in boundary is a plain C ABI: libbdl.so must not link libtorch, libpython or anything beyond the CUDA
+    runtime and the C/C++ runtimes."""
+    import subprocess
+    from bayesdll_b200 import _lib
+    out = subprocess.check_output(["readelf", "-d", _lib.LIB_PATH], text=True)
+    needed = [ln.split("[")[1].rstrip("]") for ln in out.splitlines() if "NEEDED" in ln]
+    assert needed, out
+    allowed = ("libcudart", "libstdc++", "libm.", "libgcc_s", "libc.", "libdl", "libpthread", "librt", "ld-linux")
+    assert all(n.startswith(allowed) for n in needed), needed
+    assert any(n.startswith("libcudart") for n in needed)
