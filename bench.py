@@ -248,6 +248,9 @@ def run_ours(args):
         del theta, g, theta0, v
         torch.cuda.empty_cache()
         extras["train_step"] = guarded("train_step", train_step_extra, device, rank, world)
+        torch.cuda.empty_cache()
+        extras["train_step_resnet101"] = guarded("train_step_resnet101", train_step_extra, device, rank, world, steps=10,
+                                                 batch=16, backbone="resnet101")
     if not args.no_ensemble:
         torch.cuda.empty_cache()
         extras["ensemble"] = guarded("ensemble", ensemble_extra, device, rank, world, args)
@@ -469,7 +472,7 @@ def sample_store_extra(lay, theta, step, device, peak, reps=20):
             "file_identical": bool(same)}
 
 
-def train_step_extra(device, rank, world, steps=6, batch=64):
+def train_step_extra(device, rank, world, steps=6, batch=64, backbone="vit_l_32"):
     """The call a user of the drop-in makes: Model.forward(x, y, net, net0, criterion, lrs, Ninflate, nd)."""
     import argparse as ap
     import logging
@@ -477,8 +480,8 @@ def train_step_extra(device, rank, world, steps=6, batch=64):
     from bayesdll_b200.methods import sghmc
     torch.manual_seed(42 + rank)
     with torch.device(device):
-        net = shapes.create_backbone("vit_l_32", 37)
-        net0 = shapes.create_backbone("vit_l_32", 37)
+        net = shapes.create_backbone(backbone, 37)
+        net0 = shapes.create_backbone(backbone, 37)
     a = ap.Namespace(device=device, ND=HP["ND"], lr=HP["lr_body"], lr_head=HP["lr_head"], momentum=0.5, epochs=1,
                      pretrained="synthetic", num_classes=37, ece_num_bins=15, test_eval_freq=1, log_dir=tempfile.gettempdir(),
                      seed=42 + rank,
@@ -506,10 +509,43 @@ def train_step_extra(device, rank, world, steps=6, batch=64):
     torch.cuda.synchronize()
     dt = allmax(time.perf_counter() - t0, world, device)
     n = runner.model.chain.layout.n_dense
+    # the same user call the reference's way: fwd + bwd, then the per-tensor eager update loop + SGD step
+    # (baseline/eager_port.py restating methods/sghmc.py:482-510, :229) on the same network and GPU
+    ref_ms = None
+    try:
+        from baseline import eager_port
+        names = [nm for nm, _ in runner.net.named_parameters()]
+        params = [p for _, p in runner.net.named_parameters()]
+        params0 = [p.data for p in runner.net0.parameters()]
+        mom = [torch.zeros_like(p) for p in params]
+        hp = dict(lr_body=HP["lr_body"], lr_head=HP["lr_head"], ND=HP["ND"], Ninflate=HP["Ninflate"], prior_sig=HP["prior_sig"],
+                  nd=HP["nd"], alpha=HP["alpha"])
+
+        def one_ref():
+            x, y = x_host.to(device, non_blocking=True), y_host.to(device, non_blocking=True)
+            out = runner.net(x)
+            loss_t = runner.criterion(out, y)
+            runner.net.zero_grad()
+            loss_t.backward()
+            eager_port.sghmc_step_eager([p.data for p in params], [p.grad for p in params], params0, mom, names,
+                                        runner.net.readout_name, **hp)
+            return loss_t.item()
+        for _ in range(2):
+            one_ref()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            one_ref()
+        torch.cuda.synchronize()
+        ref_ms = allmax(time.perf_counter() - t0, world, device) / steps * 1e3
+        del mom
+    except Exception as e:                                   # context figure only
+        ref_ms = f"failed: {type(e).__name__}: {e}"
     res = {"value": world * n * steps / dt, "unit": "params/s", "ms_per_step": dt / steps * 1e3, "steps": steps,
+           "reference_structure_ms_per_step": ref_ms,
            "images_per_s": world * batch * steps / dt, "h2d_bytes_per_step": x_host.numel() * 4 + y_host.numel() * 8,
            "d2h_bytes_per_step": 4, "last_loss": loss,
-           "api": "bayesdll_b200.methods.sghmc.Model.forward on torchvision vit_l_32, batch 64, fp32 fwd/bwd in PyTorch"}
+           "api": f"bayesdll_b200.methods.sghmc.Model.forward on torchvision {backbone}, batch {batch}, fp32 fwd/bwd in PyTorch"}
     del runner, net, net0
     return res
 
