@@ -272,7 +272,8 @@ step_kernel(const StepParams p) {
                 cursor_seek(cur, p, q);
                 cls[u] = cur.cls;
                 const uint64_t i = static_cast<uint64_t>(q) << 2;
-                if (!p.flat_g) g[u] = ld_stream(cur.gbase + i);
+                const bool skipped = (cur.cls & BDL_CLS_SKIP) != 0;       // p.grad is None: no gradient to read (g may be null)
+                if (!p.flat_g && !skipped) g[u] = ld_stream(cur.gbase + i);
                 if (cur.own_g && i + 4 > cur.valid_end) {  // tail group of a per-run gradient: zero the padding lanes
                     if (i + 0 >= cur.valid_end) g[u].x = 0.f;
                     if (i + 1 >= cur.valid_end) g[u].y = 0.f;

@@ -227,3 +227,63 @@ def test_noise_torch_mode_reproduces_reference_rng_stream(cuda_device):
     for (n_, p), view, vview in zip(named, chain.layout.views(chain.theta), chain.layout.views(chain.v)):
         assert torch.equal(view, p.data), n_
         assert torch.equal(vview, vs[n_]), n_
+
+
+@pytest.mark.parametrize("variant_name", ["sghmc", "adam_csghmc"])
+def test_parameters_without_gradient_are_left_untouched(cuda_device, variant_name):
+    """``if p.grad is not None`` (methods/sghmc.py:484): frozen / unused parameters keep theta and momentum; no flat
+    gradient buffer exists in that case, so the kernel must not read a gradient for those runs at all."""
+    from bayesdll_b200 import _lib, ops
+    from bayesdll_b200.chain import ChainState
+    dev = cuda_device
+    gen = torch.Generator().manual_seed(21)
+    variant = dict(sghmc=_lib.SGHMC, adam_csghmc=_lib.ADAM_CSGHMC)[variant_name]
+    ref, ref0 = _Net(gen).to(dev), _Net(gen).to(dev)
+    net, net0 = _Net(gen).to(dev), _Net(gen).to(dev)
+    net.load_state_dict(ref.state_dict())
+    net0.load_state_dict(ref0.state_dict())
+    chain = ChainState(net, net0, variant=variant, bias_mode="informative", noise="torch", seed=0)
+    named = list(ref.named_parameters())
+    names = [n for n, _ in named]
+    frozen = {"layers.1.weight", "norm.bias"}
+    p0s = [p for _, p in ref0.named_parameters()]
+    opt = er.make_sgd([p for n, p in named if READOUT not in n], [p for n, p in named if READOUT in n], HP["lr_body"],
+                      HP["lr_head"], 0.0)
+    vs = {n: torch.zeros_like(p) for n, p in named}
+    ms = {n: torch.zeros_like(p) for n, p in named}
+    ss = {n: torch.zeros_like(p) for n, p in named}
+    N = HP["ND"] * HP["Ninflate"]
+    before = {n: p.detach().clone() for n, p in named if n in frozen}
+    for t in range(1, 3):
+        grads = [None if n in frozen else (torch.randn(p.shape, generator=gen) * 0.05).to(dev) for n, p in named]
+        xis = [torch.randn(p.shape, generator=gen).to(dev) for _, p in named]
+        live = [(n, p) for (n, p), g in zip(named, grads) if g is not None]
+        live_p0 = [p0 for p0, g in zip(p0s, grads) if g is not None]
+        live_xi = [x for x, g in zip(xis, grads) if g is not None]
+        for (_, p), g in zip(named, grads):
+            p.grad = None if g is None else g.clone()
+        kw = dict(lr_body=HP["lr_body"], lr_head=HP["lr_head"], N=N, prior_sig=HP["prior_sig"], nd=HP["nd"])
+        if variant_name == "sghmc":
+            er.sghmc(live, live_p0, live_xi, vs, READOUT, alpha=HP["alpha"], bias="informative", **kw)
+        else:
+            er.adam(live, live_p0, live_xi, vs, ms, ss, READOUT, alpha=HP["alpha"], beta1=HP["beta1"], beta2=HP["beta2"],
+                    eps=HP["eps"], t=t, bias="informative", cyclical=True, temperature=HP["temperature"], **kw)
+        opt.step()
+        for p, g in zip(chain.params, grads):
+            p.grad = None if g is None else g.clone()
+        xi_flat = torch.zeros(chain.layout.n_padded, device=dev)
+        for view, xi in zip(chain.layout.views(xi_flat), xis):
+            view.copy_(xi)
+        sc = ops.make_scalars(variant, lr_body=HP["lr_body"], lr_head=HP["lr_head"], ND=HP["ND"], Ninflate=HP["Ninflate"],
+                              prior_sig=HP["prior_sig"], nd=HP["nd"], alpha=HP["alpha"], beta1=HP["beta1"], beta2=HP["beta2"],
+                              eps=HP["eps"], temperature=HP["temperature"], t=t)
+        runs_dev, nruns = chain._gradient_table()
+        assert chain.g_flat is None                               # nothing was gathered: every live gradient is read in place
+        ops.step(variant, chain.theta, None, chain.theta0, chain.v, chain.m, chain.s, None, runs_dev, nruns, sc,
+                 ops.make_noise(xi=xi_flat))
+    torch.cuda.synchronize()
+    for (n_, p), th, vv in zip(named, chain.layout.views(chain.theta), chain.layout.views(chain.v)):
+        assert torch.equal(th, p.data), n_
+        assert torch.equal(vv, vs[n_]), n_
+        if n_ in frozen:
+            assert torch.equal(th, before[n_]) and not vv.any()
