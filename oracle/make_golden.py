@@ -238,6 +238,29 @@ def make_calibration_golden():
     save("calibration", **out)
 
 
+def make_attribute_inventory():
+    """Names the reference's Runner / Model instances carry after __init__ (``self.<name> = ...`` statements) and the
+    public methods of both classes, per method file: the duck-typed surface other code may read."""
+    import ast
+    import json
+    ref = refshim.find_reference()
+    inv = {}
+    for m in ("sgld", "sghmc", "csgld", "csghmc", "csghmc_fs", "adam_sghmc", "adam_csghmc"):
+        tree = ast.parse(open(os.path.join(ref, "methods", f"{m}.py")).read())
+        for node in tree.body:
+            if isinstance(node, ast.ClassDef) and node.name in ("Runner", "Model"):
+                methods = [n.name for n in node.body if isinstance(n, ast.FunctionDef)]
+                init = next(n for n in node.body if isinstance(n, ast.FunctionDef) and n.name == "__init__")
+                attrs = sorted({t.attr for st in ast.walk(init) if isinstance(st, (ast.Assign, ast.AugAssign, ast.AnnAssign))
+                                for t in ast.walk(st) if isinstance(t, ast.Attribute) and isinstance(t.ctx, ast.Store)
+                                and isinstance(t.value, ast.Name) and t.value.id == "self"})
+                inv[f"{m}.{node.name}"] = {"methods": methods, "init_attributes": attrs}
+    path = os.path.join(GOLDEN_DIR, "api_inventory.json")
+    with open(path, "w") as f:
+        json.dump(inv, f, indent=1, sort_keys=True)
+    print(f"wrote {path}")
+
+
 def make_temperature_golden():
     """calibration.find_optimal_temperature (the reference's own function, scipy BFGS) on the calibration data sets, plus
     values of its objective at fixed temperatures computed with the reference's expression (calibration.py:179-183)."""
@@ -278,3 +301,5 @@ if __name__ == "__main__":
         make_golden_runner.main(save, only=list(make_golden_runner.FS_CASES) + ["real_csghmc_fs"])
     if "temperature" in which:
         make_temperature_golden()
+    if "attrs" in which:
+        make_attribute_inventory()

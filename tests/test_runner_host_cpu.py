@@ -66,3 +66,39 @@ def test_cycle_variance_spec_keeps_reference_quirks():
     wel = _bare(W, samples_per_cycle={1: 1, 2: 6}, _cyc2={1: "a", 2: "b"})
     assert wel._cycle_variance_spec(1) == (None, ops.VAR_TINY, 1.0)
     assert wel._cycle_variance_spec(2) == ("b", ops.VAR_FROM_WELFORD, 5.0)
+
+
+@pytest.mark.parametrize("method", ["sgld", "sghmc", "csgld", "csghmc", "csghmc_fs", "adam_sghmc", "adam_csghmc"])
+def test_runner_and_model_carry_the_reference_surface(method, tmp_path):
+    """Every public method of the reference's Runner / Model and every attribute their __init__ sets
+    (tests/golden/api_inventory.json, extracted from the reference's sources by oracle/make_golden.py attrs) exists on
+    the drop-in objects right after construction.  Construction needs no device: the flat state is built on first use."""
+    import importlib
+    import json
+    import logging
+    import os
+    import torch
+    import golden_util as gu
+    from oracle import make_golden_runner as mgr
+    inv = json.load(open(os.path.join(os.path.dirname(gu.golden_path("cyclical")), "api_inventory.json")))
+    hp = dict(prior_sig=1.0, Ninflate=1.0, nd=1.0, burnin=1, thin=1, nst=2, bias="informative", momentum_decay=0.1)
+    args = mgr.make_args(hp, str(tmp_path), torch.device("cpu"), momentum=0.5, epochs=4, num_cycles=2)
+    lg = logging.getLogger("surface")
+    lg.addHandler(logging.NullHandler())
+    mod = importlib.import_module(f"bayesdll_b200.methods.{method}")
+    runner = mod.Runner(mgr.InjectNet(1), mgr.InjectNet(2), args, lg)
+    for kind, obj in (("Runner", runner), ("Model", runner.model)):
+        entry = inv[f"{method}.{kind}"]
+        missing = [m for m in entry["methods"] if not callable(getattr(obj, m, None))]
+        assert not missing, f"{method}.{kind} lacks methods {missing}"
+        missing = [a for a in entry["init_attributes"] if not hasattr(obj, a)]
+        assert not missing, f"{method}.{kind} lacks attributes {missing}"
+    # the values other code reads have the reference's types
+    assert isinstance(runner.Ninflate, float) and isinstance(runner.nst, int) and isinstance(runner.thin, int)
+    assert [g["lr"] for g in runner.optimizer.param_groups] == [args.lr, args.lr_head]
+    assert isinstance(runner.criterion, torch.nn.CrossEntropyLoss)
+    # no CPU fallback: the first step on a CPU device is refused
+    from bayesdll_b200 import _lib
+    x, y = torch.zeros(4, 1, 4, 4), torch.zeros(4, dtype=torch.long)
+    with pytest.raises(_lib.BdlError, match="CUDA devices only"):
+        runner.model(x, y, runner.net, runner.net0, mgr.InjectCriterion(), [1e-3, 1e-2], 1.0, 1.0)
