@@ -299,6 +299,9 @@ if __name__ == "__main__":
     if "runner_fs" in which:                  # only the full-sample-store cases (methods/csghmc_fs.py)
         from oracle import make_golden_runner
         make_golden_runner.main(save, only=list(make_golden_runner.FS_CASES) + ["real_csghmc_fs"])
+    if "cfg1" in which:                       # BASELINE.json configs[0]: mlp_mnist SGLD end to end
+        from oracle import make_golden_runner
+        make_golden_runner.main(save, only="cfg1")
     if "temperature" in which:
         make_temperature_golden()
     if "attrs" in which:

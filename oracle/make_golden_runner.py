@@ -191,6 +191,81 @@ def run_reference_real_case(name):
     return rec
 
 
+# BASELINE.json configs[0]: mlp_mnist SGLD, the reference's own CPU-runnable case (README.md:83), on synthetic 28x28 batches
+# of 128.  burnin / thin / epochs are shortened (1 / 2 / 3 instead of 5 / 10 / 100) so the run takes seconds; everything
+# else is the documented command line.  2.8 M parameters: the noise comes from a seeded generator (refshim.SeededTape) and
+# the fixture keeps summaries (strided samples + fp64 sums) instead of whole vectors.
+CFG1 = dict(hp=dict(prior_sig=1.0, Ninflate=1e3, nd=1.0, burnin=1, thin=2, bias="informative", nst=5),
+            lr=1e-2, lr_head=1e-2, momentum=0.5, epochs=3, ND=30000, batch=128, n_train=4, n_eval=2, seed=4242, tape_seed=777)
+
+
+def cfg1_loaders():
+    rng = np.random.default_rng(CFG1["seed"])
+
+    def mk(nb):
+        return [(torch.from_numpy(rng.standard_normal((CFG1["batch"], 1, 28, 28)).astype(np.float32)),
+                 torch.from_numpy(rng.integers(0, 10, CFG1["batch"]).astype(np.int64))) for _ in range(nb)]
+    return mk(CFG1["n_train"]), mk(CFG1["n_eval"]), mk(CFG1["n_eval"])
+
+
+def cfg1_network():
+    """The reference's mlp_mnist (networks/small_nets.py:7-45: 784-1000-1000-1000-10) with a fixed CPU initialisation."""
+    from bayesdll_b200 import shapes
+    torch.manual_seed(CFG1["seed"])
+    return shapes.create_backbone("mlp_mnist", 10)
+
+
+def cfg1_args(log_dir, device, extra_hp=None):
+    a = make_args(dict(CFG1["hp"], **(extra_hp or {})), log_dir, device, momentum=CFG1["momentum"], epochs=CFG1["epochs"],
+                  lr=CFG1["lr"], lr_head=CFG1["lr_head"], ND=CFG1["ND"])
+    a.num_classes = 10
+    a.pretrained = None                        # zero prior mean, as the documented command line (no --pretrained)
+    return a
+
+
+def summarize(vec):
+    v = np.asarray(vec, np.float32).reshape(-1)
+    return dict(sample=v[::701].copy(), sum=np.float64(v.astype(np.float64).sum()),
+                sumsq=np.float64((v.astype(np.float64) ** 2).sum()), n=v.size)
+
+
+def run_reference_cfg1():
+    mod = refshim.load("methods.sgld")
+    loaders = cfg1_loaders()
+    net = cfg1_network()
+    log_dir = tempfile.mkdtemp(prefix="bdl_golden_cfg1_")
+    args = cfg1_args(log_dir, torch.device("cpu"))
+    logger = logging.getLogger("golden.cfg1")
+    logger.addHandler(logging.NullHandler())
+    logger.propagate = False
+    runner = mod.Runner(net, None, args, logger)
+    evals = []
+    orig_eval = runner.evaluate
+
+    def recording_eval(loader):
+        res = orig_eval(loader)
+        evals.append(res)
+        return res
+    runner.evaluate = recording_eval
+    cwd = os.getcwd()
+    os.chdir(log_dir)
+    try:
+        with refshim.injected_noise(CFG1["tape_seed"]) as tp:
+            runner.train(*loaders)
+            used, calls = tp.pos, tp.calls
+    finally:
+        os.chdir(cwd)
+    rec = dict(tape_used=used, tape_calls=calls, n_evals=len(evals), post_theta_cnt=runner.post_theta_cnt)
+    theta = torch.cat([p.detach().reshape(-1) for p in runner.net.parameters()]).numpy()
+    for name, vec in (("theta", theta), ("mom1", runner.post_theta_mom1.numpy()), ("mom2", runner.post_theta_mom2.numpy())):
+        for k, v in summarize(vec).items():
+            rec[f"{name}_{k}"] = v
+    for i, (loss, err, targets, logits, logits_all) in enumerate(evals):
+        rec[f"eval{i}_loss"], rec[f"eval{i}_err"] = loss, err
+        rec[f"eval{i}_targets"], rec[f"eval{i}_logits"] = targets, logits
+    return rec
+
+
 def make_loaders(seed, n_train=3, n_val=2, n_test=2):
     rng = np.random.default_rng(seed)
 
@@ -384,6 +459,11 @@ def run_reference_case(name):
 
 def main(save, only=None):
     torch.set_num_threads(1)
+    if only == "cfg1":
+        rec = run_reference_cfg1()
+        save("runner_cfg1_mlp_sgld", **rec)
+        print(f"  cfg1 mlp_mnist SGLD: {rec['tape_calls']} noise calls / {rec['tape_used']} draws, evaluate() calls {rec['n_evals']}")
+        return
     if only is not None:
         for name in only:
             rec = run_reference_real_case(name) if name in REAL_CASES else run_reference_case(name)

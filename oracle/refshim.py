@@ -119,9 +119,29 @@ class NoiseTape:
         return out.to(like.device)
 
 
+class SeededTape:
+    """Like ``NoiseTape`` for runs whose noise would not fit a fixture (millions of parameters x many draws): values come
+    from ``numpy.random.default_rng(seed).standard_normal(n, float32)`` call by call, so the golden generator and the GPU
+    test regenerate the same stream from the seed alone (both make the same sequence of calls)."""
+
+    def __init__(self, seed):
+        import numpy as np
+        self.rng = np.random.default_rng(seed)
+        self.pos = 0
+        self.calls = 0
+
+    def __call__(self, like, **kw):
+        import numpy as np
+        n = like.numel()
+        out = torch.from_numpy(self.rng.standard_normal(n, dtype=np.float32)).reshape(like.shape)
+        self.pos += n
+        self.calls += 1
+        return out.to(like.device)
+
+
 @contextlib.contextmanager
 def injected_noise(flat_noise):
-    tape = NoiseTape(flat_noise)
+    tape = SeededTape(int(flat_noise)) if isinstance(flat_noise, (int,)) else NoiseTape(flat_noise)
     orig = torch.randn_like
     torch.randn_like = tape
     try:

@@ -468,3 +468,47 @@ def test_checkpoint_roundtrip(cuda_device, tmp_path, name):
         assert torch.equal(fresh._dense(fresh.model.chain.buf), runner._dense(runner.model.chain.buf))   # padding is not part of a ckpt
         p0 = fresh.model.chain.params[0]
         assert fresh.optimizer.state[p0]["momentum_buffer"].data_ptr() == fresh.model.chain.layout.views(fresh.model.chain.buf)[0].data_ptr()
+
+
+def test_baseline_cfg1_mlp_mnist_sgld_end_to_end(cuda_device, tmp_path):
+    """BASELINE.json configs[0] -- mlp_mnist SGLD (prior_sig=1, Ninflate=1e3, nst=5, lr=1e-2, momentum=0.5, batch 128), the
+    reference's own CPU-runnable case: the reference ran it on CPU (oracle/make_golden_runner.py cfg1, shortened burn-in),
+    the drop-in runs it on the GPU with the same seeded noise stream.  Real autograd on both sides, so gradients differ
+    at the 1e-7 level (CPU vs GPU matmul) and results are compared with a tolerance; 2.8 M parameters are compared
+    through strided samples and fp64 sums."""
+    from oracle import make_golden_runner as mgr
+    from oracle import refshim
+    from bayesdll_b200.methods import sgld
+    z = np.load(gu.golden_path("runner_cfg1_mlp_sgld"), allow_pickle=False)
+    net = mgr.cfg1_network()
+    args = mgr.cfg1_args(str(tmp_path), cuda_device, extra_hp=dict(noise="torch", div="ieee"))
+    runner = sgld.Runner(net, None, args, _logger())
+    evals = []
+    orig = runner.evaluate
+
+    def rec(loader):
+        r = orig(loader)
+        evals.append(r)
+        return r
+    runner.evaluate = rec
+    cwd = os.getcwd()
+    os.chdir(tmp_path)
+    try:
+        with refshim.injected_noise(mgr.CFG1["tape_seed"]) as tape:
+            runner.train(*mgr.cfg1_loaders())
+    finally:
+        os.chdir(cwd)
+    assert tape.pos == int(z["tape_used"]) and tape.calls == int(z["tape_calls"])
+    assert runner.post_theta_cnt == int(z["post_theta_cnt"]) and len(evals) == int(z["n_evals"])
+    got = {"theta": runner._dense(runner.model.chain.theta), "mom1": runner.post_theta_mom1, "mom2": runner.post_theta_mom2}
+    for name, vec in got.items():
+        s = mgr.summarize(vec.cpu().numpy())
+        assert s["n"] == int(z[f"{name}_n"]) == 2797010
+        assert gu.max_rel(s["sample"], z[f"{name}_sample"]) <= 2e-4, (name, gu.max_rel(s["sample"], z[f"{name}_sample"]))
+        assert abs(s["sumsq"] - float(z[f"{name}_sumsq"])) <= 1e-5 * float(z[f"{name}_sumsq"]), name
+        assert abs(s["sum"] - float(z[f"{name}_sum"])) <= 1e-4 * np.sqrt(float(z[f"{name}_sumsq"]) * s["n"]), name
+    for i, (loss, err, targets, logits, _) in enumerate(evals):
+        assert np.array_equal(targets, z[f"eval{i}_targets"])
+        np.testing.assert_allclose(logits, z[f"eval{i}_logits"], atol=5e-3, rtol=5e-3)
+        assert abs(loss - float(z[f"eval{i}_loss"])) <= 5e-3
+    assert os.path.exists(os.path.join(tmp_path, "ckpt.pt")) and os.path.exists(os.path.join(tmp_path, "logits_test.pkl"))
