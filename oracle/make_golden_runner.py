@@ -266,6 +266,41 @@ def run_reference_cfg1():
     return rec
 
 
+# BASELINE.json configs[1]: torchvision ResNet-101 (37 classes) cSGHMC with the cyclical step size, Pets-shaped synthetic
+# 224x224 batches of 16, random-init net0 (pretrain_resnet101.py:127, README.md:111).  No CPU recording is kept for this
+# case: a random-init ResNet-101 is numerically chaotic (plain PyTorch CPU vs GPU gradients of conv1 already differ by 6 %
+# at the first step and 180 % at the second), so a cross-device trajectory comparison says nothing about the sampler.  The
+# helpers below feed tests/test_backbone_parity_gpu.py, which runs the reference's statements and the drop-in side by
+# side on the SAME device and requires bit-identical parameters and BatchNorm buffers.
+CFG2 = dict(hp=dict(prior_sig=1.0, Ninflate=1.0, nd=0.01, burnin=0, momentum_decay=0.18, thin=1, bias="informative", nst=1),
+            lr=1e-4, lr_head=1e-2, momentum=0.0, epochs=2, num_cycles=2, ND=1840, batch=16, n_train=3, n_eval=1, seed=2121,
+            tape_seed=888)
+
+
+def cfg2_loaders():
+    rng = np.random.default_rng(CFG2["seed"])
+
+    def mk(nb):
+        return [(torch.from_numpy(rng.standard_normal((CFG2["batch"], 3, 224, 224)).astype(np.float32)),
+                 torch.from_numpy(rng.integers(0, 37, CFG2["batch"]).astype(np.int64))) for _ in range(nb)]
+    return mk(CFG2["n_train"]), mk(CFG2["n_eval"]), mk(CFG2["n_eval"])
+
+
+def cfg2_networks():
+    from bayesdll_b200 import shapes
+    torch.manual_seed(CFG2["seed"])
+    net = shapes.create_backbone("resnet101", 37)
+    net0 = shapes.create_backbone("resnet101", 37)
+    return net, net0
+
+
+def cfg2_args(log_dir, device, extra_hp=None):
+    a = make_args(dict(CFG2["hp"], **(extra_hp or {})), log_dir, device, momentum=CFG2["momentum"], epochs=CFG2["epochs"],
+                  num_cycles=CFG2["num_cycles"], lr=CFG2["lr"], lr_head=CFG2["lr_head"], ND=CFG2["ND"])
+    a.num_classes = 37
+    return a
+
+
 def make_loaders(seed, n_train=3, n_val=2, n_test=2):
     rng = np.random.default_rng(seed)
 
