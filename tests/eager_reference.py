@@ -79,3 +79,46 @@ def adam(named, p0s, xis, vs, ms, ss, readout, *, lr_body, lr_head, N, prior_sig
         vm = vm * (1 - alpha) + lr * precond_grad + noise
         vs[name], ms[name], ss[name] = vm, m, s
         p.grad = vm.clone() if cyclical else p.grad + vm.clone()
+
+
+@torch.no_grad()
+def evaluate_cyclical_avg(net, mom1, mom2, samples_per_cycle, gmm_weights, nst, loader, device):
+    """methods/csgld.py:333-456 for nst > 0: per batch, per kept cycle, ``nst`` networks drawn as
+    ``p_mean + p_var.sqrt() * randn_like(p)`` with ``p_var = clamp(ratio * (mom2 - mom1**2), 1e-12)``; component output
+    ``logsumexp_S(log_softmax_K) - log S``; mixture = weighted sum of the component outputs.
+    ``mom1`` / ``mom2``: dict cycle -> dense parameters_to_vector-ordered vectors.  Returns (logits, logits_all, targets)."""
+    import copy
+    import torch.nn.functional as F
+    from torch.nn.utils import vector_to_parameters
+    logits, logits_all, targets = [], [], []
+    for x, y in loader:
+        x, y = x.to(device), y.to(device)
+        comps, mix = [], None
+        for c in mom1:
+            w = gmm_weights.get(c, 0.0)
+            if w < 1e-10:
+                continue
+            net_c = copy.deepcopy(net)
+            net_c.eval()
+            means, variances = copy.deepcopy(net_c), copy.deepcopy(net_c)
+            cnt = samples_per_cycle.get(c, 0)
+            ratio = cnt / (cnt - 1)
+            var = ratio * (mom2[c] - mom1[c] ** 2) if cnt > 1 else mom2[c] - mom1[c] ** 2
+            var.clamp_(min=1e-12)
+            vector_to_parameters(var, variances.parameters())
+            vector_to_parameters(mom1[c], means.parameters())
+            outs = []
+            for _ in range(nst):
+                sample = copy.deepcopy(net_c)
+                for p, pm, pv in zip(sample.parameters(), means.parameters(), variances.parameters()):
+                    eps = torch.randn_like(p)
+                    p.copy_(pm + pv.sqrt() * eps)
+                outs.append(sample(x))
+            stacked = torch.stack(outs, dim=2)
+            comp = F.log_softmax(stacked, dim=1).logsumexp(-1) - np.log(nst)
+            comps.append(stacked)
+            mix = w * comp if mix is None else mix + w * comp
+        logits.append(mix)
+        logits_all.append(torch.stack(comps, dim=3))
+        targets.append(y)
+    return torch.cat(logits), torch.cat(logits_all), torch.cat(targets)

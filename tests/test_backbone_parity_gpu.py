@@ -129,3 +129,42 @@ def test_cfg3_cfg4_vit_l_32_training_steps(cuda_device, deterministic_fp32, tmp_
         assert loss_a == loss.item()
         _assert_identical(t, runner, named, vs, *( (ms, ss) if method == "adam_csghmc" else ()))
     assert runner.model.chain.layout.n_dense == 305548325
+
+
+def test_cfg5_resnet101_csgld_ensemble_and_calibration(cuda_device, deterministic_fp32, tmp_path):
+    """configs[4]: ResNet-101 cSGLD posterior-predictive ensemble (cycles x nst samples, GMM mixture) + ECE/MCE/NLL.  The
+    drop-in trains two short cycles, then ``evaluate()`` (noise=torch, seeded) is compared with the reference's evaluate
+    statements (methods/csgld.py:333-456) fed with the drop-in's own cycle moments on the same GPU: every sampled
+    network's logits are bit-identical (same draws, same forward), the mixture within 1e-5, and the calibration metrics
+    of both agree."""
+    from oracle import make_golden_runner as mgr
+    from bayesdll_b200 import calibration
+    from bayesdll_b200.methods import csgld
+    dev = cuda_device
+    net, net0 = mgr.cfg2_networks()
+    hp = dict(prior_sig=1.0, Ninflate=1.0, nd=0.01, thin=1, bias="informative", nst=2, noise="torch")
+    args = mgr.make_args(hp, str(tmp_path), dev, momentum=0.5, epochs=4, num_cycles=2, lr=1e-4, lr_head=1e-2, ND=1840)
+    args.num_classes = 37
+    runner = csgld.Runner(net, net0, args, _logger())
+    train, _, test = mgr.cfg2_loaders()
+    gen = torch.Generator().manual_seed(9)
+    test = test + [(torch.randn(16, 3, 224, 224, generator=gen), torch.randint(0, 37, (16,), generator=gen))]
+    torch.manual_seed(1)
+    runner.train(train, None, test)
+    assert sorted(runner.cycle_theta_mom1) == [1, 2] and all(v >= 2 for v in runner.samples_per_cycle.values())
+    torch.manual_seed(123)
+    loss, err, targets, logits, logits_all = runner.evaluate(test)
+    weights = runner.calculate_gmm_weights()
+    torch.manual_seed(123)
+    ref_logits, ref_all, ref_targets = er.evaluate_cyclical_avg(runner.net, runner.cycle_theta_mom1, runner.cycle_theta_mom2,
+                                                                runner.samples_per_cycle, weights, runner.nst, test, dev)
+    assert logits_all.shape == tuple(ref_all.shape) == (32, 37, 2, 2)
+    assert torch.equal(torch.from_numpy(logits_all), ref_all.cpu()), "a sampled network's logits differ"
+    assert torch.equal(torch.from_numpy(targets), ref_targets.cpu())
+    torch.testing.assert_close(torch.from_numpy(logits), ref_logits.float().cpu(), atol=1e-5, rtol=1e-5)
+    ref_loss = torch.nn.functional.cross_entropy(ref_logits.float(), ref_targets).item()
+    assert abs(loss - ref_loss) <= 1e-5 * max(1.0, abs(ref_loss))
+    assert err == ref_logits.argmax(1).ne(ref_targets).float().mean().item()
+    a = calibration.analyze(targets, logits, 15, None)
+    b = calibration.analyze(ref_targets.cpu().numpy(), ref_logits.float().cpu().numpy(), 15, None)
+    assert all(abs(x - y) <= 1e-5 for x, y in zip(a, b))
