@@ -68,7 +68,7 @@ def build(force=False, verbose=False):
             sys.stderr.write(f"--- {src} ---\n{out}\n")
     if failed:
         raise RuntimeError("libbdl build failed")
-    subprocess.check_call([nvcc, "-shared", "-o", OUT, *objs, "-lcudart"])
+    subprocess.check_call([nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", OUT, *objs, "-lcudart"])
     return OUT
 
 
