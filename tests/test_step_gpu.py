@@ -275,3 +275,52 @@ def test_fused_capture_argument_errors(cuda_device):
     cap.kind = 9
     with pytest.raises(_lib.BdlError, match="capture kind"):
         ops.step(_lib.SGHMC, z(64), z(64), z(64), z(64), None, None, None, runs_dev, nruns, sc, ops.make_noise(seed=1), capture=cap)
+
+
+@pytest.mark.parametrize("variant_name", ["sgld", "sgld_mu0", "sghmc", "csghmc", "adam_sghmc", "adam_csghmc"])
+@pytest.mark.parametrize("philox", [True, False])
+def test_fast_path_build_equals_generic_build(cuda_device, variant_name, philox):
+    """The library's default launch for a two-run (body | head) inline table with a flat gradient is a leaner build of the
+    same kernel (no tile loop, no table dispatch).  An explicit launch-shape request runs the generic build: same bits,
+    both division modes, ragged tail, head boundary in the middle of a tile, and a skipped head run."""
+    from bayesdll_b200 import _lib, ops
+    from bayesdll_b200.flat import FlatLayout
+    dev = cuda_device
+    base = variant_name.split("_mu")[0]
+    variant = dict(sgld=_lib.SGLD, sghmc=_lib.SGHMC, csghmc=_lib.CSGHMC, adam_sghmc=_lib.ADAM_SGHMC,
+                   adam_csghmc=_lib.ADAM_CSGHMC)[base]
+    mu = 0.5 if variant_name in ("sgld", "adam_sghmc") else 0.0
+    adam = base.startswith("adam")
+    default_threads = 256 if variant_name == "sgld_mu0" else (128 if base == "csghmc" else 64)
+    lay = FlatLayout([("body.weight", (1_000_003,)), ("classifier.weight", (37, 1021)), ("classifier.bias", (37,))], "classifier")
+    n = lay.n_padded
+    gen = torch.Generator(device=dev).manual_seed(5)
+    init = {k: torch.randn(n, device=dev, generator=gen) * sc for k, sc in
+            dict(theta=0.1, g=0.05, theta0=0.1, v=0.01, m=0.01, buf=0.01, xi=1.0).items()}
+    init["s"] = torch.rand(n, device=dev, generator=gen) * 1e-3 + 1e-6
+    for skip_head in (False, True):
+        tab = lay.run_table("informative")
+        assert len(tab) == 2
+        if skip_head:
+            tab[1].cls |= _lib.CLS_SKIP
+        runs_dev, nruns = ops.upload_runs(tab, dev)
+        for div in (_lib.DIV_RECIP, _lib.DIV_IEEE):
+            sc = ops.make_scalars(variant, lr_body=1e-3, lr_head=1e-2, ND=1840, Ninflate=10.0, prior_sig=0.9, nd=0.7, alpha=0.18,
+                                  mu=mu, t=5, temperature=1.3, div_mode=div)
+            res = []
+            for cfg in ((0, 0, 0), (0, 1, default_threads), (0, 2, 128)):
+                ops.set_launch_config(*cfg)
+                st = {k: v.clone() for k, v in init.items()}
+                nz = ops.make_noise(seed=11, subseq=4) if philox else ops.make_noise(xi=st["xi"])
+                ops.step(variant, st["theta"], st["g"], None if base == "csghmc" else st["theta0"],
+                         None if base == "sgld" else st["v"], st["m"] if adam else None, st["s"] if adam else None,
+                         st["buf"] if mu else None, runs_dev, nruns, sc, nz)
+                torch.cuda.synchronize()
+                ops.set_launch_config(0, 0, 0)
+                res.append(st)
+            for k in ("theta", "v", "m", "s", "buf"):
+                assert torch.equal(res[0][k], res[1][k]) and torch.equal(res[0][k], res[2][k]), (k, skip_head, div)
+            assert not torch.equal(res[0]["theta"], init["theta"])
+            if skip_head:
+                hb = lay.segments[1].begin
+                assert torch.equal(res[0]["theta"][hb:], init["theta"][hb:])
