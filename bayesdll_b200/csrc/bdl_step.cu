@@ -200,14 +200,13 @@ __device__ __forceinline__ uint32_t cursor_find_warp(const StepParams& p, uint32
 // (bdl_moments_welford arithmetic).  Fusing saves the capture kernel's re-read of theta: 40 instead of 44 B/param for
 // SGHMC + moments, which is every step after burn-in when thin = 1 (BASELINE.json configs[2]).
 // kFast: the launch every BASELINE config makes -- grid == #tiles (one tile per CTA, no tile loop), the two-run
-// body | head table inside the kernel arguments, a flat gradient buffer, no capture.  Same arithmetic, ~10 % fewer
+// body | head table inside the kernel arguments, a flat gradient buffer (with or without capture).  Same arithmetic, ~10 % fewer
 // instructions (no tile-loop bookkeeping, no table-kind dispatch); matters when the box's power cap pulls the SM clock
 // down and the kernel turns issue-sensitive.
 template <int kVariant, bool kHasBuf, bool kPhilox, int kDiv, int kU, int kT, int kCap = 0, bool kFast = false>
 __global__ void __launch_bounds__(kT, (min_blocks<kVariant, kHasBuf, kPhilox, kU, kT, kCap>()))
 step_kernel(const StepParams p) {
     using U = Uses<kVariant>;
-    static_assert(!kFast || kCap == 0, "the fast path has no capture");
     constexpr uint32_t tile_groups = kT * kU;
     uint32_t tile = blockIdx.x;
     uint32_t ntiles = 0;
@@ -383,9 +382,9 @@ static int launch_shape(const StepParams& p, cudaStream_t st) {
     }
     if (grid > 0x7FFFFFFFull) grid = 0x7FFFFFFFull;
     if (grid == 0) return BDL_OK;
-    if constexpr (kCap == 0 && kAllowFast) {
+    if constexpr (kAllowFast) {
         if (grid == ntiles && p.inl_n == 2 && p.flat_g) {
-            step_kernel<kVariant, kHasBuf, kPhilox, kDiv, kU, kT, 0, true><<<static_cast<uint32_t>(grid), kT, 0, st>>>(p);
+            step_kernel<kVariant, kHasBuf, kPhilox, kDiv, kU, kT, kCap, true><<<static_cast<uint32_t>(grid), kT, 0, st>>>(p);
             return check_cuda(cudaGetLastError(), "step_kernel launch");
         }
     }
@@ -404,8 +403,8 @@ static int launch_u(const StepParams& p, cudaStream_t st) {
     if (p.cap1) {
         // fused capture: two more streams per element -> always >= 5, i.e. the 64-thread shape; the launch-shape knobs
         // of bdl_set_launch_config do not apply (one instantiation per variant keeps the binary small)
-        return p.cap_kind == BDL_CAPTURE_WELFORD ? launch_shape<kVariant, kHasBuf, kPhilox, kDiv, 1, 64, 2>(p, st)
-                               : launch_shape<kVariant, kHasBuf, kPhilox, kDiv, 1, 64, 1>(p, st);
+        return p.cap_kind == BDL_CAPTURE_WELFORD ? launch_shape<kVariant, kHasBuf, kPhilox, kDiv, 1, 64, 2, true>(p, st)
+                               : launch_shape<kVariant, kHasBuf, kPhilox, kDiv, 1, 64, 1, true>(p, st);
     }
     const int unroll = g_unroll ? g_unroll : kDefaultUnroll;
     const int threads = g_threads ? g_threads : kAutoThreads;

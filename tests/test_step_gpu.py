@@ -324,3 +324,41 @@ def test_fast_path_build_equals_generic_build(cuda_device, variant_name, philox)
             if skip_head:
                 hb = lay.segments[1].begin
                 assert torch.equal(res[0]["theta"][hb:], init["theta"][hb:])
+
+
+@pytest.mark.parametrize("variant_name", ["sghmc", "csghmc", "adam_csghmc", "sgld"])
+@pytest.mark.parametrize("kind", ["avg", "welford"])
+def test_fast_path_with_capture_equals_step_then_moments(cuda_device, variant_name, kind):
+    """The lean default build also carries the fused capture (two-run inline table + flat gradient, the runners' launch
+    after burn-in when the gradient is gathered): identical to the plain step followed by the stand-alone moment kernel."""
+    from bayesdll_b200 import _lib, ops
+    from bayesdll_b200.flat import FlatLayout
+    dev = cuda_device
+    variant = dict(sgld=_lib.SGLD, sghmc=_lib.SGHMC, csghmc=_lib.CSGHMC, adam_csghmc=_lib.ADAM_CSGHMC)[variant_name]
+    mu = 0.5 if variant_name == "sgld" else 0.0
+    adam = variant_name.startswith("adam")
+    lay = FlatLayout([("body.weight", (500_003,)), ("classifier.weight", (37, 301)), ("classifier.bias", (37,))], "classifier")
+    n = lay.n_padded
+    gen = torch.Generator(device=dev).manual_seed(8)
+    init = {k: torch.randn(n, device=dev, generator=gen) * sc for k, sc in
+            dict(theta=0.1, g=0.05, theta0=0.1, v=0.01, m=0.01, buf=0.01).items()}
+    init["s"] = torch.rand(n, device=dev, generator=gen) * 1e-3 + 1e-6
+    runs_dev, nruns = ops.upload_runs(lay.run_table("informative"), dev)
+    for div in (_lib.DIV_RECIP, _lib.DIV_IEEE):
+        sc = ops.make_scalars(variant, lr_body=1e-3, lr_head=1e-2, ND=1840, Ninflate=10.0, prior_sig=0.9, nd=0.7, alpha=0.18,
+                              mu=mu, t=5, temperature=1.3, div_mode=div)
+        A = {k: v.clone() for k, v in init.items()}
+        B = {k: v.clone() for k, v in init.items()}
+        capA = [torch.full((n,), 3.0, device=dev), torch.full((n,), 3.0, device=dev)]
+        capB = [t.clone() for t in capA]
+        for step_no, (cnt, first) in enumerate([(1 if kind == "welford" else 0, True), (3, False)]):
+            args = lambda S: (variant, S["theta"], S["g"], None if variant_name == "csghmc" else S["theta0"],
+                              None if variant_name == "sgld" else S["v"], S["m"] if adam else None, S["s"] if adam else None,
+                              S["buf"] if mu else None, runs_dev, nruns, sc, ops.make_noise(seed=2, subseq=step_no))
+            ops.step(*args(A), capture=ops.make_capture(kind, capA[0], capA[1], cnt, init=first))
+            ops.step(*args(B))
+            (ops.moments_welford if kind == "welford" else ops.moments_avg)(B["theta"], capB[0], capB[1], cnt, init=first, div_mode=div)
+        torch.cuda.synchronize()
+        for k in A:
+            assert torch.equal(A[k], B[k]), (k, div)
+        assert torch.equal(capA[0], capB[0]) and torch.equal(capA[1], capB[1]), div
