@@ -18,7 +18,9 @@ struct bdl_chain {
     bdl_run* runs_dev = nullptr;
     cudaStream_t s_h2d = nullptr, s_cmp = nullptr, s_d2h = nullptr;
     std::vector<cudaEvent_t> ev_h2d, ev_cmp;
-    uint64_t chunk = 0;   // elements per chunk (multiple of 4)
+    uint64_t chunk = 0;   // elements per steady-state chunk (multiple of 4)
+    std::vector<uint64_t> bounds;   // chunk boundaries (elements): ramp-up / ramp-down chunks at both ends shorten the
+                                    // pipeline's fill (first H2D before any compute) and drain (last D2H after all compute)
 };
 
 namespace {
@@ -70,7 +72,24 @@ extern "C" int bdl_chain_create(uint64_t n, int variant, int with_sgd_momentum, 
     if (rc == BDL_OK) rc = check_cuda(cudaStreamCreateWithFlags(&c->s_h2d, cudaStreamNonBlocking), "stream");
     if (rc == BDL_OK) rc = check_cuda(cudaStreamCreateWithFlags(&c->s_cmp, cudaStreamNonBlocking), "stream");
     if (rc == BDL_OK) rc = check_cuda(cudaStreamCreateWithFlags(&c->s_d2h, cudaStreamNonBlocking), "stream");
-    const uint64_t nchunks = (n + c->chunk - 1) / c->chunk;
+    {   // boundaries: chunk/8, chunk/4, chunk/2, then full chunks, then chunk/2, chunk/4, chunk/8 (all multiples of 4)
+        const uint64_t ramp[3] = {c->chunk / 8 / 4 * 4, c->chunk / 4 / 4 * 4, c->chunk / 2 / 4 * 4};
+        uint64_t head = 0, tail = 0;
+        for (uint64_t r : ramp) { head += r; tail += r; }
+        c->bounds.push_back(0);
+        if (ramp[0] >= 4 && n > 2 * (head + tail)) {
+            uint64_t pos = 0;
+            for (int i = 0; i < 3; ++i) { pos += ramp[i]; c->bounds.push_back(pos); }
+            const uint64_t mid_end = n - tail;
+            while (pos + c->chunk < mid_end) { pos += c->chunk; c->bounds.push_back(pos); }
+            if (pos < mid_end) { pos = mid_end; c->bounds.push_back(pos); }
+            for (int i = 2; i >= 0; --i) { pos += ramp[i]; c->bounds.push_back(pos); }
+        } else {
+            for (uint64_t pos = c->chunk; pos < n; pos += c->chunk) c->bounds.push_back(pos);
+            c->bounds.push_back(n);
+        }
+    }
+    const uint64_t nchunks = c->bounds.size() - 1;
     for (uint64_t i = 0; i < nchunks && rc == BDL_OK; ++i) {
         cudaEvent_t a, b;
         rc = check_cuda(cudaEventCreateWithFlags(&a, cudaEventDisableTiming), "event");
@@ -115,10 +134,10 @@ extern "C" int bdl_chain_step_host(bdl_chain* c, const float* g_host, float* the
     for (uint32_t r = 0; r < nruns; ++r)
         BDL_REQUIRE(runs_host[r].g_dev == nullptr, BDL_ERR_UNSUPPORTED, "bdl_chain_step_host: per-run gradient pointers not supported");
     BDL_CUDA(cudaMemcpyAsync(c->runs_dev, runs_host, nruns * sizeof(bdl_run), cudaMemcpyHostToDevice, c->s_cmp));
-    const uint64_t nchunks = (c->n + c->chunk - 1) / c->chunk;
+    const uint64_t nchunks = c->bounds.size() - 1;
     for (uint64_t k = 0; k < nchunks; ++k) {
-        const uint64_t off = k * c->chunk;
-        const uint64_t len = c->n - off < c->chunk ? c->n - off : c->chunk;
+        const uint64_t off = c->bounds[k];
+        const uint64_t len = c->bounds[k + 1] - off;
         BDL_CUDA(cudaMemcpyAsync(c->buf[kGrad] + off, g_host + off, len * sizeof(float), cudaMemcpyHostToDevice, c->s_h2d));
         BDL_CUDA(cudaEventRecord(c->ev_h2d[k], c->s_h2d));
         BDL_CUDA(cudaStreamWaitEvent(c->s_cmp, c->ev_h2d[k], 0));
