@@ -11,11 +11,11 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libbdl.so")
 
 # ---- enums / constants (include/bdl.h) -------------------------------------------------------
-BDL_ABI_VERSION = 4
+BDL_ABI_VERSION = 5
 SGLD, SGHMC, CSGHMC, ADAM_SGHMC, ADAM_CSGHMC = range(5)
 VARIANT_NAMES = {SGLD: "sgld", SGHMC: "sghmc", CSGHMC: "csghmc", ADAM_SGHMC: "adam_sghmc",
                  ADAM_CSGHMC: "adam_csghmc"}
-CLS_HEAD, CLS_PRIOR, CLS_SKIP = 1, 2, 4
+CLS_HEAD, CLS_PRIOR, CLS_SKIP, CLS_NODROP = 1, 2, 4, 8
 DIV_IEEE, DIV_RECIP = 0, 1
 STREAM_STEP, STREAM_DRAW, STREAM_USER = 0, 1, 2
 BUF_THETA, BUF_THETA0, BUF_V, BUF_M, BUF_S, BUF_SGD, BUF_GRAD = range(7)
@@ -70,6 +70,7 @@ SIGNATURES = {
     "bdl_capture_ring": [_P, _P, _U64, _U64, _P],
     "bdl_set_ring_config": [_I32],
     "bdl_draw": [_P, _P, _P, _P, _U64, _I32, _F, _I32, C.POINTER(Noise), _P],
+    "bdl_dropout_mix": [_P, _P, _P, _P, _U64, _P, _U32, _F, C.POINTER(Noise), _P],
     "bdl_ensemble": [_P, _U32, _U32, _U32, _F, _F, _I32, _P, _P],
     "bdl_ce_err": [_P, _P, _U32, _U32, _P, _P, _P],
     "bdl_lse_accum": [_P, _U32, _U32, _P, _P, _P],

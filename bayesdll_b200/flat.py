@@ -96,6 +96,25 @@ class FlatLayout:
             arr[i].g_dev = 0 if grad_ptrs is None else int(grad_ptrs[i])
         return arr
 
+    def dropout_run_table(self, bias_mode: str):
+        """Run table for ``ops.dropout_mix``: bias tensors carry BDL_CLS_NODROP in the 'gaussian' / 'ignore' bias modes
+        (z = ones_like(p), methods/mc_dropout.py:383-389); 'spikymix' drops biases like weights."""
+        if bias_mode not in ("gaussian", "spikymix", "ignore"):
+            raise KeyError(bias_mode)
+        runs = []
+        for s in self.segments:
+            c = _lib.CLS_NODROP if (s.is_bias and bias_mode != "spikymix") else 0
+            if runs and runs[-1][3] == c:
+                runs[-1] = (runs[-1][0], s.end, s.valid_end, c)
+            else:
+                runs.append((s.begin, s.end, s.valid_end, c))
+        if len(runs) > _lib.MAX_RUNS:
+            raise ValueError(f"{len(runs)} runs exceed BDL_MAX_RUNS={_lib.MAX_RUNS}")
+        arr = (_lib.Run * len(runs))()
+        for i, (b, e, ve, c) in enumerate(runs):
+            arr[i].begin, arr[i].end, arr[i].valid_end, arr[i].cls, arr[i].g_dev = b, e, ve, c, 0
+        return arr
+
     def per_element(self, bias_mode: str):
         """(is_head, P) fp32/bool arrays over the padded layout (padding inherits its tensor's class).
         Used by tests to drive the oracle on the same padded buffers."""

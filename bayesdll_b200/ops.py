@@ -14,7 +14,7 @@ from . import _lib
 from ._lib import ADAM_SGHMC, CSGHMC, DIV_RECIP, SGHMC, SGLD, STREAM_STEP, STREAM_USER, BdlError, Noise, Scalars
 
 __all__ = ["make_scalars", "upload_runs", "step", "make_capture", "philox_normal", "moments_avg", "moments_welford",
-           "capture_ring", "draw", "ensemble", "ce_err", "lse_accum", "lse_rescale", "lse_finalize", "calibrate", "bma_mean",
+           "capture_ring", "draw", "ensemble", "ce_err", "lse_accum", "lse_rescale", "lse_finalize", "calibrate", "bma_mean", "dropout_mix",
            "nll_temperature",
            "set_launch_config"]
 
@@ -206,7 +206,7 @@ def capture_ring(theta, ring, slot):
     _lib.check(rc, "bdl_capture_ring")
 
 
-VAR_FROM_MOMENTS, VAR_FROM_WELFORD, VAR_TINY, VAR_GIVEN = 0, 1, 2, 3
+VAR_FROM_MOMENTS, VAR_FROM_WELFORD, VAR_TINY, VAR_GIVEN, STD_GIVEN = 0, 1, 2, 3, 4
 
 
 @_on_tensor_device
@@ -216,6 +216,22 @@ def draw(mean, second, out, var_mode, scale, noise, div_mode=DIV_RECIP, center=N
                               _ptr(center, "center", allow_none=True), _ptr(out, "out"),
                               mean.numel(), int(var_mode), float(scale), div_mode, C.byref(noise), _stream())
     _lib.check(rc, "bdl_draw")
+
+
+@_on_tensor_device
+def dropout_mix(m, theta0, out, p_drop, noise, runs_dev=None, nruns=0, z_out=None):
+    """MC-Dropout draw: out = z*m + (1-z)*theta0, z = (u > p_drop) (see bdl_dropout_mix).  ``noise``: make_noise(seed=...)
+    for in-kernel Philox uniforms or make_noise(xi=u) for injected uniforms; ``runs_dev``: optional device run table
+    whose CLS_NODROP rows keep z = 1; ``z_out``: optional fp32 mask output."""
+    n = m.numel()
+    for name, t in (("theta0", theta0), ("out", out), ("z_out", z_out)):
+        if t is not None and t.numel() != n:
+            raise BdlError(f"{name}: length {t.numel()} != m length {n}")
+    rc = _lib.load().bdl_dropout_mix(_ptr(m, "m"), _ptr(theta0, "theta0"), _ptr(out, "out"), _ptr(z_out, "z_out", allow_none=True),
+                                     n, None if runs_dev is None else _ptr(runs_dev, "runs", torch.uint8), int(nruns),
+                                     float(p_drop), C.byref(noise), _stream())
+    _lib.check(rc, "bdl_dropout_mix")
+    return out
 
 
 @_on_tensor_device

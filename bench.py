@@ -382,6 +382,23 @@ def variant_rates(lay, theta, g, theta0, v, runs_dev, nruns, device, world, peak
         "achieved_gbs_per_gpu": gbs, "frac_of_measured_peak": gbs / peak, "separate_launches_ms": ms_s,
         "speedup_vs_separate": ms_s / ms_f,
         "note": "bdl_step_capture: step + running-moment update of the new theta in one pass (thin=1 steady state)"}
+    # streaming draws (12 B/param each: two reads, one write): the posterior draw of evaluate() (a9) and the per-step
+    # reparameterisation draws of the VI / MC-Dropout families
+    dr_tab, dr_n = ops.upload_runs(lay.dropout_run_table("gaussian"), device)
+    draws = [("posterior_draw", lambda i: ops.draw(mom1, mom2, buf, ops.VAR_FROM_MOMENTS, 1.25,
+                                                   ops.make_noise(seed=seed, subseq=4000 + i, stream_id=_lib.STREAM_DRAW))),
+             ("vi_reparam_draw", lambda i: ops.draw(mom1, mom2, buf, ops.STD_GIVEN, 1.0,
+                                                    ops.make_noise(seed=seed, subseq=5000 + i, stream_id=_lib.STREAM_DRAW))),
+             ("mc_dropout_mix_bias_gaussian", lambda i: ops.dropout_mix(mom1, theta0, buf, 0.1, ops.make_noise(
+                 seed=seed, subseq=6000 + i, stream_id=_lib.STREAM_DRAW), dr_tab, dr_n)),
+             ("mc_dropout_mix_spikymix", lambda i: ops.dropout_mix(mom1, theta0, buf, 0.1, ops.make_noise(
+                 seed=seed, subseq=7000 + i, stream_id=_lib.STREAM_DRAW)))]
+    for name, fn in draws:
+        ms = timed(fn)
+        gbs = 12 * n_dense / (ms * 1e-3) / 1e9
+        out[name] = {"params_per_s": world * n_dense / (ms * 1e-3), "ms_per_launch": ms, "bytes_per_param": 12,
+                     "achieved_gbs_per_gpu": gbs, "frac_of_measured_peak": gbs / peak}
+    out["mc_dropout_mix_bias_gaussian"]["runs"] = dr_n
     # the shape Runner.train() actually launches: one run per tensor, each row pointing at that tensor's own
     # (separately allocated) autograd gradient -- no flat gradient buffer, no gather pass
     del m, s2, buf

@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define BDL_ABI_VERSION 4
+#define BDL_ABI_VERSION 5
 
 typedef enum {
     BDL_OK = 0,
@@ -53,6 +53,7 @@ typedef enum {
 #define BDL_CLS_HEAD 1u    /* readout_name in pname  -> lr_head / head noise scale (methods/sghmc.py:485-488) */
 #define BDL_CLS_PRIOR 2u   /* prior pull enabled; cleared for 'bias' in pname && bias=='uninformative' (:494) */
 #define BDL_CLS_SKIP 4u    /* p.grad is None: the reference leaves such a tensor untouched (:484)            */
+#define BDL_CLS_NODROP 8u  /* bdl_dropout_mix only: z = 1 for this run (bias tensors, mc_dropout.py:383-389)        */
 
 /* A run = a contiguous range of the padded flat layout whose elements share one class
  * (and, optionally, one gradient tensor).  Runs are sorted, contiguous and cover [0, n). */
@@ -194,11 +195,22 @@ int bdl_set_ring_config(int chunks_per_cta);
  *   var_mode 1: var = max(second / scale, 1e-12)              scale = fp32(n-1)    (csghmc.py:451-459)
  *   var_mode 2: var = 1e-12                                   (csghmc.py:458)
  *   var_mode 3: second already holds the variance
+ *   var_mode 4: second holds a standard deviation s_: theta = mean + max(s_, 1e-8) * eps -- the VI reparameterisation
+ *               draw (methods/vi.py:402-406), no square root
  *   center_dev (optional): draw around this vector instead of `mean` while the variance still comes from
  *   (mean, second) -- cSGLD's cycle likelihoods perturb the *current* theta with the cycle's variance
  *   (methods/csgld.py:518-541).  NULL -> centre = mean. */
 int bdl_draw(const float* mean_dev, const float* second_dev, const float* center_dev, float* theta_out_dev, uint64_t n,
              int var_mode, float scale, int div_mode, const bdl_noise* noise, void* stream);
+
+/* (section 8f row 4) MC-Dropout reparameterisation draw (methods/mc_dropout.py:378-394):
+ *   z = (u > p_drop) ? 1 : 0 with u ~ U[0,1) ;  theta_out = z*m + (1-z)*theta0 ; runs carrying BDL_CLS_NODROP keep z = 1.
+ *   noise->xi_dev == NULL: in-kernel Philox uniforms (same counter layout as the Gaussian stream, 24 bits per value);
+ *   noise->xi_dev != NULL: injected uniforms in the padded flat layout (parity mode: replaces torch.rand_like).
+ *   z_out_dev (optional): the mask as fp32 0/1, which the reference keeps for its gradient (mc_dropout.py:393-394).
+ *   runs_dev / nruns: DEVICE run table (only the BDL_CLS_NODROP bit is read); NULL / 0 = dropout everywhere. */
+int bdl_dropout_mix(const float* m_dev, const float* theta0_dev, float* theta_out_dev, float* z_out_dev, uint64_t n,
+                    const bdl_run* runs_dev, uint32_t nruns, float p_drop, const bdl_noise* noise, void* stream);
 
 /* (a10) Ensemble average for one test batch (methods/sgld.py:283-305):
  *   logits_all [B,K,S] fp32 (contiguous, S fastest, i.e. torch.stack(outs, 2)) ->

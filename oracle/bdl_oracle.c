@@ -220,6 +220,7 @@ int bdl_oracle_draw(const float* mean, const float* second, const float* center,
             else if (var_mode == 1) var = fmaxf(div_s(second[i], scale, inv, div_mode), 1e-12f);
             else if (var_mode == 2) var = 1e-12f;
             else var = second[i];
+            if (var_mode == 4) { out[i] = (center ? center[i] : mean[i]) + (fmaxf(second[i], 1e-8f) * z[k]); continue; } /* vi.py:402-406 */
             out[i] = (center ? center[i] : mean[i]) + (sqrtf(var) * z[k]);
         }
     }

@@ -261,6 +261,64 @@ def make_attribute_inventory():
     print(f"wrote {path}")
 
 
+def make_reparam_draw_goldens():
+    """The per-step reparameterisation draws of the reference's own ``vi.Model.forward`` and ``mc_dropout.Model.forward``
+    (eval_grad=0), with ``torch.randn_like`` / ``torch.rand_like`` served from recorded tapes: the workhorse network's
+    parameters after the call are the draw."""
+    import contextlib
+    from oracle import make_golden_runner as mgr
+    rng = np.random.default_rng(31)
+    x = torch.from_numpy(rng.standard_normal((mgr.BATCH, 1, 4, 4)).astype(np.float32))
+    y = torch.from_numpy(rng.integers(0, mgr.K_CLASSES, mgr.BATCH).astype(np.int64))
+    crit = torch.nn.CrossEntropyLoss()
+    names = [n for n, _ in mgr.InjectNet(0).named_parameters()]
+    sizes = [p.numel() for _, p in mgr.InjectNet(0).named_parameters()]
+    out = dict(names=np.array(names), sizes=np.array(sizes))
+    flatten = lambda mod: torch.cat([p.detach().reshape(-1) for p in mod.parameters()]).numpy().copy()
+
+    vi = refshim.load("methods.vi")
+    net, net0 = mgr.InjectNet(41), mgr.InjectNet(42)
+    model = vi.Model(net, ND=12)
+    with torch.no_grad():
+        for p in model.s_.parameters():                      # spread around the clamp: negatives, < 1e-8, ordinary values
+            vals = rng.choice([-1e-3, 0.0, 3e-9, 1e-8, 2e-8, 1e-6, 1e-3, 0.05], size=tuple(p.shape)).astype(np.float32)
+            p.copy_(torch.from_numpy(vals) * torch.from_numpy(rng.uniform(0.5, 1.5, tuple(p.shape)).astype(np.float32)))
+    tape = rng.standard_normal(sum(sizes)).astype(np.float32)
+    net.eval()
+    with refshim.injected_noise(tape) as tp:
+        model.forward(x, y, net, net0, crit, eval_grad=0)
+        assert tp.pos == tape.size
+    out.update(vi_m=flatten(model.m), vi_s=flatten(model.s_), vi_eps=tape, vi_theta=flatten(net))
+
+    mcd = refshim.load("methods.mc_dropout")
+
+    @contextlib.contextmanager
+    def injected_uniforms(flat):
+        t = refshim.NoiseTape(flat)
+        orig = torch.rand_like
+        torch.rand_like = t
+        try:
+            yield t
+        finally:
+            torch.rand_like = orig
+    for mode in ("gaussian", "spikymix", "ignore"):
+        net, net0 = mgr.InjectNet(51), mgr.InjectNet(52)
+        model = mcd.Model(net, ND=12, p_drop=0.3, bias=mode)
+        with torch.no_grad():
+            for p in model.m.parameters():
+                p.add_(torch.from_numpy(rng.standard_normal(tuple(p.shape)).astype(np.float32)))
+        u = rng.random(sum(sizes)).astype(np.float32)
+        u[::97] = np.float32(0.3)                            # exactly p_drop: '>' must not keep these
+        net.eval()
+        with injected_uniforms(u) as tp:
+            model.forward(x, y, net, net0, crit, eval_grad=0)
+            used = tp.pos
+        out.update({f"mcd_{mode}_m": flatten(model.m), f"mcd_{mode}_theta0": flatten(net0), f"mcd_{mode}_u": u[:used],
+                    f"mcd_{mode}_used": used, f"mcd_{mode}_theta": flatten(net)})
+    out["p_drop"] = np.float32(0.3)
+    save("reparam_draws", **out)
+
+
 def make_temperature_golden():
     """calibration.find_optimal_temperature (the reference's own function, scipy BFGS) on the calibration data sets, plus
     values of its objective at fixed temperatures computed with the reference's expression (calibration.py:179-183)."""
@@ -306,3 +364,5 @@ if __name__ == "__main__":
         make_temperature_golden()
     if "attrs" in which:
         make_attribute_inventory()
+    if "reparam" in which:
+        make_reparam_draw_goldens()

@@ -394,3 +394,18 @@ def bma_mean(logits_all):
     for m in range(1, la.shape[2]):
         acc += la[:, :, m]
     return (acc / la.shape[2]).astype(f32)
+
+
+# ----------------------------------------------------------------------------------------------
+# (8f row 4) per-step reparameterisation draws of the VI and MC-Dropout families
+# ----------------------------------------------------------------------------------------------
+def vi_sample(m, s_, eps):
+    """methods/vi.py:402-406: ``p.copy_(p_m + p_s_.clamp(min=1e-8) * eps)``."""
+    return (np.asarray(m, f32) + np.maximum(np.asarray(s_, f32), f32(1e-8)) * np.asarray(eps, f32)).astype(f32)
+
+
+def mc_dropout_mix(m, theta0, u, p_drop, nodrop):
+    """methods/mc_dropout.py:378-394: ``z = (rand_like(p) > p_drop).float()`` (ones where ``nodrop``: bias tensors in the
+    'gaussian' / 'ignore' modes), ``p.copy_(z*p_m + (1-z)*p0)``.  Returns (theta, z)."""
+    z = np.where(np.asarray(nodrop, bool) | (np.asarray(u, f32) > f32(p_drop)), f32(1), f32(0)).astype(f32)
+    return (z * np.asarray(m, f32) + (f32(1) - z) * np.asarray(theta0, f32)).astype(f32), z

@@ -108,3 +108,21 @@ def replay_step_case(name, impl, chained=True, div_mode="true"):
                 continue
             pairs[k].append((np.asarray(st[k]).copy(), z[k][t]))
     return pairs
+
+
+def mc_dropout_dense_inputs(z, mode):
+    """(u, nodrop) over the dense parameter vector for one MC-Dropout golden: the reference's uniform tape holds values
+    only for the tensors it drops, in order; tensors kept whole (bias, modes 'gaussian' / 'ignore') get u = 0."""
+    names, sizes = z["names"].tolist(), z["sizes"].tolist()
+    tape = z[f"mcd_{mode}_u"]
+    u, nodrop, pos = [], [], 0
+    for name, k in zip(names, sizes):
+        keep = "bias" in name and mode != "spikymix"
+        if keep:
+            u.append(np.zeros(k, np.float32))
+        else:
+            u.append(tape[pos:pos + k])
+            pos += k
+        nodrop.append(np.full(k, keep))
+    assert pos == int(z[f"mcd_{mode}_used"]) == tape.size
+    return np.concatenate(u).astype(np.float32), np.concatenate(nodrop)

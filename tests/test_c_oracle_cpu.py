@@ -123,3 +123,6 @@ def test_c_oracle_moments_and_draw_vs_numpy():
         assert np.array_equal(out, so.posterior_draw(m1, so.variance_from_moments(m1, m2, 5 / 4), eps))
         co.draw(mean, M2, out, 1, 6.0, div, nz)
         assert np.array_equal(out, so.posterior_draw(mean, so.variance_from_welford(M2, 7, div_name), eps))
+        s_ = (M2 * np.float32(1e-8) - np.float32(5e-9)).astype(np.float32)          # straddles the 1e-8 clamp
+        co.draw(mean, s_, out, 4, 1.0, div, nz)
+        assert np.array_equal(out, so.vi_sample(mean, s_, eps))

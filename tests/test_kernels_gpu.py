@@ -234,3 +234,115 @@ def test_temperature_objective_and_optimum(cuda_device, tag):
     e1 = calibration.analyze(labels, logits, 15, None, temperature=Topt)
     e2 = calibration.analyze(labels, logits, 15, None, temperature=t[f"{tag}_Topt"])
     assert all(abs(x - y) <= 1e-5 * max(1.0, abs(y)) for x, y in zip(e1, e2))
+
+
+# ---- (8f row 4) per-step reparameterisation draws of the VI / MC-Dropout families --------------------------------
+def _reparam_layout(z):
+    from bayesdll_b200.flat import FlatLayout
+    return FlatLayout([(nm, (int(k),)) for nm, k in zip(z["names"].tolist(), z["sizes"].tolist())], "classifier")
+
+
+def test_vi_reparam_draw_matches_reference_golden(cuda_device):
+    from bayesdll_b200 import ops
+    z = np.load(gu.golden_path("reparam_draws"), allow_pickle=False)
+    lay = _reparam_layout(z)
+    d = lambda a: torch.from_numpy(lay.padded_numpy(a)).to(cuda_device)
+    out = torch.empty(lay.n_padded, device=cuda_device)
+    ops.draw(d(z["vi_m"]), d(z["vi_s"]), out, ops.STD_GIVEN, 1.0, ops.make_noise(xi=d(z["vi_eps"])))
+    assert bits_equal(lay.dense_numpy(out.cpu().numpy()), z["vi_theta"])
+
+
+@pytest.mark.parametrize("n", [4, 100_004, 3_000_000])
+def test_vi_reparam_draw_bit_exact_and_philox_equivalent(cuda_device, n):
+    from bayesdll_b200 import _lib, ops
+    rng = np.random.default_rng(n + 5)
+    m = rng.standard_normal(n).astype(np.float32)
+    s_ = (rng.standard_normal(n) * 1e-2).astype(np.float32)
+    s_[::5] = rng.choice([-1.0, 0.0, 5e-9, 1e-8, 2e-8], size=s_[::5].shape).astype(np.float32)
+    eps = rng.standard_normal(n).astype(np.float32)
+    d = lambda a: torch.from_numpy(a).to(cuda_device)
+    out = torch.empty(n, device=cuda_device)
+    ops.draw(d(m), d(s_), out, ops.STD_GIVEN, 1.0, ops.make_noise(xi=d(eps)))
+    assert bits_equal(out.cpu().numpy(), so.vi_sample(m, s_, eps))
+    xi = torch.empty(n, device=cuda_device)
+    ops.philox_normal(xi, 5, _lib.STREAM_DRAW, 99)
+    a, b = torch.empty(n, device=cuda_device), torch.empty(n, device=cuda_device)
+    ops.draw(d(m), d(s_), a, ops.STD_GIVEN, 1.0, ops.make_noise(xi=xi))
+    ops.draw(d(m), d(s_), b, ops.STD_GIVEN, 1.0, ops.make_noise(seed=5, subseq=99, stream_id=_lib.STREAM_DRAW))
+    assert torch.equal(a, b)
+
+
+@pytest.mark.parametrize("mode", ["gaussian", "spikymix", "ignore"])
+def test_mc_dropout_draw_matches_reference_golden(cuda_device, mode):
+    from bayesdll_b200 import ops
+    z = np.load(gu.golden_path("reparam_draws"), allow_pickle=False)
+    lay = _reparam_layout(z)
+    u_dense, _ = gu.mc_dropout_dense_inputs(z, mode)
+    d = lambda a: torch.from_numpy(lay.padded_numpy(a)).to(cuda_device)
+    runs_dev, nruns = ops.upload_runs(lay.dropout_run_table(mode), cuda_device)
+    out, mask = torch.empty(lay.n_padded, device=cuda_device), torch.empty(lay.n_padded, device=cuda_device)
+    ops.dropout_mix(d(z[f"mcd_{mode}_m"]), d(z[f"mcd_{mode}_theta0"]), out, float(z["p_drop"]), ops.make_noise(xi=d(u_dense)),
+                    runs_dev, nruns, z_out=mask)
+    assert bits_equal(lay.dense_numpy(out.cpu().numpy()), z[f"mcd_{mode}_theta"])
+    out2 = torch.empty_like(out)                                                    # without the mask output
+    ops.dropout_mix(d(z[f"mcd_{mode}_m"]), d(z[f"mcd_{mode}_theta0"]), out2, float(z["p_drop"]), ops.make_noise(xi=d(u_dense)),
+                    runs_dev, nruns)
+    assert torch.equal(out, out2)
+    mk = mask.cpu().numpy()
+    assert set(np.unique(mk).tolist()) <= {0.0, 1.0}
+    for sg in lay.segments:
+        if sg.is_bias and mode != "spikymix":
+            assert np.all(mk[sg.begin:sg.begin + sg.numel] == 1.0)
+
+
+@pytest.mark.parametrize("n", [4, 40_004, 4_000_000])
+def test_mc_dropout_draw_bit_exact_and_philox_statistics(cuda_device, n):
+    from bayesdll_b200 import ops
+    from bayesdll_b200.flat import FlatLayout
+    rng = np.random.default_rng(n + 9)
+    k = n // 4
+    lay = FlatLayout([("a.weight", (k,)), ("a.bias", (k,)), ("b.weight", (k,)), ("b.bias", (n - 3 * k,))], "b")
+    n = lay.n_padded
+    m, th0, u = (rng.standard_normal(n).astype(np.float32), rng.standard_normal(n).astype(np.float32),
+                 rng.random(n).astype(np.float32))
+    u[::11] = np.float32(0.25)
+    d = lambda a: torch.from_numpy(a).to(cuda_device)
+    for mode in ("gaussian", "spikymix"):
+        nodrop = np.zeros(n, bool)
+        for sg in lay.segments:
+            nodrop[sg.begin:sg.end] = sg.is_bias and mode != "spikymix"
+        runs_dev, nruns = ops.upload_runs(lay.dropout_run_table(mode), cuda_device)
+        out, mask = torch.empty(n, device=cuda_device), torch.empty(n, device=cuda_device)
+        ops.dropout_mix(d(m), d(th0), out, 0.25, ops.make_noise(xi=d(u)), runs_dev, nruns, z_out=mask)
+        want, wz = so.mc_dropout_mix(m, th0, u, 0.25, nodrop)
+        assert bits_equal(out.cpu().numpy(), want) and bits_equal(mask.cpu().numpy(), wz)
+    # no run table = dropout everywhere
+    ops.dropout_mix(d(m), d(th0), out, 0.25, ops.make_noise(xi=d(u)), z_out=mask)
+    want, wz = so.mc_dropout_mix(m, th0, u, 0.25, np.zeros(n, bool))
+    assert bits_equal(out.cpu().numpy(), want) and bits_equal(mask.cpu().numpy(), wz)
+    # in-kernel Philox uniforms: deterministic per (seed, subseq), different across subseq, keep rate 1 - p_drop
+    za, zb, zc = (torch.empty(n, device=cuda_device) for _ in range(3))
+    ops.dropout_mix(d(m), d(th0), out, 0.25, ops.make_noise(seed=3, subseq=1), z_out=za)
+    ops.dropout_mix(d(m), d(th0), out, 0.25, ops.make_noise(seed=3, subseq=1), z_out=zb)
+    ops.dropout_mix(d(m), d(th0), out, 0.25, ops.make_noise(seed=3, subseq=2), z_out=zc)
+    assert torch.equal(za, zb)
+    assert torch.equal(out, torch.where(zc > 0, d(m) + 0.0 * d(th0), 0.0 * d(m) + d(th0)))
+    if n >= 40_000:
+        assert not torch.equal(za, zc)
+        keep = za.double().mean().item()
+        assert abs(keep - 0.75) < 5 * np.sqrt(0.75 * 0.25 / n)
+        agree = (za == zc).double().mean().item()                                    # independent masks: 0.75^2 + 0.25^2
+        assert abs(agree - 0.625) < 5 * np.sqrt(0.625 * 0.375 / n)
+    # p_drop = 0 keeps everything (u > 0 fails only for u == 0: probability 2^-24 per element, handled like the reference)
+    ops.dropout_mix(d(m), d(th0), out, 1.0, ops.make_noise(seed=3, subseq=1), z_out=za)
+    assert za.sum().item() == 0.0
+
+
+def test_dropout_mix_argument_errors(cuda_device):
+    from bayesdll_b200 import ops
+    from bayesdll_b200._lib import BdlError
+    a = torch.zeros(8, device=cuda_device)
+    with pytest.raises(BdlError):
+        ops.dropout_mix(a, a.clone(), torch.empty(8, device=cuda_device), 1.5, ops.make_noise(seed=1))
+    with pytest.raises(BdlError):
+        ops.dropout_mix(a, torch.zeros(12, device=cuda_device), torch.empty(8, device=cuda_device), 0.5, ops.make_noise(seed=1))

@@ -94,3 +94,26 @@ def test_bma_mean_oracle_order():
         acc = (acc + la[:, :, m]).astype(np.float32)
     assert np.array_equal(got, (acc / np.float32(9)).astype(np.float32))
     assert got.dtype == np.float32
+
+
+def _reparam_golden():
+    return np.load(gu.golden_path("reparam_draws"), allow_pickle=False)
+
+
+def test_vi_reparam_draw_oracle():
+    """(8f row 4) methods/vi.py:402-406 recorded from the reference's own vi.Model.forward."""
+    z = _reparam_golden()
+    assert (z["vi_s"] < 1e-8).any() and (z["vi_s"] > 1e-8).any()         # the clamp is exercised on both sides
+    assert _bits_equal(so.vi_sample(z["vi_m"], z["vi_s"], z["vi_eps"]), z["vi_theta"])
+
+
+@pytest.mark.parametrize("mode", ["gaussian", "spikymix", "ignore"])
+def test_mc_dropout_draw_oracle(mode):
+    """(8f row 4) methods/mc_dropout.py:378-394 recorded from the reference's own mc_dropout.Model.forward.  The
+    reference consumes uniforms only for tensors it drops (bias tensors draw none in 'gaussian' / 'ignore')."""
+    z = _reparam_golden()
+    u_dense, nodrop = gu.mc_dropout_dense_inputs(z, mode)
+    theta, mask = so.mc_dropout_mix(z[f"mcd_{mode}_m"], z[f"mcd_{mode}_theta0"], u_dense, z["p_drop"], nodrop)
+    assert _bits_equal(theta, z[f"mcd_{mode}_theta"])
+    assert 0 < (mask == 0).sum() < mask.size
+    assert np.all(mask[(u_dense == z["p_drop"]) & ~nodrop] == 0)         # u == p_drop is dropped ('>' is strict)
