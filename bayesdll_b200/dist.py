@@ -243,3 +243,81 @@ def bench_sharded_ensemble(device, rank, world, rows=512, batch=64, cycles=8, ns
             "ece": float(ece), "nll": float(nll), "loss": float(loss),
             "note": "per-sample cost = 1 draw kernel (12 B/param) + PyTorch fp32 forward of 64 images; samples re-drawn "
                     "for every batch as the reference does (Appendix B.6)"}
+
+
+# ------------------------------------------------------------------------------------------------------------
+# Model-sharded Bayesian model average (csghmc_fs)
+# ------------------------------------------------------------------------------------------------------------
+def shard_models(n_models, rank, world):
+    """Round-robin assignment of the model index j (position in the reference's sorted file list)."""
+    return [j for j in range(n_models) if j % world == rank]
+
+
+class CudaBmaBackend:
+    name = "cuda"
+
+    def ce_err(self, logits, y, loss_slot, err_slot):
+        ops.ce_err(logits, y, loss_slot, err_slot)
+
+    def bma_mean(self, logits_all, out):
+        ops.bma_mean(logits_all, out)
+
+
+def bma_evaluate(nets, n_models, loader, device, *, rank=0, world=1, group=None, backend=None):
+    """The BMA pass of ``evaluate_full_samples`` over one data set (methods/csghmc_fs.py:323-391) with the models dealt
+    round-robin to the ranks.  ``nets``: {model index j: eval-mode network} for this rank's share (``shard_models``).
+    Every batch crosses PCIe once per rank and is fed to all local models; per-model CE sums / error counts land in
+    their own slots of an [S] vector.  One exchange step: an all-gather of the local logits ``[N, K, ceil(S/world)]``
+    (543 KB per model at Pets size) and an all-reduce of the 2*S per-model statistics.  The average then runs over the
+    full ``[N, K, S]`` stack in model order on every rank, so the result is **bit-identical** to the single-rank one
+    (the fp32 running sum of csghmc_fs.py:349-351 is order-sensitive, which rules out reducing partial sums).
+    -> dict(loss_per[S], err_per[S] (sums), bma_loss_sum, bma_err_sum, n, targets, logits [N,K], logits_all [N,K,S])."""
+    backend = backend or CudaBmaBackend()
+    S = int(n_models)
+    mine = shard_models(S, rank, world)
+    assert sorted(nets) == mine, f"rank {rank}: expected models {mine}, got {sorted(nets)}"
+    s_max = (S + world - 1) // world
+    loss_m = torch.zeros(S, dtype=torch.float64, device=device)      # per-model CE sums / error counts
+    err_m = torch.zeros(S, dtype=torch.int32, device=device)
+    ys, alls = [], []
+    with torch.no_grad():
+        for x, y in loader:
+            x, y = x.to(device, non_blocking=True), y.to(device, non_blocking=True)
+            outs = []
+            for j in mine:
+                out = nets[j](x).float().contiguous()
+                backend.ce_err(out, y, loss_m[j:j + 1], err_m[j:j + 1])
+                outs.append(out)
+            if not outs:                                             # more ranks than models: shape from a forward-free stub
+                outs_t = None
+            else:
+                outs_t = torch.stack(outs, 2)
+            ys.append(y)
+            alls.append(outs_t)
+    targets = torch.cat(ys)
+    N = targets.numel()
+    if world > 1:
+        import torch.distributed as dist
+        kdim = torch.tensor([alls[0].shape[1] if alls[0] is not None else 0], dtype=torch.int64, device=device)
+        dist.all_reduce(kdim, op=dist.ReduceOp.MAX, group=group)     # ranks without a model learn K
+        K = int(kdim.item())
+        local = torch.zeros(N, K, s_max, dtype=torch.float32, device=device)
+        if mine:
+            local[:, :, :len(mine)] = torch.cat(alls)
+        gathered = torch.empty(world, N, K, s_max, dtype=torch.float32, device=device)
+        dist.all_gather_into_tensor(gathered.view(-1), local.contiguous().view(-1), group=group)   # flat: one shape rule for nccl and gloo
+        # model j = r + world * i sits at gathered[r, :, :, i]
+        la = gathered.permute(1, 2, 3, 0).reshape(N, K, s_max * world)[:, :, :S].contiguous()
+        stats = torch.cat([loss_m, err_m.double()])
+        dist.all_reduce(stats, group=group)
+        loss_m, err_m = stats[:S], stats[S:]
+    else:
+        la = torch.cat(alls).contiguous()                             # [N,K,S]
+    mean = torch.empty(la.shape[:2], dtype=torch.float32, device=device)
+    backend.bma_mean(la, mean)
+    bma_loss = torch.zeros(1, dtype=torch.float64, device=device)
+    bma_err = torch.zeros(1, dtype=torch.int32, device=device)
+    backend.ce_err(mean, targets, bma_loss, bma_err)                  # CE(mean logits) over the whole set (:365-366)
+    host = torch.cat([loss_m.double(), err_m.double(), bma_loss, bma_err.double()]).cpu().numpy()   # one D2H
+    return dict(loss_per=host[:S], err_per=host[S:2 * S], bma_loss_sum=host[2 * S], bma_err_sum=host[2 * S + 1], n=N,
+                targets=targets.cpu().numpy(), logits=mean.cpu().numpy(), logits_all=la.cpu().numpy())

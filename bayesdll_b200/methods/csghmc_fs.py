@@ -26,6 +26,7 @@ import torch
 
 from .. import ops
 from ..chain import SampleRing
+from ..dist import bma_evaluate, shard_models
 from ..flat import adopt_parameters, alloc_flat
 from ..writer import FlatBackedStateDict
 from . import csghmc as _csghmc
@@ -158,6 +159,15 @@ class Runner(_csghmc.Runner):
         return net
 
     # ---- Bayesian model average ------------------------------------------------------------------------------
+    def _bma_shard(self):
+        """(rank, world, group) of the model-sharded BMA: hparams ``bma_shard=1`` inside an initialised process group,
+        every rank calling ``evaluate_full_samples`` on the same ``log_dir``; otherwise a single rank (the reference)."""
+        import torch.distributed as dist
+        if int(float(self.args.hparams.get("bma_shard", 0))) and dist.is_available() and dist.is_initialized() \
+                and dist.get_world_size() > 1:
+            return dist.get_rank(), dist.get_world_size(), None
+        return 0, 1, None
+
     def evaluate_full_samples(self, train_loader, val_loader, test_loader, desc_prefix="Full BMA"):
         args, logger = self.args, self.logger
         dev = args.device
@@ -168,8 +178,14 @@ class Runner(_csghmc.Runner):
             return
         logger.info(f"Found {len(model_files)} model checkpoints for BMA")
 
+        rank, world, group = self._bma_shard()
+        mine = set(shard_models(len(model_files), rank, world))
         nets, used_files = [], []
-        for name in model_files:
+        for j, name in enumerate(model_files):
+            if world > 1 and j not in mine:                              # another rank's model (bma_shard=1)
+                nets.append(None)
+                used_files.append(name)
+                continue
             res = self._fs_resident.get(name)
             if res is not None:
                 nets.append(res.net)
@@ -179,8 +195,11 @@ class Runner(_csghmc.Runner):
                 nets.append(self._load_sample_from_disk(name))
                 used_files.append(name)
             except Exception as e:                                   # csghmc_fs.py:307-309
+                if world > 1:                                        # the ranks must agree on the model list
+                    raise
                 logger.error(f"Failed to load model {name}: {e}")
         S = len(nets)
+        my_nets = {j: net for j, net in enumerate(nets) if net is not None}
 
         bma_results = {}
         for dataset_name, loader in (("train", train_loader), ("val", val_loader), ("test", test_loader)):
@@ -191,38 +210,15 @@ class Runner(_csghmc.Runner):
                 logger.warning(f"No valid models found for {dataset_name} evaluation")
                 continue
             tic = time.time()
-            loss_m = torch.zeros(S, dtype=torch.float64, device=dev)      # per-model CE sums / error counts
-            err_m = torch.zeros(S, dtype=torch.int32, device=dev)
-            ys, means, alls = [], [], []
-            nb = 0
-            with torch.no_grad():
-                for x, y in loader:
-                    x, y = x.to(dev, non_blocking=True), y.to(dev, non_blocking=True)
-                    outs = []
-                    for mi, net in enumerate(nets):
-                        out = net(x).float().contiguous()
-                        ops.ce_err(out, y, loss_m[mi:mi + 1], err_m[mi:mi + 1])
-                        outs.append(out)
-                    la = torch.stack(outs, 2).contiguous()                # [B,K,S]
-                    mean = torch.empty(la.shape[:2], dtype=torch.float32, device=dev)
-                    ops.bma_mean(la, mean)
-                    ys.append(y)
-                    means.append(mean)
-                    alls.append(la)
-                    nb += len(y)
-            targets_d = torch.cat(ys)
-            bma_logits_d = torch.cat(means).contiguous()
-            bma_stats = torch.zeros(1, dtype=torch.float64, device=dev), torch.zeros(1, dtype=torch.int32, device=dev)
-            ops.ce_err(bma_logits_d, targets_d, *bma_stats)              # CE(mean logits) over the whole set (:365-366)
-            host = torch.cat([loss_m, err_m.double(), bma_stats[0], bma_stats[1].double()]).cpu().numpy()   # one D2H
-            loss_per, err_per = host[:S], host[S:2 * S]
+            r = bma_evaluate(my_nets, S, loader, dev, rank=rank, world=world, group=group)
+            nb, loss_per, err_per = r["n"], r["loss_per"], r["err_per"]
             for name, ls, er in zip(used_files, loss_per, err_per):
                 logger.info(f"Model {name} on {dataset_name}: loss={ls / nb:.4f}, error={er / nb:.4f}")
-            bma_loss, bma_error = host[2 * S] / nb, host[2 * S + 1] / nb
+            bma_loss, bma_error = r["bma_loss_sum"] / nb, r["bma_err_sum"] / nb
             bma_results[dataset_name] = {
                 "loss": bma_loss, "error": bma_error, "num_models": S,
-                "targets": targets_d.cpu().numpy(), "logits": bma_logits_d.cpu().numpy(),
-                "logits_all": torch.cat(alls).cpu().numpy(),              # [samples, classes, models]
+                "targets": r["targets"], "logits": r["logits"],
+                "logits_all": r["logits_all"],                            # [samples, classes, models]
                 # reference quirk kept: total_samples is accumulated once per model, so these two are divided by
                 # nb * S * S, not nb * S (csghmc_fs.py:356-358, 385-386)
                 "individual_avg_loss": loss_per.sum() / (nb * S * S),
@@ -234,6 +230,8 @@ class Runner(_csghmc.Runner):
                         f"loss={bma_results[dataset_name]['individual_avg_loss']:.4f}, "
                         f"error={bma_results[dataset_name]['individual_avg_error']:.4f}")
 
+        if rank != 0:                                                     # sharded BMA: rank 0 owns the files
+            return bma_results
         results_path = os.path.join(args.log_dir, "bma_evaluation_results.pkl")
         with open(results_path, "wb") as f:
             pickle.dump(bma_results, f)

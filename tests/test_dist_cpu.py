@@ -141,3 +141,77 @@ def test_sharded_ensemble_world2_equals_world1():
         assert abs(ece - ece1) < 1e-6 and abs(mce - mce1) < 1e-6 and abs(nll - nll1) < 1e-6
     # both ranks hold identical results
     np.testing.assert_array_equal(res[0][4], res[1][4])
+
+
+# ---- model-sharded Bayesian model average (csghmc_fs) ---------------------------------------------------------------
+class OracleBmaBackend:
+    name = "oracle"
+
+    def ce_err(self, logits, y, loss_slot, err_slot):
+        loss_slot += torch.nn.functional.cross_entropy(logits, y, reduction="sum").double()
+        err_slot += (logits.argmax(1) != y).sum().to(torch.int32)
+
+    def bma_mean(self, logits_all, out):
+        out.copy_(torch.from_numpy(so.bma_mean(logits_all.numpy())))
+
+
+def _bma_problem(S):
+    nets = []
+    for j in range(S):
+        net = TinyNet()
+        with torch.no_grad():
+            gen = torch.Generator().manual_seed(100 + j)
+            for p in net.parameters():
+                p.add_(0.3 * torch.randn(p.shape, generator=gen))
+        nets.append(net.eval())
+    gen = torch.Generator().manual_seed(2)
+    loader = [(torch.randn(b, 12, generator=gen), torch.randint(0, 5, (b,), generator=gen)) for b in (7, 7, 3)]
+    return nets, loader
+
+
+def _bma_worker(rank, world, port, S, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    import torch.distributed as dist
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    nets, loader = _bma_problem(S)
+    mine = {j: nets[j] for j in bdist.shard_models(S, rank, world)}
+    r = bdist.bma_evaluate(mine, S, loader, torch.device("cpu"), rank=rank, world=world, backend=OracleBmaBackend())
+    q.put((rank, r))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_model_shard_assignment_is_a_partition():
+    for world in (1, 2, 3, 8):
+        for S in (1, 2, 5, 16):
+            assert sorted(sum((bdist.shard_models(S, r, world) for r in range(world)), [])) == list(range(S))
+
+
+@pytest.mark.parametrize("S", [5, 1])
+def test_sharded_bma_world2_is_bit_identical_to_world1(S):
+    """S = 5: ranks hold 3 and 2 models; S = 1: rank 1 holds none and learns the class count from the exchange."""
+    nets, loader = _bma_problem(S)
+    one = bdist.bma_evaluate(dict(enumerate(nets)), S, loader, torch.device("cpu"), backend=OracleBmaBackend())
+    # the single-rank result against the reference's statements (csghmc_fs.py:349-377)
+    with torch.no_grad():
+        la = torch.stack([torch.cat([net(x) for x, _ in loader]) for net in nets], 2).numpy()
+    y = torch.cat([y for _, y in loader])
+    assert np.array_equal(one["logits_all"], la) and np.array_equal(one["logits"], so.bma_mean(la))
+    assert one["n"] == 17 and np.array_equal(one["targets"], y.numpy())
+    want_loss = torch.nn.functional.cross_entropy(torch.from_numpy(so.bma_mean(la)), y, reduction="sum").item()
+    assert abs(one["bma_loss_sum"] - want_loss) < 1e-5
+
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_bma_worker, args=(r, 2, port, S, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted((q.get(timeout=120) for _ in range(2)), key=lambda t: t[0])
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for _, r in res:
+        for k in ("logits_all", "logits", "targets", "loss_per", "err_per"):
+            assert np.array_equal(r[k], one[k]), k
+        assert r["bma_loss_sum"] == one["bma_loss_sum"] and r["bma_err_sum"] == one["bma_err_sum"] and r["n"] == one["n"]
