@@ -18,6 +18,8 @@
 // Mapping: persistent grid-stride CTAs (grid = #SM * ctas_per_sm), 256 threads, each thread owns
 // kU float4 groups per tile, consecutive threads touch consecutive 16-byte groups (512 B per warp
 // per stream), all loads of a tile are issued before the first dependent instruction.
+#include <cstdlib>
+
 #include "bdl_common.cuh"
 
 namespace bdl {
@@ -41,6 +43,7 @@ struct StepParams {
     uint32_t inl_cls[kInlineRuns];
     uint32_t n4;       // one past the last float4 group to process
     uint32_t q_begin;  // first float4 group to process (0 except for chunked host-buffer steps)
+    uint32_t tpc;      // > 1: every CTA walks this many CONSECUTIVE tiles (device run tables: one table search per CTA, then a cursor)
     // scalars (already rounded to fp32 by the host)
     float lr[2], neg_lr[2], c[2];
     float oma, sig2, inv_sig2, N, inv_N, mu;
@@ -154,6 +157,7 @@ struct Uses {
 };
 
 constexpr int kDefaultUnroll = 1;
+constexpr long kDefaultTableTpc = 4;   // profiles/r01_ab_table_tpc.log: 1.169 -> 1.080 ms (SGHMC), 2.111 -> 1.970 ms (Adam-cSGHMC) at ViT-L/32 size
 
 // Resident CTAs per SM the kernel is compiled for: 16 data registers per stream per unroll step plus ~28 registers of
 // addressing / Philox state, rounded to the allocation granule, against the 64K-entry register file.
@@ -188,9 +192,15 @@ step_kernel(const StepParams p) {
     using U = Uses<kVariant>;
     constexpr uint32_t tile_groups = kT * kU;
     uint32_t tile = blockIdx.x;
-    uint32_t ntiles = 0;
+    uint32_t ntiles = 0, tile_step = 0;
     if constexpr (!kFast) {
         ntiles = (p.n4 - p.q_begin + tile_groups - 1) / tile_groups;
+        tile_step = gridDim.x;                             // capped grid: grid-stride over the tiles
+        if (p.tpc > 1) {                                   // consecutive tiles: still dispatched in address order
+            tile = blockIdx.x * p.tpc;
+            tile_step = 1;
+            if (ntiles > tile + p.tpc) ntiles = tile + p.tpc;
+        }
         if (tile >= ntiles) return;
     }
     RunCursor cur;
@@ -256,9 +266,19 @@ step_kernel(const StepParams p) {
             }
         } else {
         // run table in device memory (L1-resident after the first CTA of an SM touched it)
-        if (!have_cursor) {                                // all lanes take part (ballot); start from the warp's first group
-            const uint32_t qw = __shfl_sync(0xFFFFFFFFu, q0, 0);
-            cursor_load(cur, p, cursor_find_warp(p, qw < p.n4 ? qw : p.n4 - 1));
+        if (!have_cursor) {
+            // ONE search per CTA (warp 0, for the CTA's first group), published through shared memory.  The probes of a
+            // 32-ary search touch ~40 separate L1 sectors, more than the warp's own 24 data sectors; every thread then walks
+            // forward from the CTA's run (uniform addresses: one broadcast sector per field).  A/B against a search per
+            // warp (profiles/r01_ab_search_mode.log): equal at 64 threads, 1-2 % faster at 128 / 256.  have_cursor and
+            // the tile loop are CTA-uniform, so the barrier is safe.
+            __shared__ uint32_t run0_sh;
+            if (threadIdx.x < 32) {
+                const uint32_t r = cursor_find_warp(p, p.q_begin + tile * tile_groups);   // < n4 for every launched tile
+                if (threadIdx.x == 0) run0_sh = r;
+            }
+            __syncthreads();
+            cursor_load(cur, p, run0_sh);
             have_cursor = true;
         }
 #pragma unroll
@@ -337,7 +357,7 @@ step_kernel(const StepParams p) {
         if constexpr (kFast) {
             break;
         } else {
-            tile += gridDim.x;
+            tile += tile_step;
             if (tile >= ntiles) break;
         }
     }
@@ -350,6 +370,16 @@ static int g_ctas_per_sm = 0;   // 0 = one tile per CTA (default); > 0 = persist
 static int g_unroll = 0;        // 0 = default
 static int g_threads = 0;       // 0 = default
 
+// Tiles per CTA for launches whose run table carries gradient pointers (experiment knob: BDL_TABLE_TPC, read once).
+static uint32_t table_tiles_per_cta() {
+    static const uint32_t v = [] {
+        const char* e = getenv("BDL_TABLE_TPC");
+        const long x = e ? atol(e) : kDefaultTableTpc;
+        return static_cast<uint32_t>(x < 1 ? 1 : (x > 4096 ? 4096 : x));
+    }();
+    return v;
+}
+
 template <int kVariant, bool kHasBuf, bool kPhilox, int kDiv, int kU, int kT, int kCap = 0, bool kAllowFast = false>
 static int launch_shape(const StepParams& p, cudaStream_t st) {
     constexpr uint32_t tile_groups = kT * kU;
@@ -361,6 +391,17 @@ static int launch_shape(const StepParams& p, cudaStream_t st) {
     }
     if (grid > 0x7FFFFFFFull) grid = 0x7FFFFFFFull;
     if (grid == 0) return BDL_OK;
+    if (grid == ntiles && p.inl_n == 0 && !p.flat_g && table_tiles_per_cta() > 1) {
+        // run table with per-tensor gradient pointers (the training-loop launch): the gradient load depends on the table
+        // lookup.  A CTA that walks a few consecutive tiles pays the search and that late first load once; later tiles
+        // follow the register cursor.  Tables without gradient pointers (bias=uninformative) lose nothing to the lookup
+        // and stay at one tile per CTA (1.044 vs 1.053 ms).
+        StepParams pc = p;
+        pc.tpc = table_tiles_per_cta();
+        grid = (ntiles + pc.tpc - 1) / pc.tpc;
+        step_kernel<kVariant, kHasBuf, kPhilox, kDiv, kU, kT, kCap><<<static_cast<uint32_t>(grid), kT, 0, st>>>(pc);
+        return check_cuda(cudaGetLastError(), "step_kernel launch");
+    }
     if constexpr (kAllowFast) {
         if (grid == ntiles && p.inl_n == 2 && p.flat_g) {
             step_kernel<kVariant, kHasBuf, kPhilox, kDiv, kU, kT, kCap, true><<<static_cast<uint32_t>(grid), kT, 0, st>>>(p);

@@ -19,6 +19,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--rounds", type=int, default=3)
+    ap.add_argument("--only", default=None, help="regex on the case name")
     a = ap.parse_args()
     dev = torch.device("cuda:0")
     named, readout = shapes.named_shapes("vit_l_32")
@@ -32,9 +33,30 @@ def main():
     cases = [("SGHMC", _lib.SGHMC, 24, 0.0, "informative"), ("SGLD mu=0.5", _lib.SGLD, 24, 0.5, "informative"),
              ("SGLD mu=0", _lib.SGLD, 16, 0.0, "informative"), ("cSGHMC", _lib.CSGHMC, 20, 0.0, "informative"),
              ("Adam-cSGHMC", _lib.ADAM_CSGHMC, 40, 0.0, "informative"),
-             ("SGHMC uninformative (295 runs)", _lib.SGHMC, 24, 0.0, "uninformative")]
+             ("SGHMC uninformative (295 runs)", _lib.SGHMC, 24, 0.0, "uninformative"),
+             ("SGHMC per-tensor grad pointers (296 runs)", _lib.SGHMC, 24, 0.0, "pointers"),
+             ("Adam-cSGHMC per-tensor grad pointers", _lib.ADAM_CSGHMC, 40, 0.0, "pointers"),
+             ("SGHMC pointers into the flat buffer (placement control)", _lib.SGHMC, 24, 0.0, "flatptr"),
+             ("SGHMC pointers into one packed buffer (512 B pitch)", _lib.SGHMC, 24, 0.0, "packedptr")]
+    # the training-loop launch: one run per tensor, each row carrying the address of that tensor's own gradient
+    grads = [torch.randn(sg.numel, device=dev, generator=gen) * 1e-2 for sg in lay.segments]
+    runs["pointers"] = ops.upload_runs(lay.run_table("informative", grad_ptrs=[t.data_ptr() for t in grads]), dev)
+    # controls: the same dependent gradient load, but the gradients sit (a) at their flat-layout offsets, (b) packed
+    # back to back in one allocation at the caching allocator's 512 B pitch
+    flat_views = lay.flat_views(buf["g"])
+    runs["flatptr"] = ops.upload_runs(lay.run_table("informative", grad_ptrs=[t.data_ptr() for t in flat_views]), dev)
+    pitch = lambda k: (k * 4 + 511) // 512 * 512
+    packed = torch.randn(sum(pitch(sg.numel) for sg in lay.segments) // 4, device=dev, generator=gen) * 1e-2
+    offs, o = [], 0
+    for sg in lay.segments:
+        offs.append(packed.data_ptr() + o)
+        o += pitch(sg.numel)
+    runs["packedptr"] = ops.upload_runs(lay.run_table("informative", grad_ptrs=offs), dev)
     step_no = [0]
+    import re
     for name, variant, bpp, mu, bias in cases:
+        if a.only and not re.search(a.only, name):
+            continue
         adam = variant == _lib.ADAM_CSGHMC
         sc = ops.make_scalars(variant, lr_body=1e-4, lr_head=1e-2, ND=3680, Ninflate=1e3, prior_sig=1.0, nd=1.0, alpha=0.18,
                               mu=mu, t=10)
@@ -42,7 +64,7 @@ def main():
 
         def fn():
             step_no[0] += 1
-            ops.step(variant, buf["theta"], buf["g"], None if variant == _lib.CSGHMC else buf["theta0"],
+            ops.step(variant, buf["theta"], None if bias.endswith("ptr") or bias == "pointers" else buf["g"], None if variant == _lib.CSGHMC else buf["theta0"],
                      None if variant == _lib.SGLD else buf["v"], buf["m"] if adam else None, buf["s"] if adam else None,
                      buf["b"] if mu else None, rd, nr, sc, ops.make_noise(seed=42, subseq=step_no[0]))
         res = {}
