@@ -18,6 +18,7 @@ import torch
 
 from . import _lib, ops
 from .flat import adopt_parameters, alloc_flat
+from .graphfwd import GraphedForward
 
 
 def chain_seed(base_seed, rank):
@@ -69,7 +70,7 @@ class ShardedEnsemble:
     ``mixture=True``: weighted sum of per-cycle log-mean-softmax (the reference's log-space GMM, Appendix B.5)."""
 
     def __init__(self, net, layout, components, nst, seed, *, mixture, eval_id=1, rank=0, world=1, group=None,
-                 div_mode=_lib.DIV_RECIP, backend=None):
+                 div_mode=_lib.DIV_RECIP, backend=None, graph=True):
         if nst < 1:
             raise ValueError("sample sharding needs nst >= 1")
         self.layout, self.components, self.nst, self.seed = layout, components, int(nst), int(seed)
@@ -80,6 +81,7 @@ class ShardedEnsemble:
         dev = next(net.parameters()).device
         self.flat = alloc_flat(layout.n_padded, dev) if dev.type == "cuda" else torch.zeros(layout.n_padded)
         adopt_parameters(self.net, layout, self.flat)
+        self.forward = GraphedForward(self.net, enabled=graph and dev.type == "cuda")   # stable pointers: replay as a CUDA graph
         self.mine = shard_samples(len(components), self.nst, rank, world)
 
     def _all_reduce(self, t, op="sum"):
@@ -101,7 +103,7 @@ class ShardedEnsemble:
                     comp = self.components[ci]
                     self.backend.draw(comp, self.flat, self.seed, _pack_subseq(self.eval_id, b_idx, comp["cycle"], smp),
                                       self.div_mode)
-                    out = self.net(x).float().contiguous()
+                    out = self.forward(x).float().contiguous()
                     if m is None:
                         m = torch.full((C,) + tuple(out.shape), float("-inf"), dtype=torch.float32, device=dev)
                         s = torch.zeros_like(m)

@@ -27,6 +27,7 @@ from tqdm import tqdm
 from .. import _lib, calibration, ops
 from ..chain import ChainState, SampleRing
 from ..flat import adopt_parameters, alloc_flat
+from ..graphfwd import GraphedForward
 from ..writer import AsyncWriter, FlatBackedStateDict
 from .cyclical import CyclicalSGMCMC
 
@@ -175,13 +176,15 @@ class _EvalNet:
     """A copy of the live network whose parameters are views of one flat buffer, so a posterior sample is
     materialised by ONE kernel (bdl_draw) instead of ``deepcopy(net)`` + 5 eager kernels per tensor."""
 
-    def __init__(self, net, layout):
+    def __init__(self, net, layout, graph=True):
         self.net = copy.deepcopy(net)                     # inherits BatchNorm running stats (Appendix B.12)
         self.net.eval()
         self.flat = alloc_flat(layout.n_padded, next(net.parameters()).device)
         adopt_parameters(self.net, layout, self.flat)
         self.layout = layout
         self._xi = None
+        # every pointer of the forward pass is stable (the draw overwrites ``flat`` in place): replay it as a CUDA graph
+        self.forward = GraphedForward(self.net, enabled=graph)
 
     def load(self, flat_values):
         self.flat.copy_(flat_values)
@@ -237,6 +240,7 @@ class _RunnerCommon:
 
         # extra, optional knobs of the B200 path (absent from the reference's hparams -> defaults)
         self.noise_mode = str(hp.get("noise", "philox"))
+        self.use_graph = bool(int(float(hp.get("graph", 1))))   # evaluation forwards replayed as CUDA graphs (graphfwd.py)
         self.div_mode = {"recip": _lib.DIV_RECIP, "ieee": _lib.DIV_IEEE}[str(hp.get("div", "recip"))]
         seed = int(hp["seed"]) if "seed" in hp else getattr(args, "seed", None)
         self.seed = int(seed) if seed is not None else torch.initial_seed()
@@ -458,7 +462,7 @@ class BurninRunner(_RunnerCommon):
         args = self.args
         dev = args.device
         ch = self._chain()
-        ev = _EvalNet(self.net, ch.layout)
+        ev = _EvalNet(self.net, ch.layout, graph=self.use_graph)
         self._eval_calls += 1
         ratio = self._variance_ratio()
         loss_sum = torch.zeros(1, dtype=torch.float64, device=dev)
@@ -470,12 +474,12 @@ class BurninRunner(_RunnerCommon):
                 outs = []
                 if self.nst == 0:
                     ev.load(self._mom1)
-                    outs.append(ev.net(x))
+                    outs.append(ev.forward(x))
                 else:
                     for ii in range(self.nst):             # fresh draw for every batch (Appendix B.6)
                         ev.draw(self._mom1, self._mom2, ops.VAR_FROM_MOMENTS, ratio, self.noise_mode, self.seed,
                                 _pack_subseq(self._eval_calls, b_idx, 0, ii), self.div_mode)
-                        outs.append(ev.net(x))
+                        outs.append(ev.forward(x))
                 logits_all_ = torch.stack(outs, 2).contiguous().float()
                 logits_ = torch.empty(logits_all_.shape[:2], dtype=torch.float32, device=dev)
                 ops.ensemble(logits_all_, logits_, self.nst)
@@ -662,8 +666,10 @@ class CyclicalRunner(_RunnerCommon):
     def _before_cycle_eval(self, val_loader):
         pass
 
-    def _point_estimate(self, loader, net):
-        """Deterministic pass of ``net`` over ``loader``: (mean CE, error rate)."""
+    def _point_estimate(self, loader, net, fwd=None):
+        """Deterministic pass of ``net`` over ``loader``: (mean CE, error rate).  ``fwd``: optional callable computing
+        ``net(x)`` (the evaluation net's CUDA-graph replay)."""
+        fwd = fwd or net
         dev = self.args.device
         was_training = net.training
         net.eval()
@@ -673,7 +679,7 @@ class CyclicalRunner(_RunnerCommon):
         with torch.no_grad():
             for x, y in loader:
                 x, y = x.to(dev, non_blocking=True), y.to(dev, non_blocking=True)
-                ops.ce_err(net(x).float().contiguous(), y, loss_sum, err_cnt)
+                ops.ce_err(fwd(x).float().contiguous(), y, loss_sum, err_cnt)
                 nb += len(y)
         net.train(was_training)
         if nb == 0:
@@ -808,7 +814,7 @@ class CyclicalRunner(_RunnerCommon):
         ch = self._chain()
         gmm_weights = self.calculate_gmm_weights()
         self.logger.info(f"GMM component weights: {gmm_weights}")
-        ev = _EvalNet(self.net, ch.layout)
+        ev = _EvalNet(self.net, ch.layout, graph=self.use_graph)
         self._eval_calls += 1
         cycles = [c for c in self._cyc1 if not gmm_weights.get(c, 0.0) < 1e-10]
         specs = {c: self._cycle_variance_spec(c) for c in cycles} if self.nst > 0 else {}
@@ -824,13 +830,13 @@ class CyclicalRunner(_RunnerCommon):
                     outs = []
                     if self.nst == 0:
                         ev.load(self._cyc1[c])
-                        outs.append(ev.net(x))
+                        outs.append(ev.forward(x))
                     else:
                         second, var_mode, scale = specs[c]
                         for ii in range(self.nst):
                             ev.draw(self._cyc1[c], second, var_mode, scale, self.noise_mode, self.seed,
                                     _pack_subseq(self._eval_calls, b_idx, c, ii), self.div_mode)
-                            outs.append(ev.net(x))
+                            outs.append(ev.forward(x))
                     comp = torch.stack(outs, 2).contiguous().float()
                     comps.append(comp)
                     if batch_logits is None:
@@ -872,7 +878,7 @@ class CyclicalRunner(_RunnerCommon):
                 spec = self._cycle_variance_spec(c)
             else:
                 raise TypeError("cycle variance is None (reference: vector_to_parameters(None, ...), Appendix B.8)")
-        ev = _EvalNet(self.net, ch.layout)
+        ev = _EvalNet(self.net, ch.layout, graph=self.use_graph)
         self._eval_calls += 1
         likelihoods = []
         n_draws = max(1, self.nst)
@@ -883,7 +889,7 @@ class CyclicalRunner(_RunnerCommon):
                         _pack_subseq(self._eval_calls, 0xFFFFFF, c, sample_idx), self.div_mode, center=center)
             else:
                 ev.load(ch.theta)                        # net_sample = deepcopy(self.net), no perturbation
-            avg_loss, _ = self._point_estimate(train_loader, ev.net)
+            avg_loss, _ = self._point_estimate(train_loader, ev.net, fwd=ev.forward)
             likelihood = np.exp(-avg_loss)
             likelihoods.append(likelihood)
             self.logger.info(f"Sample {sample_idx + 1} - Full batch average loss: {avg_loss:.6f}, "

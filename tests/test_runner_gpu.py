@@ -512,3 +512,44 @@ def test_baseline_cfg1_mlp_mnist_sgld_end_to_end(cuda_device, tmp_path):
         np.testing.assert_allclose(logits, z[f"eval{i}_logits"], atol=5e-3, rtol=5e-3)
         assert abs(loss - float(z[f"eval{i}_loss"])) <= 5e-3
     assert os.path.exists(os.path.join(tmp_path, "ckpt.pt")) and os.path.exists(os.path.join(tmp_path, "logits_test.pkl"))
+
+
+@pytest.mark.parametrize("name", ["sghmc", "csgld", "csghmc"])
+def test_graphed_evaluation_forward_is_bit_identical_to_eager(cuda_device, tmp_path, name):
+    """evaluate() / full_batch_likelihoods replay the evaluation net's forward as a CUDA graph (graphfwd.py); hparams
+    graph=0 runs it eagerly.  Same kernels either way: every output must be bit-identical, and the graph must really
+    have been used."""
+    import importlib
+    from oracle import make_golden_runner as mgr
+    from bayesdll_b200.graphfwd import GraphedForward
+    z = np.load(gu.golden_path(f"runner_{name}"), allow_pickle=False)
+    method, hp, over = mgr.CASES[name]
+    seed = 500 + sorted(mgr.CASES).index(name)
+    results = {}
+    for graph in (1, 0):
+        net, net0 = mgr.InjectNet(seed, z["G"]), mgr.InjectNet(seed + 1)
+        d = tmp_path / f"g{graph}"
+        d.mkdir()
+        args = mgr.make_args(dict(hp, graph=graph), str(d), cuda_device, **over)
+        runner = importlib.import_module(f"bayesdll_b200.methods.{method}").Runner(net, net0, args, _logger())
+        runner.criterion = mgr.InjectCriterion()
+        loaders = mgr.loaders_from_arrays(z)
+        before = (GraphedForward.total_captures, GraphedForward.total_replays)
+        cwd = os.getcwd()
+        os.chdir(d)
+        try:
+            runner.train(*loaders)
+        finally:
+            os.chdir(cwd)
+        out = runner.evaluate(loaders[2])
+        used = (GraphedForward.total_captures - before[0], GraphedForward.total_replays - before[1])
+        results[graph] = (out, getattr(runner, "cycle_likelihoods", None), used)
+    (o1, l1, used1), (o0, l0, used0) = results[1], results[0]
+    assert used0 == (0, 0) and used1[0] >= 1 and used1[1] >= runner.nst
+    assert o1[0] == o0[0] and o1[1] == o0[1]
+    for a, b in zip(o1[2:], o0[2:]):
+        assert np.array_equal(np.asarray(a), np.asarray(b)) and np.asarray(a).dtype == np.asarray(b).dtype
+    if l1 is not None:                                      # cycle -> likelihoods of the nst full-batch passes
+        assert sorted(l1) == sorted(l0)
+        for c in l1:
+            assert np.array_equal(np.asarray(l1[c], np.float64), np.asarray(l0[c], np.float64))
