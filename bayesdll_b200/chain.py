@@ -63,6 +63,7 @@ class ChainState:
         self._run_dev = [torch.empty(self._run_np.nbytes, dtype=torch.uint8, device=device) for _ in range(2)]
         self._run_evt = [None, None]
         self._run_slot = 0
+        self._table_sig = None
 
     # ---- views handed to reference-style code ------------------------------------------------
     def named_views(self, flat):
@@ -114,6 +115,12 @@ class ChainState:
             base_cls = rows["cls"] & ~np.uint32(_lib.CLS_SKIP)
             rows["cls"] = np.where(skip, base_cls | np.uint32(_lib.CLS_SKIP), base_cls)
             self._had_skip = bool(n_none)
+        # unchanged table (gradients at fixed addresses, e.g. a CUDA-graph-captured backward): the copy on the device is
+        # still valid
+        sig = rows.tobytes()
+        if sig == self._table_sig:
+            return self._run_dev[self._run_slot], len(rows)
+        self._table_sig = sig
         k = self._run_slot = self._run_slot ^ 1
         if self._run_evt[k] is not None:
             self._run_evt[k].synchronize()               # the copy that last used this staging buffer has run

@@ -93,7 +93,8 @@ class FusedModel(nn.Module):
         self.t = 0
         self._chain = None
         self._opts = dict(sgd_momentum=0.0, seed=None, noise="philox", grad_mode="table", div_mode=_lib.DIV_RECIP,
-                          optimizer=None)
+                          optimizer=None, graph_train=False)
+        self._train_graphs = {}        # (net, shapes, criterion) -> eager-call count | captured graph | "eager"
 
     def configure(self, **opts):
         unknown = set(opts) - set(self._opts)
@@ -149,12 +150,69 @@ class FusedModel(nn.Module):
         chain = self._ensure_chain(net, net0)
         if self.VARIANT in (_lib.ADAM_SGHMC, _lib.ADAM_CSGHMC):
             self.t += 1                                   # methods/adam_sghmc.py:494
-        out = net(x)
-        loss = criterion(out, y)
-        net.zero_grad()                                   # grads -> None; autograd hands us fresh tensors
-        loss.backward()
+        replayed = self._graphed_fwd_bwd(x, y, net, criterion) if self._opts["graph_train"] else None
+        if replayed is not None:
+            loss, out = replayed
+        else:
+            out = net(x)
+            loss = criterion(out, y)
+            net.zero_grad()                               # grads -> None; autograd hands us fresh tensors
+            loss.backward()
         chain.update(self._scalars(lrs, Ninflate, nd, should_sample), capture=None if capture is None else capture())
         return loss.detach(), out.detach()
+
+    # ---- optional: forward + backward as ONE CUDA-graph replay (hparams graph_train=1) -----------------------------
+    def _graphed_fwd_bwd(self, x, y, net, criterion):
+        """The backbone's forward + loss + backward replayed as a CUDA graph (the fused sampler step stays a separate
+        launch: its scalars and Philox counter change every step).  Same kernels as eager, so gradients, BatchNorm
+        buffers and the loss are bit-identical; what disappears is the host's launch cost (ResNet-101, batch 16: ~1000
+        launches per step), and the gradients live at fixed addresses, so the per-tensor run table stops changing.
+        Opt-in because a capture freezes host-side control flow of ``net.forward`` / ``criterion``.  Per key the first two
+        calls run eagerly (warm-up), the third captures; a failed capture falls back to eager with one warning.
+        Returns (loss, out) clones with ``p.grad`` populated, or None when this call has to run eagerly."""
+        if not (x.is_cuda and net.training):
+            return None
+        key = (id(net), tuple(x.shape), x.dtype, tuple(y.shape), y.dtype, id(criterion))
+        ent = self._train_graphs.get(key, 0)
+        if ent == "eager":
+            return None
+        params = self._chain.params
+        if isinstance(ent, int):
+            if ent < 2:
+                self._train_graphs[key] = ent + 1
+                return None
+            try:
+                net.zero_grad()                           # gradients must be allocated inside the graph's private pool
+                sx, sy = x.clone(), y.clone()
+                graph = torch.cuda.CUDAGraph()
+                # eager steps create AccumulateGrad nodes on the caller's stream, the capture on torch's capture stream;
+                # gradients are first assignments either way (no accumulate kernel), so torch's stream-mismatch
+                # warning is moot for this module from here on
+                quiet = getattr(torch.autograd.graph, "set_warn_on_accumulate_grad_stream_mismatch", None)
+                if quiet is not None:
+                    quiet(False)
+                with torch.cuda.graph(graph, capture_error_mode="thread_local"):
+                    out = net(sx)
+                    loss = criterion(out, sy)
+                    loss.backward()
+                ent = dict(graph=graph, x=sx, y=sy, out=out, loss=loss, grads=[p.grad for p in params], net=net,
+                           criterion=criterion)
+            except Exception as e:
+                import warnings
+                warnings.warn(f"CUDA-graph capture of the training step failed ({type(e).__name__}: {e}); running eagerly")
+                torch.cuda.synchronize()
+                net.zero_grad()
+                self._train_graphs[key] = "eager"
+                return None
+            self._train_graphs[key] = ent
+        else:
+            ent["x"].copy_(x)
+            ent["y"].copy_(y)
+            for p, g in zip(params, ent["grads"]):        # after an eager step (e.g. a ragged last batch) in between
+                if p.grad is not g:
+                    p.grad = g
+        ent["graph"].replay()
+        return ent["loss"].detach().clone(), ent["out"].detach().clone()
 
     def forward(self, x, y, net, net0, criterion, lrs, Ninflate=1.0, nd=1.0, should_sample=False):
         """Same contract as the reference: returns ``(loss: float, out: detached [B,K])``; side effect: ``net`` holds the
@@ -245,7 +303,8 @@ class _RunnerCommon:
         seed = int(hp["seed"]) if "seed" in hp else getattr(args, "seed", None)
         self.seed = int(seed) if seed is not None else torch.initial_seed()
         self.model.configure(sgd_momentum=mu, seed=self.seed, noise=self.noise_mode,
-                             grad_mode=str(hp.get("grad", "table")), div_mode=self.div_mode, optimizer=self.optimizer)
+                             grad_mode=str(hp.get("grad", "table")), div_mode=self.div_mode, optimizer=self.optimizer,
+                             graph_train=bool(int(float(hp.get("graph_train", 0)))))
         self._eval_calls = 0
         # fuse=1 (default): the moment capture that follows a sampler step runs inside the step kernel; fuse=0: separate
         # launch right after it, like the reference's statement order (bit-identical either way)

@@ -526,6 +526,24 @@ def train_step_extra(device, rank, world, steps=6, batch=64, backbone="vit_l_32"
     torch.cuda.synchronize()
     dt = allmax(time.perf_counter() - t0, world, device)
     n = runner.model.chain.layout.n_dense
+    # hparams graph_train=1: forward + loss + backward replayed as one CUDA graph, then the fused step (bit-identical, tested)
+    graph_ms = None
+    try:
+        runner.model.configure(graph_train=True)
+        for _ in range(4):                                   # two eager warm-ups, the capture, one replay
+            one()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            one()
+        torch.cuda.synchronize()
+        graph_ms = allmax(time.perf_counter() - t0, world, device) / steps * 1e3
+        if not any(isinstance(v, dict) for v in runner.model._train_graphs.values()):
+            graph_ms = f"not captured: {list(runner.model._train_graphs.values())}"
+    except Exception as e:
+        graph_ms = f"failed: {type(e).__name__}: {e}"
+    runner.model.configure(graph_train=False)
+    runner.model._train_graphs.clear()
     # the same user call the reference's way: fwd + bwd, then the per-tensor eager update loop + SGD step
     # (baseline/eager_port.py restating methods/sghmc.py:482-510, :229) on the same network and GPU
     ref_ms = None
@@ -559,7 +577,7 @@ def train_step_extra(device, rank, world, steps=6, batch=64, backbone="vit_l_32"
     except Exception as e:                                   # context figure only
         ref_ms = f"failed: {type(e).__name__}: {e}"
     res = {"value": world * n * steps / dt, "unit": "params/s", "ms_per_step": dt / steps * 1e3, "steps": steps,
-           "reference_structure_ms_per_step": ref_ms,
+           "graph_train_ms_per_step": graph_ms, "reference_structure_ms_per_step": ref_ms,
            "images_per_s": world * batch * steps / dt, "h2d_bytes_per_step": x_host.numel() * 4 + y_host.numel() * 8,
            "d2h_bytes_per_step": 4, "last_loss": loss,
            "api": f"bayesdll_b200.methods.sghmc.Model.forward on torchvision {backbone}, batch {batch}, fp32 fwd/bwd in PyTorch"}

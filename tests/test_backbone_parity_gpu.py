@@ -46,14 +46,16 @@ def _assert_identical(step, runner, named, vs, ms=None, ss=None):
             assert torch.equal(m, ms[n]) and torch.equal(s, ss[n]), f"step {step}: Adam moments[{n}] differ"
 
 
-def test_cfg2_resnet101_csghmc_training_steps(cuda_device, deterministic_fp32, tmp_path):
-    """configs[1]: ResNet-101 cSGHMC, batches of 16 (methods/csghmc.py:747-778; alternating exploration / sampling)."""
+@pytest.mark.parametrize("graph_train", [0, 1])
+def test_cfg2_resnet101_csghmc_training_steps(cuda_device, deterministic_fp32, tmp_path, graph_train):
+    """configs[1]: ResNet-101 cSGHMC, batches of 16 (methods/csghmc.py:747-778; alternating exploration / sampling).
+    graph_train=1: the drop-in replays forward + backward as one CUDA graph from its third step on -- still bit-identical."""
     from oracle import make_golden_runner as mgr
     from bayesdll_b200.methods import csghmc
     dev = cuda_device
     net, net0 = mgr.cfg2_networks()
     ref = copy.deepcopy(net).to(dev)
-    args = mgr.cfg2_args(str(tmp_path), dev, extra_hp=dict(noise="torch"))
+    args = mgr.cfg2_args(str(tmp_path), dev, extra_hp=dict(noise="torch", graph_train=graph_train))
     runner = csghmc.Runner(net, net0, args, _logger())
     crit = torch.nn.CrossEntropyLoss()
     named = list(ref.named_parameters())
@@ -79,6 +81,8 @@ def test_cfg2_resnet101_csghmc_training_steps(cuda_device, deterministic_fp32, t
         for (bn, a), (_, b) in zip(runner.net.named_buffers(), ref.named_buffers()):
             assert torch.equal(a, b), f"step {t}: buffer {bn} differs"
     assert runner.model.chain.layout.n_dense == 42575973
+    captured = sum(isinstance(v, dict) for v in runner.model._train_graphs.values())
+    assert captured == (1 if graph_train else 0)
 
 
 @pytest.mark.parametrize("method", ["sghmc", "adam_csghmc"])

@@ -553,3 +553,59 @@ def test_graphed_evaluation_forward_is_bit_identical_to_eager(cuda_device, tmp_p
         assert sorted(l1) == sorted(l0)
         for c in l1:
             assert np.array_equal(np.asarray(l1[c], np.float64), np.asarray(l0[c], np.float64))
+
+
+class _ConvBN(torch.nn.Module):
+    """A real autograd network with BatchNorm buffers and dropout (host-side control flow free: capturable)."""
+    readout_name = "classifier"
+
+    def __init__(self, seed):
+        super().__init__()
+        torch.manual_seed(seed)
+        self.features = torch.nn.Sequential(torch.nn.Conv2d(3, 8, 3, padding=1), torch.nn.BatchNorm2d(8), torch.nn.ReLU(),
+                                            torch.nn.Conv2d(8, 12, 3, stride=2, padding=1), torch.nn.BatchNorm2d(12),
+                                            torch.nn.ReLU(), torch.nn.AdaptiveAvgPool2d(1), torch.nn.Flatten())
+        self.drop = torch.nn.Dropout(0.1)
+        self.classifier = torch.nn.Linear(12, 7)
+
+    def forward(self, x):
+        return self.classifier(self.drop(self.features(x)))
+
+
+@pytest.mark.parametrize("method", ["sghmc", "adam_csghmc", "sgld"])
+def test_graphed_training_step_is_bit_identical_to_eager(cuda_device, method, request):
+    """hparams graph_train=1: forward + loss + backward replayed as one CUDA graph, the fused sampler step launched
+    after it.  Parameters, sampler state, BatchNorm buffers, loss and logits must equal the eager run bit for bit at
+    every step -- including an odd-sized batch in between (runs eagerly, then the graph resumes)."""
+    import importlib
+    from bayesdll_b200 import _lib
+    mod = importlib.import_module(f"bayesdll_b200.methods.{method}")
+    gen = torch.Generator().manual_seed(5)
+    batches = [(torch.randn(6 if i == 5 else 16, 3, 12, 12, generator=gen), torch.randint(0, 7, (6 if i == 5 else 16,), generator=gen))
+               for i in range(9)]
+    runs = {}
+    # cuDNN's default backward kernels for these tiny convolutions use atomics: two EAGER runs already differ in the last
+    # bits of the gradient (1e-10; Adam's normalisation then amplifies it), so the comparison pins deterministic kernels
+    monkey = torch.backends.cudnn.deterministic
+    torch.backends.cudnn.deterministic = True
+    request.addfinalizer(lambda: setattr(torch.backends.cudnn, "deterministic", monkey))
+    for graph in (True, False):
+        net, net0 = _ConvBN(1).to(cuda_device).train(), _ConvBN(2).to(cuda_device)
+        model = mod.Model(ND=500, prior_sig=1.0, bias="informative")
+        model.configure(seed=11, graph_train=graph, sgd_momentum=0.5 if method == "sgld" else 0.0)
+        crit = torch.nn.CrossEntropyLoss()
+        torch.manual_seed(123)                                      # dropout masks come from torch's CUDA generator
+        trace = []
+        for x, y in batches:
+            loss, out = model.forward(x.to(cuda_device), y.to(cuda_device), net, net0, crit, [1e-3, 1e-2], Ninflate=10.0, nd=1.0,
+                                      **({"should_sample": True} if method == "adam_csghmc" else {}))
+            ch = model.chain
+            state = [ch.theta.clone()] + [t.clone() for t in (ch.v, ch.m, ch.s, ch.buf) if t is not None]
+            state += [b.clone() for b in net.buffers()]
+            trace.append((loss, out.clone(), state))
+        runs[graph] = (trace, dict(model._train_graphs))
+    (tg, used), (te, unused) = runs[True], runs[False]
+    assert unused == {} and sum(isinstance(v, dict) for v in used.values()) == 1     # one captured graph (the 16-row batches)
+    for (l1, o1, s1), (l0, o0, s0) in zip(tg, te):
+        assert l1 == l0 and torch.equal(o1, o0)
+        assert len(s1) == len(s0) and all(torch.equal(a, b) for a, b in zip(s1, s0))
