@@ -40,8 +40,9 @@ def needs_build():
     return any(os.path.getmtime(d) > t for d in deps if os.path.exists(d))
 
 
-def build(force=False, verbose=False):
-    if not force and not needs_build():
+def build(force=False, verbose=False, only=None):
+    """``only``: recompile just these sources and relink with the objects already in build/ (A/B builds)."""
+    if not force and not only and not needs_build():
         return OUT
     nvcc = _nvcc()
     objdir = os.path.join(HERE, "build")
@@ -54,7 +55,9 @@ def build(force=False, verbose=False):
             continue
         obj = os.path.join(objdir, src.replace(".cu", ".o"))
         objs.append(obj)
-        cmd = [nvcc, *NVCC_FLAGS, "-c", path, "-o", obj]
+        if only and src not in only and os.path.exists(obj):
+            continue
+        cmd = [nvcc, *NVCC_FLAGS, *os.environ.get("BDL_NVCC_EXTRA", "").split(), "-c", path, "-o", obj]   # e.g. -DBDL_LD_MODE=1 for A/B builds
         if verbose:
             cmd.insert(1, "-Xptxas=-v")
         procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
@@ -73,4 +76,5 @@ def build(force=False, verbose=False):
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    _only = [a for a in sys.argv[1:] if a.endswith(".cu")]
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv, only=_only or None))
