@@ -172,7 +172,8 @@ class FusedModel(nn.Module):
         Returns (loss, out) clones with ``p.grad`` populated, or None when this call has to run eagerly."""
         if not (x.is_cuda and net.training):
             return None
-        key = (id(net), tuple(x.shape), x.dtype, tuple(y.shape), y.dtype, id(criterion))
+        # the chain is part of the key: a rebuilt chain re-points every parameter at a new flat buffer
+        key = (id(net), id(self._chain), tuple(x.shape), x.dtype, tuple(y.shape), y.dtype, id(criterion))
         ent = self._train_graphs.get(key, 0)
         if ent == "eager":
             return None
@@ -196,7 +197,7 @@ class FusedModel(nn.Module):
                     loss = criterion(out, sy)
                     loss.backward()
                 ent = dict(graph=graph, x=sx, y=sy, out=out, loss=loss, grads=[p.grad for p in params], net=net,
-                           criterion=criterion)
+                           criterion=criterion, chain=self._chain)   # the references keep the ids in the key unique
             except Exception as e:
                 import warnings
                 warnings.warn(f"CUDA-graph capture of the training step failed ({type(e).__name__}: {e}); running eagerly")

@@ -338,11 +338,13 @@ def test_csgld_full_sample_uses_hbm_ring(cuda_device, tmp_path):
     assert np.array_equal(got.view(np.uint32), z["theta_final"].view(np.uint32))
 
 
+@pytest.mark.parametrize("graph_train", [0, 1])
 @pytest.mark.parametrize("name", ["real_sghmc", "real_csghmc", "real_adam_csghmc", "real_csghmc_fs"])
-def test_runner_real_network_end_to_end(cuda_device, tmp_path, name):
+def test_runner_real_network_end_to_end(cuda_device, tmp_path, name, graph_train):
     """A real conv + BatchNorm network trained through ordinary autograd: the reference on CPU (recorded) vs the drop-in
     on the GPU, both fed the same noise tape.  Gradients come from different conv implementations (1e-7-level
-    differences), so trajectories are compared with a tolerance instead of bit-for-bit."""
+    differences), so trajectories are compared with a tolerance instead of bit-for-bit.  graph_train=1: the whole
+    ``Runner.train()`` with forward + backward replayed as a CUDA graph (fused capture, raw-sample store, BMA included)."""
     import importlib
     from oracle import make_golden_runner as mgr
     from oracle import refshim
@@ -350,7 +352,8 @@ def test_runner_real_network_end_to_end(cuda_device, tmp_path, name):
     method, hp, over = mgr.REAL_CASES[name]
     seed = mgr.REAL_SEEDS[name]
     net, net0 = mgr.RealNet(seed), mgr.RealNet(seed + 1)
-    args = mgr.make_args(dict(hp, noise="torch", div="ieee"), str(tmp_path), cuda_device, lr=2e-2, lr_head=5e-2, **over)
+    args = mgr.make_args(dict(hp, noise="torch", div="ieee", graph_train=graph_train), str(tmp_path), cuda_device, lr=2e-2,
+                         lr_head=5e-2, **over)
     runner = importlib.import_module(f"bayesdll_b200.methods.{method}").Runner(net, net0, args, _logger())
     evals = []
     orig = runner.evaluate
@@ -377,6 +380,7 @@ def test_runner_real_network_end_to_end(cuda_device, tmp_path, name):
     finally:
         os.chdir(cwd)
     assert tape.pos == int(z["tape_used"])
+    assert sum(isinstance(v, dict) for v in runner.model._train_graphs.values()) == (1 if graph_train else 0)
     theta = runner._dense(runner.model.chain.theta).cpu().numpy()
     assert gu.max_rel(theta, z["theta_final"]) <= 2e-4, gu.max_rel(theta, z["theta_final"])
     if "n_bma" in z.files:
