@@ -346,3 +346,33 @@ def test_dropout_mix_argument_errors(cuda_device):
         ops.dropout_mix(a, a.clone(), torch.empty(8, device=cuda_device), 1.5, ops.make_noise(seed=1))
     with pytest.raises(BdlError):
         ops.dropout_mix(a, torch.zeros(12, device=cuda_device), torch.empty(8, device=cuda_device), 0.5, ops.make_noise(seed=1))
+
+
+def test_clamped_variance_sqrt_is_ieee_for_every_float(cuda_device):
+    """bdl_draw (modes 0-2) clamps the variance at 1e-12 and takes an IEEE square root.  Sweep EVERY fp32 bit pattern from
+    1e-12 up to and including +inf (1.41e9 values) plus a block of values below the clamp (zero, denormals, negatives)
+    against torch's CUDA sqrt, which is the correctly rounded one: bit-identical.  (Guards any future replacement of the
+    library square root, cf. the A/B in profiles/r01_ab_draw_sqrt.log.)"""
+    from bayesdll_b200 import _lib, ops
+    lo, hi = int(np.float32(1e-12).view(np.uint32)), 0x7F800000
+    chunk = 1 << 26
+    zeros, ones = torch.zeros(chunk, device=cuda_device), torch.ones(chunk, device=cuda_device)
+    out = torch.empty(chunk, device=cuda_device)
+    clamp = torch.tensor(1e-12, dtype=torch.float32, device=cuda_device)
+    n_checked = 0
+    for start in range(lo - 4096, hi + 1, chunk):
+        stop = min(start + chunk, hi + 1)
+        m = (stop - start + 3) // 4 * 4
+        x = torch.arange(start, start + m, device=cuda_device, dtype=torch.int32).clamp_(max=hi).view(torch.float32)
+        ops.draw(zeros[:m], x, out[:m], ops.VAR_FROM_WELFORD, 1.0, ops.make_noise(xi=ones[:m]), div_mode=_lib.DIV_IEEE)
+        want = torch.sqrt(torch.maximum(x, clamp))
+        assert torch.equal(out[:m], want), f"mismatch in bit range [{start:#x}, {stop:#x})"
+        n_checked += stop - start
+    assert n_checked == hi - lo + 1 + 4096
+    low = torch.tensor([0.0, -0.0, 1e-45, 1e-38, -1.0, 9.9e-13, float("-inf"), 1e-12], device=cuda_device)
+    ops.draw(zeros[:8], low, out[:8], ops.VAR_FROM_WELFORD, 1.0, ops.make_noise(xi=ones[:8]), div_mode=_lib.DIV_IEEE)
+    assert torch.equal(out[:8], torch.sqrt(clamp).expand(8))
+    # the moments path shares the function: ratio*(mom2 - mom1^2) with mom1 = 0, ratio = 1 is mom2 itself
+    x = torch.tensor([1e-12, 3.0, 1e30, float("inf")], device=cuda_device)
+    ops.draw(zeros[:4], x, out[:4], ops.VAR_FROM_MOMENTS, 1.0, ops.make_noise(xi=ones[:4]))
+    assert torch.equal(out[:4], torch.sqrt(x))
