@@ -69,8 +69,8 @@ def main():
                      buf["b"] if mu else None, rd, nr, sc, ops.make_noise(seed=42, subseq=step_no[0]))
         res = {}
         for _ in range(a.rounds):
-            for T in (64, 128, 256):
-                ops.set_launch_config(0, 1, T)
+            for T in (0, 64, 128, 256):                      # 0 = library default (the lean kFast build where it applies)
+                ops.set_launch_config(0, 0 if T == 0 else 1, T)
                 for _ in range(5):
                     fn()
                 torch.cuda.synchronize()
