@@ -20,11 +20,14 @@ class GraphedForward:
     total_replays = 0               # process-wide counters (diagnostics, tests)
     total_captures = 0
 
-    def __init__(self, net, enabled=True):
+    def __init__(self, net, enabled=True, pool=None):
+        """``pool``: a ``torch.cuda.graph_pool_handle()`` shared with other GraphedForward objects whose replays never
+        overlap in time (every replay's output is cloned before the next one runs, so they may reuse each other's
+        activation memory); default: a private pool."""
         self.net = net
         self.enabled = bool(enabled) and torch.cuda.is_available()
         self._entries = {}          # (shape, dtype) -> dict(graph, x, out) | "eager" | int (eager calls so far)
-        self._pool = None
+        self._pool = pool
         self._bound = None          # the caller's tensor whose values the static input currently holds
         self.replays = 0
         self.captures = 0
@@ -45,7 +48,9 @@ class GraphedForward:
         return dict(graph=graph, x=static_x, out=out)
 
     def __call__(self, x):
-        """net(x) -- a fresh tensor every call (replays clone the graph's static output)."""
+        """net(x) -- a fresh tensor every call (replays clone the graph's static output).  The input is copied into the
+        graph's static buffer when ``x`` is a different tensor OBJECT than last time: callers pass a new tensor per
+        batch and must not modify one in place between calls."""
         if not self.enabled or not x.is_cuda:
             return self.net(x)
         key = (tuple(x.shape), x.dtype, x.device.index)

@@ -28,6 +28,7 @@ from .. import ops
 from ..chain import SampleRing
 from ..dist import bma_evaluate, shard_models
 from ..flat import adopt_parameters, alloc_flat
+from ..graphfwd import GraphedForward
 from ..writer import FlatBackedStateDict
 from . import csghmc as _csghmc
 from ._base import reinitialize_fresh
@@ -41,7 +42,7 @@ class _ResidentSample:
     """One stored sample: a slot of the HBM ring + the buffers (BatchNorm statistics) the state_dict carried, and an
     evaluation network whose parameters are views of that slot."""
 
-    def __init__(self, net, layout, row):
+    def __init__(self, net, layout, row, graph=True, pool=None):
         self.row = row
         self.net = copy.deepcopy(net)
         self.net.eval()
@@ -50,6 +51,8 @@ class _ResidentSample:
                 p.data = v
         for p in self.net.parameters():
             p.requires_grad_(False)
+        # the slot and the buffers never move while the sample is resident: its forward is replayed as a CUDA graph
+        self.forward = GraphedForward(self.net, enabled=graph, pool=pool)
 
 
 class Runner(_csghmc.Runner):
@@ -132,12 +135,21 @@ class Runner(_csghmc.Runner):
 
         self._fs_resident.pop(name, None)
         slot = self._fs_ring.capture(ch.theta, name, self._fs_dense, before_overwrite=evict)
-        sample = _ResidentSample(self.net, ch.layout, self._fs_ring.buf[slot])
+        sample = _ResidentSample(self.net, ch.layout, self._fs_ring.buf[slot], graph=self.use_graph, pool=self._bma_graph_pool())
         self._fs_resident[name] = sample
         # on-disk contract: a state_dict (parameters from the slot, buffers from the sample's own copies)
         sd = FlatBackedStateDict.snapshot(sample.net, ch.layout, ch.names, sample.row)
         self._writer.submit(path, sd)
         return path
+
+    def _bma_graph_pool(self):
+        """One CUDA-graph memory pool for all stored models' forward graphs: they replay one after the other and every
+        output is cloned at once, so they can share activation memory instead of holding S copies of it."""
+        if not (self.use_graph and torch.cuda.is_available()):
+            return None
+        if getattr(self, "_bma_pool", None) is None:
+            self._bma_pool = torch.cuda.graph_pool_handle()
+        return self._bma_pool
 
     def _full_sample_files(self):
         """Sorted file names the reference would list (csghmc_fs.py:270): on disk or still being written."""
@@ -188,11 +200,11 @@ class Runner(_csghmc.Runner):
                 continue
             res = self._fs_resident.get(name)
             if res is not None:
-                nets.append(res.net)
+                nets.append(res.forward)
                 used_files.append(name)
                 continue
             try:
-                nets.append(self._load_sample_from_disk(name))
+                nets.append(GraphedForward(self._load_sample_from_disk(name), enabled=self.use_graph, pool=self._bma_graph_pool()))
                 used_files.append(name)
             except Exception as e:                                   # csghmc_fs.py:307-309
                 if world > 1:                                        # the ranks must agree on the model list

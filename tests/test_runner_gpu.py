@@ -170,12 +170,16 @@ def _check_bma(z, runner, tmp_path):
         assert sorted(pickle.load(f)["test"].keys()) == z["bma_pkl_keys"].tolist()
 
 
-@pytest.mark.parametrize("extra", [dict(), dict(fs_ring_slots=2), dict(io="sync")],
-                         ids=["resident", "evicting-ring", "sync-io"])
+@pytest.mark.parametrize("extra", [dict(), dict(fs_ring_slots=2), dict(io="sync"), dict(graph=0)],
+                         ids=["resident", "evicting-ring", "sync-io", "eager-forward"])
 def test_csghmc_fs_sample_store_and_bma(cuda_device, tmp_path, extra):
     """csghmc_fs: raw samples go to the HBM ring (TMA copy) and are spilled asynchronously; the BMA runs on the resident
-    slots.  A 2-slot ring forces eviction, so older samples are re-read from the spilled files: same results."""
+    slots.  A 2-slot ring forces eviction, so older samples are re-read from the spilled files: same results.  The stored
+    models' forwards are replayed as CUDA graphs sharing one memory pool (graph=0: eager)."""
+    from bayesdll_b200.graphfwd import GraphedForward
+    replays = GraphedForward.total_replays
     z, runner, evals, ret, tape = _run("csghmc_fs", cuda_device, tmp_path, extra_hp=extra)
+    assert (GraphedForward.total_replays > replays) == ("graph" not in extra)
     assert tape.pos == int(z["tape_used"])
     got = runner._dense(runner.model.chain.theta).cpu().numpy()
     assert np.array_equal(got.view(np.uint32), z["theta_final"].view(np.uint32))
