@@ -1,3 +1,7 @@
+# The round-end measurement pass (run on the GPU box through gpurun): GPU test suite, default bench, reference arm,
+# launch list of the profiled command and one ncu --set full capture of the draws / gradient-pointer step.
+# Outputs land in gpurun_out/; the summaries judged are copied to profiles/.
+mkdir -p gpurun_out
 set -x
 python -m pytest tests -m gpu -x -q 2>&1 | grep -v "batch/s" | tail -4
 ( time python bench.py ) > gpurun_out/bench_final6.json 2> gpurun_out/bench_final6.err; tail -4 gpurun_out/bench_final6.err
