@@ -23,6 +23,11 @@ def main():
     cases = [("posterior_draw", lambda i: ops.draw(theta, mom2, out, ops.VAR_FROM_MOMENTS, 1.25, ops.make_noise(seed=1, subseq=i, stream_id=_lib.STREAM_DRAW))),
              ("welford_draw", lambda i: ops.draw(theta, mom2, out, ops.VAR_FROM_WELFORD, 6.0, ops.make_noise(seed=1, subseq=i, stream_id=_lib.STREAM_DRAW))),
              ("vi_draw", lambda i: ops.draw(theta, mom2, out, ops.STD_GIVEN, 1.0, ops.make_noise(seed=1, subseq=i, stream_id=_lib.STREAM_DRAW)))]
+    if "--mix" in sys.argv:                          # the MC-Dropout mix, with and without the 294-run bias table
+        theta0 = torch.randn(n, device=dev, generator=gen) * 0.02
+        dr, dn = ops.upload_runs(lay.dropout_run_table("gaussian"), dev)
+        cases = [("mix_bias_table", lambda i: ops.dropout_mix(theta, theta0, out, 0.1, ops.make_noise(seed=1, subseq=i, stream_id=_lib.STREAM_DRAW), dr, dn)),
+                 ("mix_no_table", lambda i: ops.dropout_mix(theta, theta0, out, 0.1, ops.make_noise(seed=1, subseq=i, stream_id=_lib.STREAM_DRAW)))]
     res = {k: [] for k, _ in cases}
     for rnd in range(3):
         for name, fn in cases:
