@@ -227,6 +227,36 @@ int bdl_oracle_draw(const float* mean, const float* second, const float* center,
     return BDL_OK;
 }
 
+/* MC-Dropout reparameterisation draw (methods/mc_dropout.py:378-394), same contract as bdl_dropout_mix() with host
+ * pointers: z = (u > p_drop), theta = z*m + (1-z)*theta0; runs flagged BDL_CLS_NODROP keep z = 1.  In-kernel uniforms:
+ * the 4 Philox outputs of group q (same counter layout as the Gaussian stream), 24 bits each, u = (r >> 8) * 2^-24. */
+int bdl_oracle_dropout_mix(const float* m, const float* theta0, float* out, float* z_out, uint64_t n, const bdl_run* runs,
+                           uint32_t nruns, float p_drop, const bdl_noise* nz) {
+    if (n % 4) return BDL_ERR_INVALID;
+    const float* u_in = (const float*)(uintptr_t)nz->xi_dev;
+#pragma omp parallel for schedule(static)
+    for (int64_t q = 0; q < (int64_t)(n / 4); ++q) {
+        float u[4];
+        if (u_in) memcpy(u, u_in + 4 * q, sizeof u);
+        else {
+            uint32_t r[4];
+            philox4x32_10((uint32_t)q, nz->stream_id, (uint32_t)nz->subseq, (uint32_t)(nz->subseq >> 32), (uint32_t)nz->seed,
+                          (uint32_t)(nz->seed >> 32), r);
+            for (int k = 0; k < 4; ++k) u[k] = (float)(r[k] >> 8) * 5.9604644775390625e-08f;
+        }
+        uint32_t cls = 0;
+        for (uint32_t j = 0; j < nruns; ++j)
+            if ((uint64_t)(4 * q) < runs[j].end) { cls = runs[j].cls; break; }
+        for (int k = 0; k < 4; ++k) {
+            const uint64_t i = 4 * (uint64_t)q + k;
+            const float z = ((cls & BDL_CLS_NODROP) || u[k] > p_drop) ? 1.0f : 0.0f;
+            out[i] = (z * m[i]) + ((1.0f - z) * theta0[i]);
+            if (z_out) z_out[i] = z;
+        }
+    }
+    return BDL_OK;
+}
+
 int bdl_oracle_moments_avg(const float* theta, float* mom1, float* mom2, uint64_t n, float cnt, float cntp1, int init,
                            int div_mode) {
     const float inv = scalar_reciprocal(cntp1, div_mode);

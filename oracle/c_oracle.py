@@ -71,6 +71,14 @@ def draw(mean, second, out, var_mode, scale, div_mode, noise, center=None):
     assert rc == 0
 
 
+def dropout_mix(m, theta0, out, p_drop, noise, runs=None, z_out=None):
+    """``runs``: ctypes array of bdl_run (host) or None."""
+    rc = lib().bdl_oracle_dropout_mix(_fp(m), _fp(theta0), _fp(out), _fp(z_out), C.c_uint64(m.size),
+                                      runs if runs is not None else None, C.c_uint32(0 if runs is None else len(runs)),
+                                      C.c_float(p_drop), C.byref(noise))
+    assert rc == 0
+
+
 def moments_avg(theta, mom1, mom2, cnt, init, div_mode):
     rc = lib().bdl_oracle_moments_avg(_fp(theta), _fp(mom1), _fp(mom2), C.c_uint64(theta.size), C.c_float(cnt),
                                       C.c_float(cnt + 1), C.c_int(init), C.c_int(div_mode))

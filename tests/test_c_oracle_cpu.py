@@ -126,3 +126,39 @@ def test_c_oracle_moments_and_draw_vs_numpy():
         s_ = (M2 * np.float32(1e-8) - np.float32(5e-9)).astype(np.float32)          # straddles the 1e-8 clamp
         co.draw(mean, s_, out, 4, 1.0, div, nz)
         assert np.array_equal(out, so.vi_sample(mean, s_, eps))
+
+
+def test_c_oracle_dropout_mix_vs_numpy_and_reference_golden():
+    """bdl_oracle_dropout_mix (C) == sampler_oracle.mc_dropout_mix (numpy) on injected uniforms, incl. the recordings of
+    the reference's own mc_dropout.Model.forward; its Philox uniforms lie in [0, 1) with 24-bit resolution."""
+    import golden_util as gu
+    from bayesdll_b200.flat import FlatLayout
+    z = np.load(gu.golden_path("reparam_draws"), allow_pickle=False)
+    lay = FlatLayout([(nm, (int(k),)) for nm, k in zip(z["names"].tolist(), z["sizes"].tolist())], "classifier")
+    for mode in ("gaussian", "spikymix", "ignore"):
+        u_dense, _ = gu.mc_dropout_dense_inputs(z, mode)
+        m, th0, u = (lay.padded_numpy(z[f"mcd_{mode}_m"]), lay.padded_numpy(z[f"mcd_{mode}_theta0"]), lay.padded_numpy(u_dense))
+        nz = L.Noise()
+        nz.xi_dev = u.ctypes.data
+        out, mask = np.empty_like(m), np.empty_like(m)
+        co.dropout_mix(m, th0, out, float(z["p_drop"]), nz, runs=lay.dropout_run_table(mode), z_out=mask)
+        assert np.array_equal(lay.dense_numpy(out).view(np.uint32), z[f"mcd_{mode}_theta"].view(np.uint32))
+        nodrop = np.zeros(lay.n_padded, bool)
+        for sg in lay.segments:
+            nodrop[sg.begin:sg.end] = sg.is_bias and mode != "spikymix"
+        want, wz = so.mc_dropout_mix(m, th0, u, z["p_drop"], nodrop)
+        assert np.array_equal(out.view(np.uint32), want.view(np.uint32)) and np.array_equal(mask, wz)
+    # in-oracle Philox uniforms: reproducible, 24-bit grid in [0, 1), keep rate 1 - p_drop
+    n = 1 << 18
+    m, th0 = np.ones(n, np.float32), np.zeros(n, np.float32)
+    nz = L.Noise()
+    nz.xi_dev, nz.seed, nz.subseq, nz.stream_id = 0, 7, 3, L.STREAM_DRAW
+    a, b = np.empty(n, np.float32), np.empty(n, np.float32)
+    co.dropout_mix(m, th0, a, 0.25, nz)
+    co.dropout_mix(m, th0, b, 0.25, nz)
+    assert np.array_equal(a, b) and set(np.unique(a).tolist()) == {0.0, 1.0}
+    assert abs(a.mean() - 0.75) < 5 * np.sqrt(0.75 * 0.25 / n)
+    ctr = [5, L.STREAM_DRAW, 3, 0]
+    r = co.philox4x32_10(ctr, [7, 0])
+    co.dropout_mix(m, th0, a, 0.5, nz)
+    assert a[20:24].tolist() == [1.0 if (x >> 8) * 2.0 ** -24 > 0.5 else 0.0 for x in r]

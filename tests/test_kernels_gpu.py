@@ -376,3 +376,22 @@ def test_clamped_variance_sqrt_is_ieee_for_every_float(cuda_device):
     x = torch.tensor([1e-12, 3.0, 1e30, float("inf")], device=cuda_device)
     ops.draw(zeros[:4], x, out[:4], ops.VAR_FROM_MOMENTS, 1.0, ops.make_noise(xi=ones[:4]))
     assert torch.equal(out[:4], torch.sqrt(x))
+
+
+@pytest.mark.parametrize("n", [64, 1_000_004])
+def test_mc_dropout_in_kernel_philox_uniforms_equal_the_c_oracle(cuda_device, n):
+    """The mask drawn from the in-kernel Philox stream is bit-for-bit the one the C restatement (oracle/bdl_oracle.c)
+    derives from the same (seed, stream, subseq): integer arithmetic + one exact int->float conversion, no MUFU."""
+    from bayesdll_b200 import _lib, ops
+    from oracle import c_oracle as co
+    rng = np.random.default_rng(n)
+    m, th0 = rng.standard_normal(n).astype(np.float32), rng.standard_normal(n).astype(np.float32)
+    d = lambda a: torch.from_numpy(a).to(cuda_device)
+    out, mask = torch.empty(n, device=cuda_device), torch.empty(n, device=cuda_device)
+    for p_drop, sub in ((0.1, 5), (0.5, (1 << 40) + 9), (0.97, 0)):
+        ops.dropout_mix(d(m), d(th0), out, p_drop, ops.make_noise(seed=(3 << 33) + 11, subseq=sub, stream_id=_lib.STREAM_DRAW), z_out=mask)
+        nz = _lib.Noise()
+        nz.xi_dev, nz.seed, nz.subseq, nz.stream_id = 0, (3 << 33) + 11, sub, _lib.STREAM_DRAW
+        want, wz = np.empty(n, np.float32), np.empty(n, np.float32)
+        co.dropout_mix(m, th0, want, p_drop, nz, z_out=wz)
+        assert np.array_equal(mask.cpu().numpy(), wz) and bits_equal(out.cpu().numpy(), want)
