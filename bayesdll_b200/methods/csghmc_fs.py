@@ -24,7 +24,6 @@ import time
 
 import torch
 
-from .. import ops
 from ..chain import SampleRing
 from ..dist import bma_evaluate, shard_models
 from ..flat import adopt_parameters, alloc_flat
