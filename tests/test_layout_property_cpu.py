@@ -43,3 +43,26 @@ def test_layout_and_runs_invariants(tensors, bias_mode):
         want_prior = not (s.is_bias and bias_mode == "uninformative")
         assert bool(lay.seg_cls(s, bias_mode) & _lib.CLS_PRIOR) == want_prior
         assert bool(lay.seg_cls(s, bias_mode) & _lib.CLS_HEAD) == s.is_head
+
+
+@settings(max_examples=60, deadline=None)
+@given(st.lists(tensor_st, min_size=1, max_size=40), st.sampled_from(["gaussian", "spikymix", "ignore"]))
+def test_dropout_run_table_invariants(tensors, bias_mode):
+    """Run table of bdl_dropout_mix: sorted contiguous cover of the padded layout, neighbouring runs differ in class,
+    BDL_CLS_NODROP exactly on the bias tensors unless the mode treats them like weights (mc_dropout.py:383-389)."""
+    named = [(f"layers.{i}.{kind}", (numel,)) for i, (kind, numel, _) in enumerate(tensors)]
+    lay = FlatLayout(named, "classifier")
+    tab = lay.dropout_run_table(bias_mode)
+    rows = [(r.begin, r.end, r.valid_end, r.cls, r.g_dev) for r in tab]
+    assert rows[0][0] == 0 and rows[-1][1] == lay.n_padded
+    assert all(a[1] == b[0] and a[3] != b[3] for a, b in zip(rows, rows[1:]))
+    assert all(b < ve <= e and b % ALIGN == 0 and g in (0, None) for b, e, ve, _, g in rows)
+    nodrop = np.zeros(lay.n_padded, bool)
+    for b, e, _, c, _ in rows:
+        assert c in (0, _lib.CLS_NODROP)
+        nodrop[b:e] = bool(c & _lib.CLS_NODROP)
+    for s in lay.segments:
+        assert nodrop[s.begin:s.end].all() == (s.is_bias and bias_mode != "spikymix")
+        assert nodrop[s.begin:s.end].any() == (s.is_bias and bias_mode != "spikymix")
+    if bias_mode == "spikymix":
+        assert len(rows) == 1
