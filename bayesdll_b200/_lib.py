@@ -8,7 +8,7 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libbdl.so")
+LIB_PATH = os.environ.get("BDL_LIB_PATH") or os.path.join(HERE, "libbdl.so")   # BDL_LIB_PATH: A/B builds (tools/ab_builds.py)
 
 # ---- enums / constants (include/bdl.h) -------------------------------------------------------
 BDL_ABI_VERSION = 5
@@ -79,6 +79,7 @@ SIGNATURES = {
     "bdl_calibrate": [_P, _P, _U64, _U32, _D, _I32, _P, _U32, _P, _P, _P, _P, _P, _P, _P],
     "bdl_bma_mean": [_P, _U32, _U32, _U32, _P, _P],
     "bdl_nll_temperature": [_P, _P, _U64, _U32, _D, _P, _P, _P],
+    "bdl_selftest_math": [_P, _P],
     "bdl_chain_create": [_U64, _I32, _I32, _U64, C.POINTER(_P)],
     "bdl_chain_destroy": [_P],
     "bdl_chain_upload": [_P, _I32, _P],

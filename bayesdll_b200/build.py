@@ -14,7 +14,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "libbdl.so")
-SOURCES = ["bdl_api.cu", "bdl_step.cu", "bdl_capture.cu", "bdl_draw.cu", "bdl_predict.cu", "bdl_host.cu"]
+SOURCES = ["bdl_api.cu", "bdl_step.cu", "bdl_capture.cu", "bdl_draw.cu", "bdl_predict.cu", "bdl_host.cu", "bdl_selftest.cu"]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",

@@ -38,7 +38,9 @@ class ChainState:
         n = L.n_padded
 
         self.theta = alloc_flat(n, device)
-        adopt_parameters(net, L, self.theta)
+        self._theta_views = adopt_parameters(net, L, self.theta)
+        self._view_ptrs = [v.data_ptr() for v in self._theta_views]
+        self._probe = sorted({0, len(params) // 2, len(params) - 1})
         self.theta0 = None
         if variant != _lib.CSGHMC:                       # cSGHMC ignores net0 (Appendix B.1)
             self.theta0 = alloc_flat(n, device)
@@ -65,6 +67,28 @@ class ChainState:
         self._run_slot = 0
         self._table_sig = None
 
+    def readopt_if_moved(self):
+        """The kernels update the flat ``theta`` buffer; the network reads it through ``p.data`` views.  Code that
+        re-points ``p.data`` (``vector_to_parameters``, ``p.data = ...``) would silently detach the two: probe three
+        parameters per step, and when one moved bring every moved parameter's CURRENT values into the flat buffer and
+        re-point it.  A dtype / device change cannot be adopted and raises."""
+        if all(self.params[i].data_ptr() == self._view_ptrs[i] for i in self._probe):
+            return False
+        moved = 0
+        with torch.no_grad():
+            for p, view, ptr in zip(self.params, self._theta_views, self._view_ptrs):
+                if p.data_ptr() == ptr:
+                    continue
+                if p.dtype != torch.float32 or p.device != self.device or p.shape != view.shape:
+                    raise _lib.BdlError(
+                        f"a sampled parameter was re-pointed at a {p.dtype} tensor of shape {tuple(p.shape)} on {p.device}: "
+                        f"the chain's flat state is fp32 {tuple(view.shape)} on {self.device} (net.to / .half() after the "
+                        f"first step is not supported; build a new Runner)")
+                view.copy_(p.data)
+                p.data = view
+                moved += 1
+        return moved > 0
+
     # ---- views handed to reference-style code ------------------------------------------------
     def named_views(self, flat):
         return dict(zip(self.names, self.layout.views(flat)))
@@ -90,11 +114,15 @@ class ChainState:
         else:
             ptrs = np.array([g.data_ptr() for g in grads], dtype=np.uint64)
         # dtype / contiguity / device: autograd's gradient-layout contract makes a fresh .grad match its (contiguous,
-        # fp32) parameter, so the per-tensor Python checks (the bulk of this function's host time) run on the first
-        # step and then every 32nd; alignment is checked every step (vectorised).
+        # fp32) parameter, so the per-tensor Python checks (the bulk of this function's host time) run when any
+        # gradient ADDRESS differs from the last verified set (the caching allocator hands a steady-state training
+        # loop the same blocks every step) and every 32nd step; alignment is checked every step (vectorised).
         self._grad_checks = getattr(self, "_grad_checks", 0) + 1
         bad = (ptrs & np.uint64(15)) != 0
-        if self._grad_checks % 32 == 1 or n_none != getattr(self, "_last_none", 0):
+        verified = getattr(self, "_verified_ptrs", None)
+        ptrs_changed = verified is None or not np.array_equal(verified, ptrs)
+        if ptrs_changed or self._grad_checks % 32 == 1 or n_none != getattr(self, "_last_none", 0):
+            self._verified_ptrs = ptrs.copy()
             f32, dev = torch.float32, self.device
             for i, g in enumerate(grads):
                 if g is not None and not (g.dtype is f32 and g.is_contiguous() and g.device == dev):

@@ -15,12 +15,20 @@
 // to oracle/ (and hence to the reference's eager ops).  The only fused multiply-add is the one
 // torch's `add_(x, alpha=-lr)` performs.
 //
-// Mapping: persistent grid-stride CTAs (grid = #SM * ctas_per_sm), 256 threads, each thread owns
-// kU float4 groups per tile, consecutive threads touch consecutive 16-byte groups (512 B per warp
-// per stream), all loads of a tile are issued before the first dependent instruction.
+// Mapping: ONE tile per CTA, CTAs dispatched in address order (grid = #tiles); 64-256 threads by variant, each thread
+// owns kU (default 1) float4 groups, consecutive threads touch consecutive 16-byte groups (512 B per warp per
+// stream), all loads of a tile are issued before the first dependent instruction.  Three builds of the same
+// arithmetic: step_kernel<kFast> (flat gradient, body | head table in the kernel arguments: the benchmarked launch),
+// step_table_kernel (device run table with per-tensor gradient pointers: the launch Runner.train() makes; 4
+// consecutive tiles per CTA) and the generic step_kernel (capped / persistent grids via bdl_set_launch_config,
+// chunked host-buffer steps, > 2^31 tiles).  A persistent grid-stride grid measured 8 % slower.
 #include <cstdlib>
 
 #include "bdl_common.cuh"
+
+#ifndef BDL_ADAM_OPT
+#define BDL_ADAM_OPT 1      // Adam variants: optimistic fast-path sqrt / rcp / quotient, one cold branch per element
+#endif
 
 namespace bdl {
 
@@ -134,10 +142,23 @@ __device__ __forceinline__ void update_one(const StepParams& p, uint32_t cls, fl
         s = __fadd_rn(__fmul_rn(p.b2, s), __fmul_rn(p.omb2, __fmul_rn(gU, gU)));
         const float mh = div_scalar<kDiv>(m, p.bc1, p.inv_bc1);
         const float sh = div_scalar<kDiv>(s, p.bc2, p.inv_bc2);
-        const float den = __fadd_rn(__fsqrt_rn(sh), p.eps);
-        const float pre = __frcp_rn(den);               // 1.0 / den, correctly rounded
-        const float pg = div_by_rcp(mh, den, pre);      // m_hat / den, correctly rounded (shares the reciprocal)
-        const float ns = __fmul_rn(p.nd, __fsqrt_rn(div_scalar<kDiv>(__fmul_rn(p.two_alpha, pre), p.N, p.inv_N)));
+        float pg, ns;
+#if BDL_ADAM_OPT
+        // the three correctly rounded sqrt / reciprocal / quotient steps, optimistically on their fast paths with ONE
+        // cold branch to the library intrinsics per element (bdl_common.cuh: same bits)
+        bool slow = false;
+        const float den_f = __fadd_rn(sqrt_rn_opt(sh, slow), p.eps);
+        const float pre_f = rcp_rn_fast(den_f);             // range: div_by_rcp_opt's divisor window (2^-30, 2^30) is inside rcp's
+        pg = div_by_rcp_opt(mh, den_f, pre_f, slow);
+        ns = __fmul_rn(p.nd, sqrt_rn_opt(div_scalar<kDiv>(__fmul_rn(p.two_alpha, pre_f), p.N, p.inv_N), slow));
+        if (slow)
+#endif
+        {
+            const float den = __fadd_rn(__fsqrt_rn(sh), p.eps);
+            const float pre = __frcp_rn(den);               // 1.0 / den, correctly rounded
+            pg = div_by_rcp(mh, den, pre);                  // m_hat / den, correctly rounded (shares the reciprocal)
+            ns = __fmul_rn(p.nd, __fsqrt_rn(div_scalar<kDiv>(__fmul_rn(p.two_alpha, pre), p.N, p.inv_N)));
+        }
         const float noise = __fmul_rn(ns, xi);
         v = __fadd_rn(__fadd_rn(__fmul_rn(v, p.oma), __fmul_rn(lr, pg)), noise);
         if constexpr (kCyc) {
@@ -155,6 +176,41 @@ struct Uses {
     static constexpr bool v = (kVariant != BDL_SGLD);
     static constexpr bool adam = (kVariant == BDL_ADAM_SGHMC || kVariant == BDL_ADAM_CSGHMC);
 };
+
+// Fold the (new) theta of one float4 group into the running moments: the arithmetic of bdl_moments_avg (kCap == 1) /
+// bdl_moments_welford (kCap == 2) in bdl_capture.cu, on values still in registers.
+template <int kCap, int kDiv>
+__device__ __forceinline__ void capture_fold(const StepParams& p, uint64_t i, const float4& th, const float4& c1, const float4& c2) {
+    const float t[4] = {th.x, th.y, th.z, th.w};
+    float a[4] = {c1.x, c1.y, c1.z, c1.w};
+    float bb[4] = {c2.x, c2.y, c2.z, c2.w};
+    const bool has2 = kCap == 2 || p.cap2 != nullptr;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        if constexpr (kCap == 1) {
+            if (p.cap_init) {
+                a[k] = __fmul_rn(t[k], 1.0f);                      // theta_vec*1.0
+                bb[k] = __fmul_rn(t[k], t[k]);                     // theta_vec**2
+            } else {                                               // (theta^k + cnt*mom) / (cnt+1)
+                a[k] = div_scalar<kDiv>(__fadd_rn(t[k], __fmul_rn(p.cap_a, a[k])), p.cap_b, p.cap_inv);
+                if (has2)
+                    bb[k] = div_scalar<kDiv>(__fadd_rn(__fmul_rn(t[k], t[k]), __fmul_rn(p.cap_a, bb[k])), p.cap_b, p.cap_inv);
+            }
+        } else {
+            if (p.cap_init) {
+                a[k] = t[k];                                       // mean = theta.clone()
+                bb[k] = 0.0f;                                      // M2 = zeros_like
+            } else {
+                const float d = __fsub_rn(t[k], a[k]);             // delta
+                a[k] = __fadd_rn(a[k], div_scalar<kDiv>(d, p.cap_a, p.cap_inv));
+                const float d2 = __fsub_rn(t[k], a[k]);            // delta2
+                bb[k] = __fadd_rn(bb[k], __fmul_rn(d, d2));
+            }
+        }
+    }
+    st_stream(p.cap1 + i, make_float4(a[0], a[1], a[2], a[3]));
+    if (has2) st_stream(p.cap2 + i, make_float4(bb[0], bb[1], bb[2], bb[3]));
+}
 
 constexpr int kDefaultUnroll = 1;
 constexpr long kDefaultTableTpc = 4;   // profiles/r01_ab_table_tpc.log: 1.169 -> 1.080 ms (SGHMC), 2.111 -> 1.970 ms (Adam-cSGHMC) at ViT-L/32 size
@@ -320,38 +376,8 @@ step_kernel(const StepParams p) {
                 st_stream(p.theta + i, th[u]);
             }
             if constexpr (kCap != 0) {
-                if (inr[u]) {                              // also for skipped tensors: their (unchanged) theta is a sample too
-                    const uint64_t i = static_cast<uint64_t>(q) << 2;
-                    const float t[4] = {th[u].x, th[u].y, th[u].z, th[u].w};
-                    float a[4] = {c1[u].x, c1[u].y, c1[u].z, c1[u].w};
-                    float bb[4] = {c2[u].x, c2[u].y, c2[u].z, c2[u].w};
-                    const bool has2 = kCap == 2 || p.cap2 != nullptr;
-#pragma unroll
-                    for (int k = 0; k < 4; ++k) {
-                        if constexpr (kCap == 1) {
-                            if (p.cap_init) {
-                                a[k] = __fmul_rn(t[k], 1.0f);                      // theta_vec*1.0
-                                bb[k] = __fmul_rn(t[k], t[k]);                     // theta_vec**2
-                            } else {                                               // (theta^k + cnt*mom) / (cnt+1)
-                                a[k] = div_scalar<kDiv>(__fadd_rn(t[k], __fmul_rn(p.cap_a, a[k])), p.cap_b, p.cap_inv);
-                                if (has2)
-                                    bb[k] = div_scalar<kDiv>(__fadd_rn(__fmul_rn(t[k], t[k]), __fmul_rn(p.cap_a, bb[k])), p.cap_b, p.cap_inv);
-                            }
-                        } else {
-                            if (p.cap_init) {
-                                a[k] = t[k];                                       // mean = theta.clone()
-                                bb[k] = 0.0f;                                      // M2 = zeros_like
-                            } else {
-                                const float d = __fsub_rn(t[k], a[k]);             // delta
-                                a[k] = __fadd_rn(a[k], div_scalar<kDiv>(d, p.cap_a, p.cap_inv));
-                                const float d2 = __fsub_rn(t[k], a[k]);            // delta2
-                                bb[k] = __fadd_rn(bb[k], __fmul_rn(d, d2));
-                            }
-                        }
-                    }
-                    st_stream(p.cap1 + i, make_float4(a[0], a[1], a[2], a[3]));
-                    if (has2) st_stream(p.cap2 + i, make_float4(bb[0], bb[1], bb[2], bb[3]));
-                }
+                if (inr[u])                                // also for skipped tensors: their (unchanged) theta is a sample too
+                    capture_fold<kCap, kDiv>(p, static_cast<uint64_t>(q) << 2, th[u], c1[u], c2[u]);
             }
         }
         if constexpr (kFast) {
@@ -364,11 +390,176 @@ step_kernel(const StepParams p) {
 }
 
 // -------------------------------------------------------------------------------------------
+// Lean build of the training-loop launch: a device run table with one row per tensor,
+// each row carrying the address of that tensor's own autograd gradient (p.grad read in place, no gather pass).
+// Same arithmetic as step_kernel (update_one / capture_fold), different control:
+//   * a CTA owns kTableTpc CONSECUTIVE tiles (still dispatched in address order): ONE table search per CTA (warp 0,
+//     32-ary ballot search, published through shared memory), issued after the first tile's table-independent loads;
+//   * CTA-uniform fast path: when the CTA's whole span lies inside the run found (every CTA of a large tensor), class,
+//     gradient base and "tensor has a gradient" are CTA-uniform -- no per-thread cursor, no tail test, no bounds test,
+//     tiles fully unrolled: the per-tile instruction count is the kFast kernel's;
+//   * otherwise (span crosses a tensor boundary, holds a tensor's 16-byte tail group, or is the last CTA): per-thread
+//     register cursor {end4, cls, gbase, tail group (32-bit), tail lanes}, advanced monotonically.
+// -------------------------------------------------------------------------------------------
+#ifndef BDL_TABLE_TPC_K
+#define BDL_TABLE_TPC_K 4
+#endif
+#ifndef BDL_TABLE_PREFETCH
+#define BDL_TABLE_PREFETCH 0    // 1: uniform path issues tile t+1's loads before tile t's arithmetic (A/B knob)
+#endif
+constexpr int kTableTpc = BDL_TABLE_TPC_K;   // profiles/r01_ab_table_tpc.log: 2 tiles 1.104, 4: 1.080, 8: 1.101, 16: 1.115 ms (SGHMC, ViT-L/32)
+
+struct TableCursor {
+    uint32_t idx, end4, cls;
+    uint32_t tail_q;      // group holding the tensor's last real elements when numel % 4 != 0, else 0xFFFFFFFF
+    uint32_t tail_n;      // number of real elements in that group (1..3)
+    const float* gbase;   // gradient element for flat index i is gbase[i]
+};
+
+__device__ __forceinline__ void tcursor_load(TableCursor& c, const StepParams& p, uint32_t idx) {
+    const bdl_run* r = p.runs + idx;
+    c.idx = idx;
+    c.end4 = static_cast<uint32_t>(__ldg(&r->end) >> 2);
+    c.cls = __ldg(&r->cls);
+    const float* gr = reinterpret_cast<const float*>(__ldg(reinterpret_cast<const unsigned long long*>(&r->g_dev)));
+    const uint64_t ve = __ldg(&r->valid_end);
+    c.tail_n = gr ? static_cast<uint32_t>(ve) & 3u : 0u;     // the flat gradient buffer carries its own (zero) padding
+    c.tail_q = c.tail_n ? static_cast<uint32_t>(ve >> 2) : 0xFFFFFFFFu;
+    c.gbase = gr ? gr - __ldg(&r->begin) : p.g;
+}
+
+template <int kVariant, bool kHasBuf, bool kPhilox, int kCap>
+struct TileRegs {
+    float4 th, g, th0, v, m, s, b, xi, c1, c2;
+};
+
+template <int kVariant, bool kHasBuf, bool kPhilox, int kCap>
+__device__ __forceinline__ void tile_load(TileRegs<kVariant, kHasBuf, kPhilox, kCap>& r, const StepParams& p, uint64_t i) {
+    using U = Uses<kVariant>;
+    r.th = ld_stream(p.theta + i);
+    if constexpr (kCap != 0) {
+        if (!p.cap_init) {
+            r.c1 = ld_stream(p.cap1 + i);
+            if (kCap == 2 || p.cap2) r.c2 = ld_stream(p.cap2 + i);
+        }
+    }
+    if constexpr (U::theta0) r.th0 = ld_stream(p.theta0 + i);
+    if constexpr (U::v) r.v = ld_stream(p.v + i);
+    if constexpr (U::adam) {
+        r.m = ld_stream(p.m + i);
+        r.s = ld_stream(p.s + i);
+    }
+    if constexpr (kHasBuf) r.b = ld_stream(p.buf + i);
+    if constexpr (!kPhilox) r.xi = ld_stream(p.xi + i);
+}
+
+template <int kVariant, bool kHasBuf, bool kPhilox, int kDiv, int kCap>
+__device__ __forceinline__ void tile_update_store(TileRegs<kVariant, kHasBuf, kPhilox, kCap>& r, const StepParams& p,
+                                                  uint32_t q, uint64_t i, uint32_t cls) {
+    using U = Uses<kVariant>;
+    if constexpr (kPhilox) r.xi = philox_normal4(p.key, q);
+    update_one<kVariant, kHasBuf, kDiv>(p, cls, r.th.x, r.g.x, r.th0.x, r.v.x, r.m.x, r.s.x, r.b.x, r.xi.x);
+    update_one<kVariant, kHasBuf, kDiv>(p, cls, r.th.y, r.g.y, r.th0.y, r.v.y, r.m.y, r.s.y, r.b.y, r.xi.y);
+    update_one<kVariant, kHasBuf, kDiv>(p, cls, r.th.z, r.g.z, r.th0.z, r.v.z, r.m.z, r.s.z, r.b.z, r.xi.z);
+    update_one<kVariant, kHasBuf, kDiv>(p, cls, r.th.w, r.g.w, r.th0.w, r.v.w, r.m.w, r.s.w, r.b.w, r.xi.w);
+    if constexpr (U::v) st_stream(p.v + i, r.v);
+    if constexpr (U::adam) {
+        st_stream(p.m + i, r.m);
+        st_stream(p.s + i, r.s);
+    }
+    if constexpr (kHasBuf) st_stream(p.buf + i, r.b);
+    st_stream(p.theta + i, r.th);
+}
+
+#ifdef BDL_TABLE_MINB
+#define BDL_TABLE_BLOCKS(...) BDL_TABLE_MINB
+#else
+#define BDL_TABLE_BLOCKS(...) (min_blocks<__VA_ARGS__>())
+#endif
+template <int kVariant, bool kHasBuf, bool kPhilox, int kDiv, int kT, int kCap = 0>
+__global__ void __launch_bounds__(kT, BDL_TABLE_BLOCKS(kVariant, kHasBuf, kPhilox, 1, kT, kCap))
+step_table_kernel(const StepParams p) {
+    constexpr uint32_t cta_groups = kT * kTableTpc;
+    const uint32_t q_cta = blockIdx.x * cta_groups;          // < n4 for every launched CTA (whole range, q_begin == 0)
+    uint32_t q = q_cta + threadIdx.x;
+    TileRegs<kVariant, kHasBuf, kPhilox, kCap> r;
+    // tile 0: the loads that do not depend on the table go out before the search
+    if (q < p.n4) tile_load(r, p, static_cast<uint64_t>(q) << 2);
+    __shared__ uint32_t run0_sh;
+    if (threadIdx.x < 32) {
+        const uint32_t r0 = run_find_warp(p.runs, p.nruns, q_cta);
+        if (threadIdx.x == 0) run0_sh = r0;
+    }
+    __syncthreads();
+    TableCursor cur;
+    tcursor_load(cur, p, run0_sh);
+    const uint32_t q_last = q_cta + cta_groups;              // one past the CTA's span
+    if (q_last <= p.n4 && (q_last < cur.end4 || (q_last == cur.end4 && cur.tail_n == 0))) {
+        // ---- CTA-uniform: the whole span is real elements of ONE tensor ----
+        const uint32_t cls = cur.cls;
+        const bool live = (cls & BDL_CLS_SKIP) == 0;         // p.grad is None -> tensor left untouched (still captured)
+        const float* gbase = cur.gbase;
+#if BDL_TABLE_PREFETCH
+        if (live) r.g = ld_stream(gbase + (static_cast<uint64_t>(q) << 2));
+#pragma unroll
+        for (int t = 0; t < kTableTpc; ++t, q += kT) {
+            const uint64_t i = static_cast<uint64_t>(q) << 2;
+            TileRegs<kVariant, kHasBuf, kPhilox, kCap> nx;
+            if (t + 1 < kTableTpc) {                         // next tile's loads go out before this tile's arithmetic
+                const uint64_t i2 = static_cast<uint64_t>(q + kT) << 2;
+                tile_load(nx, p, i2);
+                if (live) nx.g = ld_stream(gbase + i2);
+            }
+            if (live) tile_update_store<kVariant, kHasBuf, kPhilox, kDiv, kCap>(r, p, q, i, cls);
+            if constexpr (kCap != 0) capture_fold<kCap, kDiv>(p, i, r.th, r.c1, r.c2);
+            if (t + 1 < kTableTpc) r = nx;
+        }
+#else
+#ifdef BDL_TABLE_UNROLL1
+#pragma unroll 1
+#else
+#pragma unroll
+#endif
+        for (int t = 0; t < kTableTpc; ++t, q += kT) {
+            const uint64_t i = static_cast<uint64_t>(q) << 2;
+            if (t > 0) tile_load(r, p, i);
+            if (live) {
+                r.g = ld_stream(gbase + i);
+                tile_update_store<kVariant, kHasBuf, kPhilox, kDiv, kCap>(r, p, q, i, cls);
+            }
+            if constexpr (kCap != 0) capture_fold<kCap, kDiv>(p, i, r.th, r.c1, r.c2);
+        }
+#endif
+        return;
+    }
+    // ---- general: per-thread cursor ----
+#pragma unroll 1
+    for (int t = 0; t < kTableTpc; ++t, q += kT) {
+        if (q >= p.n4) break;
+        const uint64_t i = static_cast<uint64_t>(q) << 2;
+        if (t > 0) tile_load(r, p, i);
+        while (q >= cur.end4 && cur.idx + 1 < p.nruns) tcursor_load(cur, p, cur.idx + 1);   // runs are sorted and contiguous
+        if ((cur.cls & BDL_CLS_SKIP) == 0) {
+            r.g = ld_stream(cur.gbase + i);
+            if (q == cur.tail_q) {                           // tail group of a tensor: lanes past its end are padding (g = 0)
+                if (cur.tail_n < 2) r.g.y = 0.f;
+                if (cur.tail_n < 3) r.g.z = 0.f;
+                r.g.w = 0.f;
+            }
+            tile_update_store<kVariant, kHasBuf, kPhilox, kDiv, kCap>(r, p, q, i, cur.cls);
+        }
+        if constexpr (kCap != 0) capture_fold<kCap, kDiv>(p, i, r.th, r.c1, r.c2);
+    }
+}
+
+// -------------------------------------------------------------------------------------------
 // host side
 // -------------------------------------------------------------------------------------------
-static int g_ctas_per_sm = 0;   // 0 = one tile per CTA (default); > 0 = persistent grid of #SM * ctas_per_sm CTAs
-static int g_unroll = 0;        // 0 = default
-static int g_threads = 0;       // 0 = default
+// Launch-shape overrides (bdl_set_launch_config): per calling thread, so a sweep on one thread / device never changes
+// what another thread launches.
+static thread_local int g_ctas_per_sm = 0;   // 0 = one tile per CTA (default); > 0 = persistent grid of #SM * ctas_per_sm CTAs
+static thread_local int g_unroll = 0;        // 0 = default
+static thread_local int g_threads = 0;       // 0 = default
 
 // Tiles per CTA for launches whose run table carries gradient pointers (experiment knob: BDL_TABLE_TPC, read once).
 static uint32_t table_tiles_per_cta() {
@@ -393,9 +584,22 @@ static int launch_shape(const StepParams& p, cudaStream_t st) {
     if (grid == 0) return BDL_OK;
     if (grid == ntiles && p.inl_n == 0 && !p.flat_g && table_tiles_per_cta() > 1) {
         // run table with per-tensor gradient pointers (the training-loop launch): the gradient load depends on the table
-        // lookup.  A CTA that walks a few consecutive tiles pays the search and that late first load once; later tiles
-        // follow the register cursor.  Tables without gradient pointers (bias=uninformative) lose nothing to the lookup
-        // and stay at one tile per CTA (1.044 vs 1.053 ms).
+        // lookup.  A CTA that walks a few consecutive tiles pays the search and that late first load once.  Tables
+        // without gradient pointers (bias=uninformative) lose nothing to the lookup and stay at one tile per CTA
+        // (1.044 vs 1.053 ms).
+        if constexpr (kAllowFast && kU == 1) {
+            if (table_tiles_per_cta() == static_cast<uint32_t>(kTableTpc) && p.q_begin == 0) {   // the lean build
+#ifdef BDL_TABLE_T
+                constexpr int kTT = BDL_TABLE_T;                 // A/B knob: CTA size of the table kernel
+#else
+                constexpr int kTT = kT;
+#endif
+                constexpr uint32_t span = kTT * kTableTpc;
+                grid = (static_cast<uint64_t>(p.n4) + span - 1) / span;
+                step_table_kernel<kVariant, kHasBuf, kPhilox, kDiv, kTT, kCap><<<static_cast<uint32_t>(grid), kTT, 0, st>>>(p);
+                return check_cuda(cudaGetLastError(), "step_table_kernel launch");
+            }
+        }
         StepParams pc = p;
         pc.tpc = table_tiles_per_cta();
         grid = (ntiles + pc.tpc - 1) / pc.tpc;
@@ -431,8 +635,11 @@ static int launch_u(const StepParams& p, cudaStream_t st) {
     if (g_unroll == 0 && g_threads == 0)       // library defaults: this shape also has the fast-path build (an explicit
         return launch_shape<kVariant, kHasBuf, kPhilox, kDiv, kDefaultUnroll, kAutoThreads, 0, true>(p, st);   // shape request runs the generic one)
 #define BDL_SHAPE(UU, TT) if (unroll == UU && threads == TT) return launch_shape<kVariant, kHasBuf, kPhilox, kDiv, UU, TT>(p, st)
-    BDL_SHAPE(1, 64); BDL_SHAPE(1, 128); BDL_SHAPE(1, 256); BDL_SHAPE(1, 512);
+    BDL_SHAPE(1, 64);
+#ifndef BDL_AB_SLIM
+    BDL_SHAPE(1, 128); BDL_SHAPE(1, 256); BDL_SHAPE(1, 512);
     BDL_SHAPE(2, 64); BDL_SHAPE(2, 128); BDL_SHAPE(2, 256); BDL_SHAPE(2, 512);
+#endif
 #undef BDL_SHAPE
     set_error("bdl_step: unsupported launch shape unroll=%d threads=%d (unroll 1|2, threads 64|128|256|512)", unroll, threads);
     return BDL_ERR_INVALID;
@@ -544,6 +751,13 @@ int step_range(int variant, float* theta, const float* g, const float* theta0, f
 
     const bool philox = nz->xi_dev == nullptr;
     const int d = sc->div_mode;
+#ifdef BDL_AB_SLIM
+    // A/B builds (tools/ab_builds.py): only what the sweep launches, so that a build takes seconds
+    BDL_REQUIRE(philox && d == BDL_DIV_RECIP && !has_buf && (variant == BDL_SGHMC || variant == BDL_ADAM_CSGHMC),
+                BDL_ERR_UNSUPPORTED, "slim A/B build: SGHMC / Adam-cSGHMC with Philox noise and reciprocal division only");
+    return variant == BDL_SGHMC ? launch_u<BDL_SGHMC, false, true, BDL_DIV_RECIP>(p, st)
+                                : launch_u<BDL_ADAM_CSGHMC, false, true, BDL_DIV_RECIP>(p, st);
+#else
     switch (variant) {
         case BDL_SGLD:
             return has_buf ? launch_nd<BDL_SGLD, true>(p, philox, d, st) : launch_nd<BDL_SGLD, false>(p, philox, d, st);
@@ -557,6 +771,7 @@ int step_range(int variant, float* theta, const float* g, const float* theta0, f
         default:
             return launch_nd<BDL_ADAM_CSGHMC, false>(p, philox, d, st);
     }
+#endif
 }
 
 }  // namespace bdl

@@ -248,6 +248,49 @@ def bench_sharded_ensemble(device, rank, world, rows=512, batch=64, cycles=8, ns
 
 
 # ------------------------------------------------------------------------------------------------------------
+# Sample sharding behind Runner.evaluate() / full_batch_likelihoods()  (hparams eval_shard=1)
+# ------------------------------------------------------------------------------------------------------------
+def process_group():
+    """(rank, world) of the default process group, (0, 1) outside one."""
+    import torch.distributed as dist
+    if dist.is_available() and dist.is_initialized():
+        return dist.get_rank(), dist.get_world_size()
+    return 0, 1
+
+
+def my_samples(n_samples, rank, world):
+    """Round-robin share of the flat sample index j = component * nst + s."""
+    return [j for j in range(n_samples) if j % world == rank]
+
+
+def gather_samples(local, n_samples, world, group=None):
+    """The exchange step of a sample-sharded evaluation that must return the reference's ``logits_all``:
+    ``local`` [N, K, s_max] holds this rank's samples in the order of ``my_samples`` (zero-padded to
+    s_max = ceil(S / world)); ONE all-gather returns the full [N, K, S] stack in sample order on every rank.
+    Sample j = r + world * i sits at gathered[r, :, :, i].  Every later reduction runs on the full stack with the very
+    kernels the single-rank path uses, so its results do not depend on the number of ranks (bit-identical)."""
+    import torch.distributed as dist
+    N, K, s_max = local.shape
+    assert s_max == (n_samples + world - 1) // world
+    gathered = torch.empty((world, N, K, s_max), dtype=local.dtype, device=local.device)
+    dist.all_gather_into_tensor(gathered.view(-1), local.contiguous().view(-1), group=group)   # flat: one shape rule for nccl and gloo
+    return gathered.permute(1, 2, 3, 0).reshape(N, K, s_max * world)[:, :, :n_samples].contiguous()
+
+
+def agree_across_ranks(t, what, group=None):
+    """Every rank must have walked the same data (same loader order): compare an order-sensitive checksum."""
+    import torch.distributed as dist
+    w = torch.arange(1, t.numel() + 1, dtype=torch.float64, device=t.device)
+    h = torch.stack([(t.reshape(-1).double() * w).sum(), torch.tensor(float(t.numel()), dtype=torch.float64, device=t.device)])
+    lo, hi = h.clone(), h.clone()
+    dist.all_reduce(lo, op=dist.ReduceOp.MIN, group=group)
+    dist.all_reduce(hi, op=dist.ReduceOp.MAX, group=group)
+    if not torch.equal(lo, hi):
+        raise RuntimeError(f"eval_shard: the ranks disagree on {what} -- every rank must iterate the same data in the same "
+                           f"order (no shuffling, no DistributedSampler) and hold the same chain state")
+
+
+# ------------------------------------------------------------------------------------------------------------
 # Model-sharded Bayesian model average (csghmc_fs, SURVEY 8f row 2)
 # ------------------------------------------------------------------------------------------------------------
 def shard_models(n_models, rank, world):

@@ -28,7 +28,6 @@ class GraphedForward:
         self.enabled = bool(enabled) and torch.cuda.is_available()
         self._entries = {}          # (shape, dtype) -> dict(graph, x, out) | "eager" | int (eager calls so far)
         self._pool = pool
-        self._bound = None          # the caller's tensor whose values the static input currently holds
         self.replays = 0
         self.captures = 0
 
@@ -49,8 +48,9 @@ class GraphedForward:
 
     def __call__(self, x):
         """net(x) -- a fresh tensor every call (replays clone the graph's static output).  The input is copied into the
-        graph's static buffer when ``x`` is a different tensor OBJECT than last time: callers pass a new tensor per
-        batch and must not modify one in place between calls."""
+        graph's static buffer on EVERY call: tensor identity says nothing about the values (a caller may refill one
+        preallocated batch tensor in place), and the copy is noise next to the forward it feeds (38 MB = ~12 us on
+        B200 against a 9 ms ResNet-101 pass)."""
         if not self.enabled or not x.is_cuda:
             return self.net(x)
         key = (tuple(x.shape), x.dtype, x.device.index)
@@ -63,7 +63,6 @@ class GraphedForward:
                 return self.net(x)
             try:
                 ent = self._capture(x)
-                self._bound = x
             except Exception as e:                        # not capturable: eager from now on
                 warnings.warn(f"CUDA-graph capture of the evaluation forward failed ({type(e).__name__}: {e}); "
                               f"running it eagerly")
@@ -71,9 +70,7 @@ class GraphedForward:
                 self._entries[key] = "eager"
                 return self.net(x)
             self._entries[key] = ent
-        if self._bound is not x:                          # a new batch: one device copy into the graph's input
-            ent["x"].copy_(x)
-            self._bound = x
+        ent["x"].copy_(x)                                 # always: never trust identity for freshness
         ent["graph"].replay()
         self.replays += 1
         GraphedForward.total_replays += 1

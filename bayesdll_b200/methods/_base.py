@@ -14,6 +14,7 @@ stored vector, and the quirks listed in SURVEY.md Appendix B.
 What is different: one fused kernel per step instead of ~12-30 eager kernels per tensor, no per-sample
 ``deepcopy(net)``, no host sync per batch in ``evaluate`` and none per step in ``train_one_epoch``.
 """
+import contextlib
 import copy
 import os
 import pickle
@@ -25,6 +26,7 @@ import torch.nn as nn
 from tqdm import tqdm
 
 from .. import _lib, calibration, ops
+from .. import dist as bdist
 from ..chain import ChainState, SampleRing
 from ..flat import adopt_parameters, alloc_flat
 from ..graphfwd import GraphedForward
@@ -93,7 +95,7 @@ class FusedModel(nn.Module):
         self.t = 0
         self._chain = None
         self._opts = dict(sgd_momentum=0.0, seed=None, noise="philox", grad_mode="table", div_mode=_lib.DIV_RECIP,
-                          optimizer=None, graph_train=False)
+                          optimizer=None, graph_train=False, release_grads=True)
         self._train_graphs = {}        # (net, shapes, criterion) -> eager-call count | captured graph | "eager"
 
     def configure(self, **opts):
@@ -124,6 +126,7 @@ class FusedModel(nn.Module):
     def _ensure_chain(self, net, net0):
         ch = self._chain
         if ch is not None and ch.params and ch.params[0] is next(iter(net.parameters())):
+            ch.readopt_if_moved()                         # p.data re-pointed by user code (vector_to_parameters, ...)
             return ch
         o = self._opts
         seed = o["seed"] if o["seed"] is not None else torch.initial_seed()
@@ -159,6 +162,13 @@ class FusedModel(nn.Module):
             net.zero_grad()                               # grads -> None; autograd hands us fresh tensors
             loss.backward()
         chain.update(self._scalars(lrs, Ninflate, nd, should_sample), capture=None if capture is None else capture())
+        if self._opts["release_grads"]:
+            # The reference leaves the modified gradient in p.grad for the caller's optimizer.step(); here the update is
+            # already applied, so a REAL torch optimizer stepping on p.grad would update theta a second time.  With the
+            # gradients released every optimizer skips every parameter (``if p.grad is None: continue``); the kernel
+            # launched above still owns their memory in stream order.
+            for p in chain.params:
+                p.grad = None
         return loss.detach(), out.detach()
 
     # ---- optional: forward + backward as ONE CUDA-graph replay (hparams graph_train=1) -----------------------------
@@ -261,6 +271,94 @@ class _EvalNet:
         ops.draw(mean, second, self.flat, var_mode, scale, nz, div_mode, center=center)
 
 
+class _Phases:
+    """Device time per evaluation phase (draw | forward | reduce | exchange), measured with CUDA events on the launching
+    stream when ``Runner.profile_eval`` is set (bench.py's ensemble leg); otherwise free."""
+
+    def __init__(self, enabled):
+        self.enabled = bool(enabled)
+        self.spans = {}
+        self.host = {}
+
+    @contextlib.contextmanager
+    def __call__(self, name):
+        if not self.enabled:
+            yield
+            return
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        try:
+            yield
+        finally:
+            e1.record()
+            self.spans.setdefault(name, []).append((e0, e1))
+
+    def summary(self):
+        """{phase: milliseconds}; synchronises."""
+        if not self.enabled:
+            return {}
+        torch.cuda.synchronize()
+        out = {k: float(sum(a.elapsed_time(b) for a, b in v)) for k, v in self.spans.items()}
+        out.update({f"{k}_launches": len(v) for k, v in self.spans.items()})
+        out.update(self.host)
+        return out
+
+
+def _prefetch(loader, dev):
+    """(x, y) batches on the device.  The NEXT batch's host-to-device copy runs on a side stream (copy engine) while the
+    current batch computes: with 8 ranks sharing one PCIe root the 38 MB image batches would otherwise sit on the
+    critical path of every rank."""
+    if torch.device(dev).type != "cuda":
+        for x, y in loader:
+            yield x.to(dev), y.to(dev)
+        return
+    side = torch.cuda.Stream(dev)
+
+    def issue(item):
+        x, y = item
+        if x.is_cuda and y.is_cuda:
+            return x, y, None
+        side.wait_stream(torch.cuda.current_stream(dev))      # the buffers being recycled by the allocator are idle
+        with torch.cuda.stream(side):
+            xd, yd = x.to(dev, non_blocking=True), y.to(dev, non_blocking=True)
+            evt = torch.cuda.Event()
+            evt.record(side)
+        return xd, yd, evt
+
+    it = iter(loader)
+    try:
+        nxt = issue(next(it))
+    except StopIteration:
+        return
+    while nxt is not None:
+        xd, yd, evt = nxt
+        cur = torch.cuda.current_stream(dev)
+        if evt is not None:
+            cur.wait_event(evt)
+            xd.record_stream(cur)
+            yd.record_stream(cur)
+        try:
+            nxt = issue(next(it))
+        except StopIteration:
+            nxt = None
+        yield xd, yd
+
+
+class _EvalAccumulator:
+    """Device-side accumulators of one ``evaluate()`` call: CE sum, error count and the per-batch outputs."""
+
+    def __init__(self, dev):
+        self.loss_sum = torch.zeros(1, dtype=torch.float64, device=dev)
+        self.err_cnt = torch.zeros(1, dtype=torch.int32, device=dev)
+        self.nb, self.ys, self.lgs, self.lgalls = 0, [], [], []
+
+    def add(self, y, logits, logits_all):
+        self.ys.append(y)
+        self.lgs.append(logits)
+        self.lgalls.append(logits_all)
+        self.nb += len(y)
+
+
 def _pack_subseq(eval_id, batch, cycle, sample):
     """64-bit Philox sub-sequence of one posterior draw: independent of how samples are sharded over ranks."""
     return ((eval_id & 0xFFFF) << 48) | ((batch & 0xFFFFFF) << 24) | ((cycle & 0xFF) << 16) | (sample & 0xFFFF)
@@ -271,11 +369,17 @@ class _RunnerCommon:
 
     MODEL_CLS = None
     SGD_MOMENTUM_FROM_ARGS = False     # SGD(momentum=args.momentum) vs SGD(momentum=0)
+    SUPPORTS_CLIP_GRAD = False         # args.clip_grad: see CyclicalRunner
 
     # ---- construction (methods/sghmc.py:18-67) ------------------------------------------------------------
     def __init__(self, net, net0, args, logger):
         self.args = args
         self.logger = logger
+        self.clip_grad = getattr(args, "clip_grad", None)   # consulted by the cyclical runners only (methods/csgld.py:250)
+        if self.clip_grad is not None and not self.SUPPORTS_CLIP_GRAD:
+            raise NotImplementedError(
+                f"args.clip_grad={self.clip_grad!r}: gradient-norm clipping between Model.forward and optimizer.step() "
+                f"(methods/csgld.py:250-251) is not available for {type(self).__module__}; leave args.clip_grad unset")
         if args.pretrained is None:                       # zero prior mean
             self.net0 = copy.deepcopy(net)
             with torch.no_grad():
@@ -307,6 +411,13 @@ class _RunnerCommon:
                              grad_mode=str(hp.get("grad", "table")), div_mode=self.div_mode, optimizer=self.optimizer,
                              graph_train=bool(int(float(hp.get("graph_train", 0)))))
         self._eval_calls = 0
+        # eval_shard=1: inside an initialised torch.distributed process group whose ranks hold the SAME chain state,
+        # evaluate() / full_batch_likelihoods() deal the posterior samples round-robin to the ranks; results
+        # are bit-identical to one rank and identical on every rank.  Off by default: independent chains (one per
+        # rank) must not pool their samples.
+        self.eval_shard = bool(int(float(hp.get("eval_shard", 0))))
+        self.profile_eval = False        # True: evaluate() leaves a per-phase device-time split in self.eval_phases
+        self.eval_phases = {}
         # fuse=1 (default): the moment capture that follows a sampler step runs inside the step kernel; fuse=0: separate
         # launch right after it, like the reference's statement order (bit-identical either way)
         self.fuse_capture = str(hp.get("fuse", "1")).lower() not in ("0", "false", "no")
@@ -331,11 +442,45 @@ class _RunnerCommon:
     def _dense(self, flat):
         return self._chain().layout.to_dense(flat)
 
-    def _finish_eval(self, loss_sum, err_cnt, nb, ys, lgs, lgalls):
-        targets = torch.cat(ys).cpu().numpy()
-        logits = torch.cat(lgs).cpu().numpy()
-        logits_all = torch.cat(lgalls).cpu().numpy()
-        return loss_sum.item() / nb, err_cnt.item() / nb, targets, logits, logits_all
+    def _shard(self):
+        """(rank, world) of the sample-sharded evaluation: the default process group when hparams ``eval_shard=1``,
+        else (0, 1)."""
+        if self.eval_shard:
+            if self.noise_mode != "philox":
+                raise ValueError("eval_shard=1 needs the counter-based Philox draws (noise=philox): a torch.randn_like "
+                                 "stream cannot be dealt to ranks")
+            return bdist.process_group()
+        return 0, 1
+
+    def _gather_eval(self, local_batches, rows, n_samples, rank, world, phases):
+        """This rank's per-batch sample logits (lists of [B,K] tensors in ``my_samples`` order) -> the full [N,K,S]
+        stack on every rank: the evaluation's one exchange step (an all-gather of N*K*ceil(S/world) floats per rank)."""
+        import torch.distributed as dist
+        dev = self.args.device
+        n_mine = len(bdist.my_samples(n_samples, rank, world))
+        k_local = local_batches[0][0].shape[1] if n_mine and local_batches else 0
+        kk = torch.tensor([k_local, sum(rows)], dtype=torch.int64, device=dev)
+        dist.all_reduce(kk, op=dist.ReduceOp.MAX)              # ranks without a sample learn K; all agree on N
+        K, N = int(kk[0].item()), int(kk[1].item())
+        if N != sum(rows):
+            raise RuntimeError("eval_shard: the ranks iterated a different number of rows")
+        s_max = (n_samples + world - 1) // world
+        local = torch.zeros((N, K, s_max), dtype=torch.float32, device=dev)
+        if n_mine:
+            local[:, :, :n_mine] = torch.cat([torch.stack(outs, 2) for outs in local_batches]).float()
+        with phases("exchange"):
+            return bdist.gather_samples(local, n_samples, world)
+
+    def _finish_eval(self, acc, phases=None):
+        t0 = time.perf_counter()
+        targets = torch.cat(acc.ys).cpu().numpy()
+        logits = torch.cat(acc.lgs).cpu().numpy()
+        logits_all = torch.cat(acc.lgalls).cpu().numpy()
+        out = acc.loss_sum.item() / acc.nb, acc.err_cnt.item() / acc.nb, targets, logits, logits_all
+        if phases is not None and phases.enabled:
+            phases.host["d2h_and_sync_ms"] = (time.perf_counter() - t0) * 1e3
+            self.eval_phases = phases.summary()
+        return out
 
     # ---- writers (methods/sghmc.py:356-367) -----------------------------------------------------------
     def save_logits(self, targets, logits, logits_all, suffix=None):
@@ -519,36 +664,54 @@ class BurninRunner(_RunnerCommon):
         return self.post_theta_cnt / (self.post_theta_cnt - 1) if self.post_theta_cnt > 1 else 1.0
 
     def evaluate(self, test_loader):
+        """(loss, err, targets[N], logits[N,K], logits_all[N,K,S]) as methods/sghmc.py:256-324.  With ``eval_shard=1`` in
+        a process group the ``nst`` draws are dealt round-robin to the ranks, one all-gather assembles ``logits_all`` and
+        the ensemble / CE reductions then run over the full stack on every rank: same bits as one rank."""
         args = self.args
         dev = args.device
         ch = self._chain()
         ev = _EvalNet(self.net, ch.layout, graph=self.use_graph)
         self._eval_calls += 1
         ratio = self._variance_ratio()
-        loss_sum = torch.zeros(1, dtype=torch.float64, device=dev)
-        err_cnt = torch.zeros(1, dtype=torch.int32, device=dev)
-        nb, ys, lgs, lgalls = 0, [], [], []
+        rank, world = self._shard()
+        S = max(1, self.nst)
+        mine = bdist.my_samples(S, rank, world)
+        ph = _Phases(self.profile_eval)
+        acc = _EvalAccumulator(dev)
+        local, rows, ys = [], [], []
         with torch.no_grad(), tqdm(test_loader, unit="batch") as tepoch:
-            for b_idx, (x, y) in enumerate(tepoch):
-                x, y = x.to(dev, non_blocking=True), y.to(dev, non_blocking=True)
+            for b_idx, (x, y) in enumerate(_prefetch(tepoch, dev)):
                 outs = []
-                if self.nst == 0:
-                    ev.load(self._mom1)
-                    outs.append(ev.forward(x))
-                else:
-                    for ii in range(self.nst):             # fresh draw for every batch (Appendix B.6)
-                        ev.draw(self._mom1, self._mom2, ops.VAR_FROM_MOMENTS, ratio, self.noise_mode, self.seed,
-                                _pack_subseq(self._eval_calls, b_idx, 0, ii), self.div_mode)
+                for ii in mine:
+                    with ph("draw"):
+                        if self.nst == 0:
+                            ev.load(self._mom1)
+                        else:                              # fresh draw for every batch (Appendix B.6)
+                            ev.draw(self._mom1, self._mom2, ops.VAR_FROM_MOMENTS, ratio, self.noise_mode, self.seed,
+                                    _pack_subseq(self._eval_calls, b_idx, 0, ii), self.div_mode)
+                    with ph("forward"):
                         outs.append(ev.forward(x))
-                logits_all_ = torch.stack(outs, 2).contiguous().float()
-                logits_ = torch.empty(logits_all_.shape[:2], dtype=torch.float32, device=dev)
-                ops.ensemble(logits_all_, logits_, self.nst)
-                ops.ce_err(logits_, y, loss_sum, err_cnt)
-                ys.append(y)
-                lgs.append(logits_)
-                lgalls.append(logits_all_)
-                nb += len(y)
-        return self._finish_eval(loss_sum, err_cnt, nb, ys, lgs, lgalls)
+                if world == 1:
+                    with ph("reduce"):
+                        self._reduce_batch(torch.stack(outs, 2).contiguous().float(), y, acc)
+                else:
+                    local.append(outs)
+                    rows.append(len(y))
+                    ys.append(y)
+        if world > 1:
+            bdist.agree_across_ranks(torch.cat(ys), "the evaluation targets")
+            la = self._gather_eval(local, rows, S, rank, world, ph)
+            with ph("reduce"):
+                for la_b, y in zip(torch.split(la, rows), ys):     # same batch boundaries as one rank: same summation order
+                    self._reduce_batch(la_b.contiguous(), y, acc)
+        return self._finish_eval(acc, ph)
+
+    def _reduce_batch(self, logits_all_, y, acc):
+        """log-mean-softmax over the samples, CE sum and error count of one batch (methods/sghmc.py:299-306)."""
+        logits_ = torch.empty(logits_all_.shape[:2], dtype=torch.float32, device=logits_all_.device)
+        ops.ensemble(logits_all_, logits_, self.nst)
+        ops.ce_err(logits_, y, acc.loss_sum, acc.err_cnt)
+        acc.add(y, logits_, logits_all_)
 
     def get_mean_vars_from_moments(self):
         """API compatibility (methods/sghmc.py:327-353): two ``net``-like modules holding mean and variance."""
@@ -737,8 +900,7 @@ class CyclicalRunner(_RunnerCommon):
         err_cnt = torch.zeros(1, dtype=torch.int32, device=dev)
         nb = 0
         with torch.no_grad():
-            for x, y in loader:
-                x, y = x.to(dev, non_blocking=True), y.to(dev, non_blocking=True)
+            for x, y in _prefetch(loader, dev):
                 ops.ce_err(fwd(x).float().contiguous(), y, loss_sum, err_cnt)
                 nb += len(y)
         net.train(was_training)
@@ -844,8 +1006,16 @@ class CyclicalRunner(_RunnerCommon):
         if self.CAPTURE == "avg":
             if self.STORE_ALL_SAMPLES and getattr(self.args, "full_sample", False):            # csgld.py:278-279
                 if self._ring is None:
-                    self._ring = SampleRing(ch.layout, ch.device, self._expected_samples())
-                self._ring.capture(ch.theta, f"{epoch}_{batch_idx}", self.all_samples)
+                    want = self._expected_samples()
+                    self._ring = SampleRing(ch.layout, ch.device, want)
+                    if self._ring.capacity < want:
+                        self.logger.warning(
+                            f"full_sample: the HBM sample ring holds {self._ring.capacity} of the {want} samples this run "
+                            f"will capture (25 % of free HBM); older samples drop out of all_samples as the ring wraps "
+                            f"(the reference keeps every sample in device memory until it runs out)")
+                # a slot about to be reused may still be queued in the writer (all_samples_TEST.ckpt holds views)
+                self._ring.capture(ch.theta, f"{epoch}_{batch_idx}", self.all_samples,
+                                   before_overwrite=lambda _old: self._writer.flush())
         else:   # Welford with the reference's double-counted n (Appendix B.3): n runs 3, 5, 7, ...
             self.samples_per_cycle[cycle] = 1 if first else self.samples_per_cycle.get(cycle, 0) + 1
 
@@ -869,6 +1039,10 @@ class CyclicalRunner(_RunnerCommon):
 
     # ---- GMM ensemble (methods/csgld.py:333-456) -----------------------------------------------------------------
     def evaluate(self, test_loader):
+        """(loss, err, targets[N], logits[N,K], logits_all[N,K,nst,C]) as methods/csgld.py:333-456.  With ``eval_shard=1``
+        in a process group the C x nst draws are dealt round-robin to the ranks (flat index cycle * nst + sample), one
+        all-gather assembles ``logits_all`` and the per-cycle log-mean-softmax, the log-space GMM mixture and the CE
+        reductions then run over the full stack on every rank: same bits as one rank."""
         args = self.args
         dev = args.device
         ch = self._chain()
@@ -878,43 +1052,64 @@ class CyclicalRunner(_RunnerCommon):
         self._eval_calls += 1
         cycles = [c for c in self._cyc1 if not gmm_weights.get(c, 0.0) < 1e-10]
         specs = {c: self._cycle_variance_spec(c) for c in cycles} if self.nst > 0 else {}
-        loss_sum = torch.zeros(1, dtype=torch.float64, device=dev)
-        err_cnt = torch.zeros(1, dtype=torch.int32, device=dev)
-        nb, ys, lgs, lgalls = 0, [], [], []
+        weights = [gmm_weights.get(c, 0.0) for c in cycles]
+        per = max(1, self.nst)
+        S = len(cycles) * per
+        rank, world = self._shard()
+        mine = bdist.my_samples(S, rank, world)
+        ph = _Phases(self.profile_eval)
+        acc = _EvalAccumulator(dev)
+        local, rows, ys = [], [], []
         with torch.no_grad(), tqdm(test_loader, unit="batch") as tepoch:
-            for b_idx, (x, y) in enumerate(tepoch):
-                x, y = x.to(dev, non_blocking=True), y.to(dev, non_blocking=True)
-                comps = []
-                batch_logits = None
-                for ci, c in enumerate(cycles):
-                    outs = []
-                    if self.nst == 0:
-                        ev.load(self._cyc1[c])
-                        outs.append(ev.forward(x))
-                    else:
-                        second, var_mode, scale = specs[c]
-                        for ii in range(self.nst):
+            for b_idx, (x, y) in enumerate(_prefetch(tepoch, dev)):
+                outs = []
+                for j in mine:
+                    c, ii = cycles[j // per], j % per
+                    with ph("draw"):
+                        if self.nst == 0:
+                            ev.load(self._cyc1[c])
+                        else:
+                            second, var_mode, scale = specs[c]
                             ev.draw(self._cyc1[c], second, var_mode, scale, self.noise_mode, self.seed,
                                     _pack_subseq(self._eval_calls, b_idx, c, ii), self.div_mode)
-                            outs.append(ev.forward(x))
-                    comp = torch.stack(outs, 2).contiguous().float()
-                    comps.append(comp)
-                    if batch_logits is None:
-                        batch_logits = torch.empty(comp.shape[:2], dtype=torch.float32, device=dev)
-                    # weighted sum of log-probabilities (Appendix B.5); nst == 0 uses the raw logits (csgld.py:419-420)
-                    if self.nst == 0:
-                        w = torch.tensor(gmm_weights.get(c, 0.0), dtype=torch.float32, device=dev)
-                        batch_logits = w * comp.squeeze(2) if ci == 0 else batch_logits + w * comp.squeeze(2)
-                    else:
-                        ops.ensemble(comp, batch_logits, self.nst, weight=gmm_weights.get(c, 0.0), mode=1 if ci == 0 else 2)
-                batch_logits_all = torch.stack(comps, dim=3) if comps else \
-                    torch.zeros((x.size(0), args.num_classes, 1, 1), device=dev)
-                ops.ce_err(batch_logits.contiguous(), y, loss_sum, err_cnt)
-                ys.append(y)
-                lgs.append(batch_logits)
-                lgalls.append(batch_logits_all)
-                nb += len(y)
-        return self._finish_eval(loss_sum, err_cnt, nb, ys, lgs, lgalls)
+                    with ph("forward"):
+                        outs.append(ev.forward(x))
+                if world == 1:
+                    with ph("reduce"):
+                        flat = torch.stack(outs, 2).float() if outs else torch.zeros((x.size(0), args.num_classes, 0), device=dev)
+                        self._reduce_batch(flat, y, acc, weights, per)
+                else:
+                    local.append(outs)
+                    rows.append(len(y))
+                    ys.append(y)
+        if world > 1:
+            bdist.agree_across_ranks(torch.cat(ys), "the evaluation targets")
+            la = self._gather_eval(local, rows, S, rank, world, ph)
+            with ph("reduce"):
+                for la_b, y in zip(torch.split(la, rows), ys):
+                    self._reduce_batch(la_b, y, acc, weights, per)
+        return self._finish_eval(acc, ph)
+
+    def _reduce_batch(self, flat, y, acc, weights, per):
+        """One batch: ``flat`` [B,K,C*per] (sample index cycle * per + s) -> ``logits_all`` [B,K,per,C], per-cycle
+        log-mean-softmax, weighted sum of log-probabilities (Appendix B.5; methods/csgld.py:416-439), CE / errors."""
+        B, K, C = flat.shape[0], flat.shape[1], len(weights)
+        dev = flat.device
+        if C == 0:
+            logits_all = torch.zeros((B, self.args.num_classes, 1, 1), device=dev)
+            batch_logits = None                            # as the reference: nothing to mix (its CE then fails, too)
+        else:
+            logits_all = flat.view(B, K, C, per).permute(0, 1, 3, 2).contiguous()      # torch.stack(comps, dim=3)
+            batch_logits = torch.empty((B, K), dtype=torch.float32, device=dev)
+        for ci, w in enumerate(weights):
+            comp = logits_all[:, :, :, ci].contiguous()                                 # torch.stack(outs, 2) of cycle ci
+            if self.nst == 0:      # raw logits of the mean parameters, no log-mean-softmax (csgld.py:419-420)
+                wt = torch.tensor(w, dtype=torch.float32, device=dev)
+                batch_logits = wt * comp.squeeze(2) if ci == 0 else batch_logits + wt * comp.squeeze(2)
+            else:
+                ops.ensemble(comp, batch_logits, self.nst, weight=w, mode=1 if ci == 0 else 2)
+        ops.ce_err(batch_logits.contiguous(), y, acc.loss_sum, acc.err_cnt)
+        acc.add(y, batch_logits, logits_all)
 
     # ---- cycle likelihoods and GMM weights (methods/csgld.py:508-594) ----------------------------------------
     def full_batch_likelihoods(self, train_loader):
@@ -940,9 +1135,13 @@ class CyclicalRunner(_RunnerCommon):
                 raise TypeError("cycle variance is None (reference: vector_to_parameters(None, ...), Appendix B.8)")
         ev = _EvalNet(self.net, ch.layout, graph=self.use_graph)
         self._eval_calls += 1
-        likelihoods = []
         n_draws = max(1, self.nst)
-        for sample_idx in range(n_draws):
+        rank, world = self._shard()
+        # eval_shard=1: every draw is a full pass over the training set, so the draws are dealt round-robin to the ranks
+        # (SURVEY 8f row 1); one all-reduce of the n_draws fp64 losses (zeros elsewhere: exact) hands every rank the same
+        # list, each entry computed by the kernels one rank would have run
+        losses = torch.zeros(n_draws, dtype=torch.float64, device=dev)
+        for sample_idx in bdist.my_samples(n_draws, rank, world):
             if self.nst > 0 and spec is not None:
                 second, var_mode, scale = spec
                 ev.draw(mean, second, var_mode, scale, self.noise_mode, self.seed,
@@ -950,6 +1149,12 @@ class CyclicalRunner(_RunnerCommon):
             else:
                 ev.load(ch.theta)                        # net_sample = deepcopy(self.net), no perturbation
             avg_loss, _ = self._point_estimate(train_loader, ev.net, fwd=ev.forward)
+            losses[sample_idx] = avg_loss
+        if world > 1:
+            import torch.distributed as dist
+            dist.all_reduce(losses)
+        likelihoods = []
+        for sample_idx, avg_loss in enumerate(losses.tolist()):
             likelihood = np.exp(-avg_loss)
             likelihoods.append(likelihood)
             self.logger.info(f"Sample {sample_idx + 1} - Full batch average loss: {avg_loss:.6f}, "

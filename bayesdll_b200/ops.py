@@ -316,6 +316,16 @@ def nll_temperature(logits, labels, temperature, row_nll, out_mean):
     return out_mean
 
 
+def selftest_math(device):
+    """Exhaustive device self-test of the branch-free sqrt / reciprocal / quotient helpers (bdl_selftest_math):
+    -> dict(mismatch=[sqrt, rcp, div], fast=[...]) over all 2^32 fp32 bit patterns."""
+    out = torch.zeros(6, dtype=torch.int64, device=device)
+    with torch.cuda.device(device):
+        _lib.check(_lib.load().bdl_selftest_math(out.data_ptr(), _stream()), "bdl_selftest_math")
+    h = out.cpu().tolist()
+    return {"mismatch": h[:3], "fast": h[3:]}
+
+
 class HostChain:
     """Python handle of the host-buffer chain API (bdl_chain_*): sampler state resident in HBM, gradient in / theta
     out through pinned host tensors.  See include/bdl.h."""

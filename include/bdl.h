@@ -263,6 +263,12 @@ int bdl_bma_mean(const float* logits_all_dev, uint32_t B, uint32_t K, uint32_t S
 int bdl_nll_temperature(const float* logits_dev, const int64_t* labels_dev, uint64_t N, uint32_t K, double temperature,
                         double* row_nll_dev, double* out_mean_dev, void* stream);
 
+/* Test / diagnostics entry: exhaustive device self-test of the library's correctly rounded fp32 helpers (the
+ * branch-free sqrt / reciprocal / quotient fast paths the Adam update rules use, methods/adam_sghmc.py:536-541) against
+ * the CUDA intrinsics over all 2^32 bit patterns.  out6_dev: 6 x uint64 = mismatches {sqrt, rcp, div}, then the number
+ * of inputs that took the fast path {sqrt, rcp, div}.  ~0.1 s on B200. */
+int bdl_selftest_math(unsigned long long* out6_dev, void* stream);
+
 /* ------------------------------------------------------------------------------------------------
  * Host-buffer form: a chain whose state is resident in HBM, stepped from HOST memory.
  * (The one place the library owns device memory.)  This is what a CPU-resident caller of the reference's

@@ -215,3 +215,50 @@ def test_sharded_bma_world2_is_bit_identical_to_world1(S):
         for k in ("logits_all", "logits", "targets", "loss_per", "err_per"):
             assert np.array_equal(r[k], one[k]), k
         assert r["bma_loss_sum"] == one["bma_loss_sum"] and r["bma_err_sum"] == one["bma_err_sum"] and r["n"] == one["n"]
+
+
+# ---- sample sharding behind Runner.evaluate (hparams eval_shard=1): the exchange helpers under gloo ----------------------
+def _gather_worker(rank, world, port, S, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    import torch.distributed as dist
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    assert bdist.process_group() == (rank, world)
+    N, K = 11, 4
+    full = torch.arange(N * K * S, dtype=torch.float32).reshape(N, K, S) * 0.5 - 3.0      # full[:, :, j] = sample j
+    mine = bdist.my_samples(S, rank, world)
+    s_max = (S + world - 1) // world
+    local = torch.zeros(N, K, s_max)
+    if mine:
+        local[:, :, :len(mine)] = full[:, :, mine]
+    got = bdist.gather_samples(local, S, world)
+    bdist.agree_across_ranks(torch.arange(5), "identical data")
+    disagree = None
+    try:
+        bdist.agree_across_ranks(torch.arange(5) + rank, "rank-dependent data")
+    except RuntimeError as e:
+        disagree = str(e)
+    q.put((rank, torch.equal(got, full), mine, disagree))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,S", [(2, 5), (3, 8), (2, 1)])
+def test_gather_samples_restores_sample_order(world, S):
+    """Ragged shares (5 samples on 2 ranks), more ranks than samples (1 sample on 2 ranks): the all-gather returns the
+    [N,K,S] stack in sample order on every rank; a rank-dependent data order is detected."""
+    assert bdist.process_group() == (0, 1)
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_gather_worker, args=(r, world, port, S, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=120) for _ in range(world))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert sorted(sum((m for _, _, m, _ in res), [])) == list(range(S))
+    for rank, ok, mine, disagree in res:
+        assert ok, f"rank {rank}: gathered stack differs"
+        assert mine == [j for j in range(S) if j % world == rank]
+        assert disagree is not None and "disagree" in disagree
