@@ -32,6 +32,18 @@ def _nvcc():
     raise RuntimeError("nvcc not found")
 
 
+def source_hash():
+    """sha256 over every kernel source, the ABI header and the nvcc flags: identifies the build an ncu capture came from
+    (profiles/traffic.json)."""
+    import hashlib
+    h = hashlib.sha256()
+    for path in sorted(os.path.join(CSRC, f) for f in os.listdir(CSRC)) + [os.path.join(ROOT, "include", "bdl.h")]:
+        with open(path, "rb") as f:
+            h.update(os.path.basename(path).encode() + b"\0" + f.read())
+    h.update(" ".join(f for f in NVCC_FLAGS if not f.startswith(ROOT)).encode())      # the include path is checkout-specific
+    return h.hexdigest()
+
+
 def needs_build():
     if not os.path.exists(OUT):
         return True

@@ -244,7 +244,7 @@ extern "C" int bdl_moments_welford(const float* theta, float* mean, float* M2, u
     return check_cuda(cudaGetLastError(), "moments_welford_kernel launch");
 }
 
-static uint32_t g_ring_chunks_per_cta = 4;
+static thread_local uint32_t g_ring_chunks_per_cta = 4;   // per calling thread (bdl_set_ring_config)
 extern "C" int bdl_set_ring_config(int chunks_per_cta) {
     using namespace bdl;
     BDL_REQUIRE(chunks_per_cta >= 1 && chunks_per_cta <= (1 << 20), BDL_ERR_INVALID, "chunks_per_cta out of range");

@@ -136,25 +136,35 @@ class ShardedEnsemble:
 
     def calibrate(self, targets, logits, num_bins):
         """ECE / MCE / NLL with the rows of ``logits`` sharded over the ranks -> (ece, mce, nll)."""
-        from .calibration import bin_edges
-        dev = self.flat.device
-        lg = torch.as_tensor(logits, dtype=torch.float32)[self.rank::self.world].contiguous().to(dev)
-        lb = torch.as_tensor(targets, dtype=torch.int64)[self.rank::self.world].contiguous().to(dev)
-        edges = torch.from_numpy(bin_edges(num_bins)).to(dev)
-        M = num_bins
-        if lg.shape[0] > 0:
-            stats = self.backend.calibrate(lg, lb, edges)
-        else:
-            stats = torch.zeros(3 * M + 2, dtype=torch.float64, device=dev)
-        self._all_reduce(stats)
-        h = stats.cpu().numpy()
-        sizes, acc_sum, conf_sum, nll_sum = h[:M], h[M:2 * M], h[2 * M:3 * M], h[3 * M]
-        nz = sizes > 0
-        accs, confs = np.zeros(M), np.zeros(M)
-        accs[nz], confs[nz] = acc_sum[nz] / sizes[nz], conf_sum[nz] / sizes[nz]
-        ece = (np.abs(accs - confs) * (sizes / sizes.sum())).sum()
-        mce = np.abs(accs - confs).max()
-        return ece, mce, nll_sum / len(targets)
+        return calibrate_sharded(targets, logits, num_bins, self.flat.device, self.rank, self.world, self.group, self.backend)
+
+
+def calibrate_sharded(targets, logits, num_bins, device, rank=0, world=1, group=None, backend=None):
+    """calibration.analyze (calibration.py:215-249) with the rows dealt round-robin to the ranks: every rank bins its
+    rows (bdl_calibrate), ONE all-reduce(SUM) of the 3*M+2 fp64 statistics (bin sizes, accuracy sums, confidence sums,
+    NLL sum, near-edge count) follows.  Bin sizes / accuracy sums are integer-valued, so they are exact for any number
+    of ranks.  -> (ece, mce, nll)."""
+    from .calibration import bin_edges
+    backend = backend or CudaBackend()
+    lg = torch.as_tensor(logits, dtype=torch.float32)[rank::world].contiguous().to(device)
+    lb = torch.as_tensor(targets, dtype=torch.int64)[rank::world].contiguous().to(device)
+    edges = torch.from_numpy(bin_edges(num_bins)).to(device)
+    M = num_bins
+    if lg.shape[0] > 0:
+        stats = backend.calibrate(lg, lb, edges)
+    else:
+        stats = torch.zeros(3 * M + 2, dtype=torch.float64, device=device)
+    if world > 1:
+        import torch.distributed as dist
+        dist.all_reduce(stats, group=group)
+    h = stats.cpu().numpy()
+    sizes, acc_sum, conf_sum, nll_sum = h[:M], h[M:2 * M], h[2 * M:3 * M], h[3 * M]
+    nz = sizes > 0
+    accs, confs = np.zeros(M), np.zeros(M)
+    accs[nz], confs[nz] = acc_sum[nz] / sizes[nz], conf_sum[nz] / sizes[nz]
+    ece = (np.abs(accs - confs) * (sizes / sizes.sum())).sum()
+    mce = np.abs(accs - confs).max()
+    return ece, mce, nll_sum / len(targets)
 
 
 def components_from_runner(runner):
@@ -170,81 +180,6 @@ def components_from_runner(runner):
         return comps, True
     return [dict(cycle=0, mean=runner._mom1, second=runner._mom2, var_mode=ops.VAR_FROM_MOMENTS,
                  scale=runner._variance_ratio(), weight=1.0)], False
-
-
-def bench_sharded_ensemble(device, rank, world, rows=512, batch=64, cycles=8, nst=5, backbone="resnet101", num_bins=15):
-    """BASELINE.json configs[4]: ResNet-101 cSGLD 8 cycles x nst 5 = 40-sample ensemble + ECE/MCE/NLL, samples sharded over
-    the ranks.  Returns a dict for bench.py's ``ensemble`` key (preds/s = rows * samples / wall time, max over ranks)."""
-    from . import shapes
-    from .flat import FlatLayout
-    torch.manual_seed(7)                                     # same weights and per-cycle statistics on every rank
-    with torch.device(device):
-        net = shapes.create_backbone(backbone, 37)
-    lay = FlatLayout.from_module(net)
-    theta = alloc_flat(lay.n_padded, device)
-    adopt_parameters(net, lay, theta)
-    x_host = torch.randn(batch, 3, 224, 224, generator=torch.Generator().manual_seed(5)).pin_memory()
-    # one training-mode pass with momentum 1 sets the BatchNorm running statistics to those of a synthetic batch, so
-    # the random-init network yields finite O(1) logits in eval mode (running stats are buffers, not sampled)
-    for mod in net.modules():
-        if isinstance(mod, torch.nn.modules.batchnorm._BatchNorm):
-            mod.momentum = 1.0
-    net.train()
-    with torch.no_grad():
-        net(x_host.to(device))
-    net.eval()
-    gen = torch.Generator(device=device).manual_seed(11)
-    comps = []
-    for c in range(1, cycles + 1):
-        mean = theta + 1e-3 * torch.randn(lay.n_padded, device=device, generator=gen)
-        second = mean * mean + 1e-6 * torch.rand(lay.n_padded, device=device, generator=gen)
-        comps.append(dict(cycle=c, mean=mean, second=second, var_mode=ops.VAR_FROM_MOMENTS, scale=nst / (nst - 1.0),
-                          weight=1.0 / cycles))
-    rows = max(batch, rows // batch * batch)
-    y_all = torch.randint(0, 37, (rows,), generator=torch.Generator().manual_seed(3))
-    loader = [(x_host, y_all[i:i + batch].pin_memory()) for i in range(0, rows, batch)]
-    ens = ShardedEnsemble(net, lay, comps, nst, seed=42, mixture=True, rank=rank, world=world)
-    ens.evaluate(loader[:1])                                 # warm-up (cuDNN autotune, allocator)
-    if world > 1:
-        import torch.distributed as dist
-        dist.barrier()
-    torch.cuda.synchronize()
-    t0 = time.perf_counter()
-    loss, err, targets, logits = ens.evaluate(loader)
-    ece, mce, nll = ens.calibrate(targets, logits, num_bins)
-    torch.cuda.synchronize()
-    dt = time.perf_counter() - t0
-    if world > 1:
-        import torch.distributed as dist
-        t = torch.tensor([dt], dtype=torch.float64, device=device)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        dt = t.item()
-    S = cycles * nst
-    # context: cost of materialising ONE posterior sample, ours (bdl_draw) vs the reference's structure on this GPU
-    # (deepcopy(net) + randn_like / sqrt / mul / add / copy_ per tensor, methods/csgld.py:404-413)
-    comp = comps[0]
-    torch.cuda.synchronize()
-    t0 = time.perf_counter()
-    for i in range(10):
-        ens.backend.draw(comp, ens.flat, 42, i, ens.div_mode)
-    torch.cuda.synchronize()
-    ours_draw_ms = (time.perf_counter() - t0) / 10 * 1e3
-    mean_views, var_views = lay.views(comp["mean"]), lay.views(torch.clamp(comp["second"] - comp["mean"] ** 2, min=1e-12))
-    t0 = time.perf_counter()
-    for i in range(3):
-        with torch.no_grad():
-            net_sample = copy.deepcopy(net)
-            for p, p_mean, p_var in zip(net_sample.parameters(), mean_views, var_views):
-                p.copy_(p_mean + p_var.sqrt() * torch.randn_like(p))
-    torch.cuda.synchronize()
-    ref_draw_ms = (time.perf_counter() - t0) / 3 * 1e3
-    del net_sample
-    return {"draw_ms": ours_draw_ms, "reference_structure_draw_ms": ref_draw_ms, "metric": "ensemble preds/s (ResNet-101 cSGLD 40-sample posterior-predictive ensemble + ECE/MCE/NLL)",
-            "value": rows * S / dt, "unit": "preds/s", "rows": rows, "samples": S, "seconds": dt, "n_gpus": world,
-            "sharding": "by sample, round-robin; all-reduce MAX+SUM of the [C,N,K] running logsumexp + one of the bin statistics",
-            "ece": float(ece), "nll": float(nll), "loss": float(loss),
-            "note": "per-sample cost = 1 draw kernel (12 B/param) + PyTorch fp32 forward of 64 images; samples re-drawn "
-                    "for every batch as the reference does (Appendix B.6)"}
 
 
 # ------------------------------------------------------------------------------------------------------------

@@ -17,12 +17,21 @@ e2e         the same update through the host-buffer C ABI (bdl_chain_step_host):
             memory and the new theta returns to pinned HOST memory every step (4 B/param each way, inside the timed
             region); theta0 / momentum stay resident.  This is what a CPU-resident caller of the reference binds.
 roofline    HBM-bound; achieved = 24 B/param * n / average kernel duration; peak = MEASURED_PEAKS.json hbm_gbs.
-cpu_baseline  the fused C/OpenMP port of the reference path (oracle/bdl_oracle.c) on the host cores, rank 0, N=1.
+cpu_baseline  the UNMODIFIED reference's own methods/sghmc.py Model.forward + optimizer.step() on the host cores (kind
+            "reference"; baseline/reference_arm.py drives it from /root/reference or baseline/_ref), bounded sample, rank 0,
+            N=1; the fused C/OpenMP port (oracle/bdl_oracle.c, kind "port") is reported next to it and is the fallback
+            when no reference tree exists.
 train_step  (extra) the full user call Model.forward on a real torchvision ViT-L/32, batch 64: x,y from pinned host,
             PyTorch fwd/bwd, fused update reading autograd's gradients in place, loss.item().
-ensemble    (extra) sample-sharded 40-sample ResNet-101 posterior-predictive ensemble + ECE, preds/s.
+ensemble    BASELINE.json configs[4] through the Runner API: csgld.Runner.evaluate() (hparams eval_shard=1) on ResNet-101,
+            8 cycles x nst 5 = 40 samples, N = 3 669 rows (Pets test size), batch 64, + ECE/MCE/NLL; preds/s and a
+            per-phase device-time split (draw | forward | reduce | exchange | d2h | calibrate).  Also mirrored into
+            e2e["ensemble_*"].
+cfg1        BASELINE.json configs[0]: mlp_mnist SGLD, the unmodified reference Runner on the host cores next to the
+            drop-in Runner on the GPU (ms/step, ensemble preds/s, calibration.analyze ms).
 
---impl reference times the CPU port on the same config / metric / unit (rank 0 only).
+--impl reference times the reference's own CPU implementation of the path (kind "reference"; the C port when no reference
+tree is found) on the same config / metric / unit (rank 0 only).
 """
 import argparse
 import json
@@ -43,6 +52,15 @@ BYTES_PER_PARAM = 24          # SGHMC: R theta,g,theta0,v ; W v,theta   (BASELIN
 HP = dict(prior_sig=1.0, Ninflate=1e3, nd=1.0, alpha=0.18, lr_body=1e-4, lr_head=1e-2, ND=1840)
 METRIC = "sampler step params/s (ViT-L/32 fused SGHMC update)"
 WORKLOAD = "ViT-L/32 (K=37, n=305548325) SGHMC fused step, net0 prior mean, in-kernel Philox; BASELINE.json configs[2]"
+
+
+def bench_config(world, n_dense):
+    """The `config` object of the JSON line -- identical in both arms (`--impl ours|reference`)."""
+    return {"workload": WORKLOAD, "hparams": "prior_sig=1.0,Ninflate=1e3,nd=1.0,momentum_decay=0.18,bias=informative",
+            "lr": HP["lr_body"], "lr_head": HP["lr_head"], "ND": HP["ND"], "params_per_chain": n_dense,
+            "chains": world, "parallelism": f"{world} independent chain(s), one per GPU, no data-path collective",
+            "l2": "inputs (4.9 GB per step) larger than L2 (126 MB); no flush needed",
+            "noise": "in-kernel Philox4x32-10 + Box-Muller", "division": "reciprocal (reference-on-CUDA semantics)"}
 
 
 def env_int(name, default):
@@ -68,12 +86,20 @@ def measured_peak():
 
 
 def recorded_traffic():
-    """dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu capture, or None."""
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the headline kernel from the committed ``ncu --set full``
+    capture -- only when that capture was taken from THIS build of the kernels (profiles/traffic.json records a hash of
+    csrc/ + include/bdl.h + the nvcc flags; tools/traffic_from_ncu.py writes it).  -> (bytes | None, note)."""
     try:
+        from bayesdll_b200 import build as b
         with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
-            return json.load(f).get("sghmc_step_dram_bytes_per_launch")
-    except Exception:
-        return None
+            rec = json.load(f)
+        have = b.source_hash()
+        if rec.get("build_hash") != have:
+            return None, (f"profiles/traffic.json was captured from build {str(rec.get('build_hash'))[:12]}, the loaded "
+                          f"library is build {have[:12]}: re-run tools/round_end_run.sh")
+        return rec.get("sghmc_step_dram_bytes_per_launch"), f"ncu capture of build {have[:12]} ({rec.get('source', '')[:80]})"
+    except Exception as e:  # noqa: BLE001
+        return None, f"no usable profiles/traffic.json ({type(e).__name__})"
 
 
 class ClockSampler:
@@ -222,8 +248,9 @@ def run_ours(args):
     peak, peak_kind = measured_peak()
     kernel_ms = e0.elapsed_time(e1) / K                      # this rank's average launch duration
     achieved = BYTES_PER_PARAM * n_dense / (kernel_ms * 1e-3) / 1e9
+    traffic, traffic_note = recorded_traffic()
     roofline = {"bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
-                "frac": round(achieved / peak, 4), "traffic": recorded_traffic(), "peak_source": peak_kind,
+                "frac": round(achieved / peak, 4), "traffic": traffic, "traffic_source": traffic_note, "peak_source": peak_kind,
                 "frac_of_nominal_8TBps": round(achieved / 8000.0, 4), "kernel": "bdl::step_kernel<SGHMC,philox,recip,U=1,T=64>, one tile per CTA",
                 "algorithmic_bytes_per_launch": BYTES_PER_PARAM * n_dense, "kernel_ms": round(kernel_ms, 4)}
 
@@ -259,18 +286,29 @@ def run_ours(args):
         extras["reference_eager_gpu"] = guarded("reference_eager_gpu", eager_gpu_rate, lay, device)
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        cpu_baseline = guarded("cpu_baseline", cpu_port_rate, lay, seconds=args.cpu_seconds, with_eager=True)
+        port = guarded("cpu_baseline", cpu_port_rate, lay, seconds=args.cpu_seconds, with_eager=True)
+        ref = guarded("cpu_baseline(reference)", reference_cpu_rate, lay, args.cpu_seconds, 3, 1)
+        if ref and "error" not in ref:                       # the reference's own code is the baseline; the port is context
+            cpu_baseline = dict(ref, fused_c_port=port)
+        else:
+            cpu_baseline = dict(port, reference_error=ref)
+    if rank == 0 and world == 1 and not args.no_cfg1:
+        extras["cfg1_mlp_mnist_sgld"] = {"reference_cpu": guarded("cfg1 reference", cfg1_line, True, "cpu"),
+                                         "ours_b200": guarded("cfg1 ours", cfg1_line, False, device)}
 
+    ens = extras.get("ensemble")
+    if isinstance(e2e, dict) and isinstance(ens, dict) and "value" in ens:
+        # BASELINE.json's metric has a second half ("ensemble preds/s at 1/2/4/8 GPU"): the same end-to-end figure (host
+        # batches in, reference 5-tuple + calibration out) rides in e2e so that the per-N record carries it
+        e2e.update({"ensemble_preds_per_s": ens["value"], "ensemble_rows": ens["rows"], "ensemble_samples": ens["samples"],
+                    "ensemble_seconds": ens["seconds"], "ensemble_phases_rank0_ms": ens["phases_rank0_ms"],
+                    "ensemble_h2d_bytes": ens["h2d_bytes"], "ensemble_d2h_bytes": ens["d2h_bytes"]})
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": "params/s", "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic (random-init weights of the named shapes, g ~ N(0,1e-2^2))",
-            "config": {"workload": WORKLOAD, "hparams": "prior_sig=1.0,Ninflate=1e3,nd=1.0,momentum_decay=0.18,bias=informative",
-                       "lr": HP["lr_body"], "lr_head": HP["lr_head"], "ND": HP["ND"], "params_per_chain": n_dense,
-                       "chains": world, "parallelism": f"{world} independent chain(s), one per GPU, no data-path collective",
-                       "l2": "inputs (4.9 GB per step) larger than L2 (126 MB); no flush needed",
-                       "noise": "in-kernel Philox4x32-10 + Box-Muller", "division": "reciprocal (reference-on-CUDA semantics)"},
+            "config": bench_config(world, n_dense),
             "hbm_gbs": achieved * 1.0, "roofline": roofline, "e2e": e2e, "gpu_launches": K, "clocks": clocks,
             "cpu_baseline": cpu_baseline,
         }
@@ -400,32 +438,30 @@ def variant_rates(lay, theta, g, theta0, v, runs_dev, nruns, device, world, peak
                      "achieved_gbs_per_gpu": gbs, "frac_of_measured_peak": gbs / peak}
     out["mc_dropout_mix_bias_gaussian"]["runs"] = dr_n
     # the shape Runner.train() actually launches: one run per tensor, each row pointing at that tensor's own
-    # (separately allocated) autograd gradient -- no flat gradient buffer, no gather pass
-    del m, s2, buf
+    # (separately allocated) autograd gradient -- no flat gradient buffer, no gather pass (step_table_kernel)
+    del buf
     grads = [torch.randn(sg.numel, device=device) * 1e-2 for sg in lay.segments]
     ok = all(t.data_ptr() % 16 == 0 for t in grads)
     tab = lay.run_table("informative", grad_ptrs=[t.data_ptr() for t in grads])
     rd, nr = ops.upload_runs(tab, device)
-    sc = make_scalars(_lib.SGHMC)
-
-    def one_ptr(i):
-        ops.step(_lib.SGHMC, theta, None, theta0, v, None, None, None, rd, nr, sc, ops.make_noise(seed=seed, subseq=2000 + i))
-    for i in range(3):
-        one_ptr(i)
-    barrier(world)
-    torch.cuda.synchronize()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for i in range(steps):
-        one_ptr(3 + i)
-    e1.record()
-    torch.cuda.synchronize()
-    ms = allmax(e0.elapsed_time(e1), world, device) / steps
-    gbs = 24 * n_dense / (ms * 1e-3) / 1e9
-    out["sghmc_per_tensor_gradient_pointers"] = {
-        "params_per_s": world * n_dense / (ms * 1e-3), "ms_per_step": ms, "bytes_per_param": 24, "achieved_gbs_per_gpu": gbs,
-        "frac_of_measured_peak": gbs / peak, "runs": nr, "aligned": ok,
-        "note": "run table with one row per tensor carrying that tensor's p.grad address (the training-loop launch)"}
+    sc_s = make_scalars(_lib.SGHMC)
+    sc_a = ops.make_scalars(_lib.ADAM_CSGHMC, lr_body=HP["lr_body"], lr_head=HP["lr_head"], ND=HP["ND"], Ninflate=HP["Ninflate"],
+                            prior_sig=HP["prior_sig"], nd=HP["nd"], alpha=0.05, t=10, div_mode=_lib.DIV_RECIP)
+    s2.fill_(1e-6)
+    m.zero_()
+    ptr_cases = [("sghmc_per_tensor_gradient_pointers", 24,
+                  lambda i: ops.step(_lib.SGHMC, theta, None, theta0, v, None, None, None, rd, nr, sc_s,
+                                     ops.make_noise(seed=seed, subseq=2000 + i))),
+                 ("adam_csghmc_per_tensor_gradient_pointers", 40,
+                  lambda i: ops.step(_lib.ADAM_CSGHMC, theta, None, theta0, v, m, s2, None, rd, nr, sc_a,
+                                     ops.make_noise(seed=seed, subseq=8000 + i)))]
+    for name, bpp, fn in ptr_cases:
+        ms = timed(fn)
+        gbs = bpp * n_dense / (ms * 1e-3) / 1e9
+        out[name] = {"params_per_s": world * n_dense / (ms * 1e-3), "ms_per_step": ms, "bytes_per_param": bpp,
+                     "achieved_gbs_per_gpu": gbs, "frac_of_measured_peak": gbs / peak, "frac_of_nominal_8TBps": gbs / 8000.0,
+                     "runs": nr, "aligned": ok, "kernel": "bdl::step_table_kernel",
+                     "note": "run table with one row per tensor carrying that tensor's p.grad address (the training-loop launch)"}
     return out
 
 
@@ -586,8 +622,109 @@ def train_step_extra(device, rank, world, steps=6, batch=64, backbone="vit_l_32"
 
 
 def ensemble_extra(device, rank, world, args):
+    """BASELINE.json configs[4] through the Runner API: ``csgld.Runner.evaluate()`` with hparams ``eval_shard=1`` on a
+    ResNet-101 (K=37), 8 cycles x nst 5 = 40 posterior samples re-drawn for every batch (Appendix B.6), N = 3 669 rows
+    (Pets test size) in batches of 64 from pinned host memory, then ECE / MCE / NLL with the rows sharded over the ranks
+    and ONE all-reduce of the bin statistics.  preds/s = rows * samples / wall time (max over ranks); the per-phase split
+    is device time from CUDA events on rank 0."""
+    import argparse as ap
+    import logging
+    from bayesdll_b200 import calibration, ops, shapes
     from bayesdll_b200 import dist as bdist
-    return bdist.bench_sharded_ensemble(device, rank, world, rows=args.ensemble_rows, batch=64, cycles=8, nst=5)
+    from bayesdll_b200.methods import csgld
+    rows, batch, cycles, nst = args.ensemble_rows, 64, 8, 5
+    torch.manual_seed(7)                                     # same weights and per-cycle statistics on every rank
+    with torch.device(device):
+        net = shapes.create_backbone("resnet101", 37)
+    x_host = torch.randn(batch, 3, 224, 224, generator=torch.Generator().manual_seed(5)).pin_memory()
+    # one training-mode pass with momentum 1 sets the BatchNorm running statistics to those of a synthetic batch, so the
+    # random-init network yields finite O(1) logits in eval mode (running stats are buffers, not sampled)
+    for mod in net.modules():
+        if isinstance(mod, torch.nn.modules.batchnorm._BatchNorm):
+            mod.momentum = 1.0
+    net.train()
+    with torch.no_grad():
+        net(x_host.to(device))
+    net.eval()
+    a = ap.Namespace(device=device, ND=3680, lr=1e-4, lr_head=1e-2, momentum=0.5, epochs=8, pretrained=None,
+                     num_classes=37, ece_num_bins=15, test_eval_freq=1, log_dir=tempfile.gettempdir(), seed=42,
+                     num_cycles=cycles, proportion_exploration=0.5, full_sample=False,
+                     hparams=dict(prior_sig="1.0", Ninflate="1.0", nd="0.01", thin="10", bias="informative", nst=str(nst),
+                                  seed="42", eval_shard="1"))
+    lg = logging.getLogger("bench.ensemble")
+    lg.addHandler(logging.NullHandler())
+    lg.propagate = False
+    runner = csgld.Runner(net, None, a, lg)
+    n = sum(p.numel() for p in runner.net.parameters())
+    gen = torch.Generator(device=device).manual_seed(11)
+    with torch.no_grad():
+        theta = torch.nn.utils.parameters_to_vector(runner.net.parameters())
+    m1, m2 = {}, {}
+    for c in range(1, cycles + 1):                           # synthetic per-cycle posterior statistics (dense, checkpoint layout)
+        mean = theta + 1e-3 * torch.randn(n, device=device, generator=gen)
+        m1[c] = mean
+        m2[c] = mean * mean + 1e-6 * torch.rand(n, device=device, generator=gen)
+    runner.cycle_theta_mom1, runner.cycle_theta_mom2 = m1, m2
+    del m1, m2, theta
+    runner.samples_per_cycle = {c: nst for c in range(1, cycles + 1)}
+    runner.cycle_likelihoods = {c: [0.5] * nst for c in range(1, cycles + 1)}
+    runner.current_cycle = cycles
+    y_all = torch.randint(0, 37, (rows,), generator=torch.Generator().manual_seed(3))
+    loader = [(x_host[:len(y_all[i:i + batch])], y_all[i:i + batch].pin_memory()) for i in range(0, rows, batch)]
+    runner.evaluate(loader[:2] + loader[-1:])                # warm-up (cuDNN autotune, allocator, both batch shapes)
+    barrier(world)
+    torch.cuda.synchronize()
+    runner.profile_eval = True
+    t0 = time.perf_counter()
+    loss, err, targets, logits, logits_all = runner.evaluate(loader)
+    t_eval = time.perf_counter() - t0
+    ece, mce, nll = bdist.calibrate_sharded(targets, logits, a.ece_num_bins, device, rank, world)
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    dt_max = allmax(dt, world, device)
+    S = cycles * nst
+    phases = dict(runner.eval_phases)
+    phases["calibrate_ms"] = (dt - t_eval) * 1e3
+    phases["wall_ms"] = dt * 1e3
+    # the same numbers the unsharded host API gives (every rank holds the full logits): bin counts must be identical
+    e1, m1_, n1 = calibration.analyze(targets, logits, a.ece_num_bins, None)
+    _, _, _, _, sizes = calibration.calc_bins(targets, logits, a.ece_num_bins)
+    # context: cost of materialising ONE posterior sample, ours (bdl_draw) vs the reference's structure on this GPU
+    # (deepcopy(net) + randn_like / sqrt / mul / add / copy_ per tensor, methods/csgld.py:404-413)
+    lay = runner.model.chain.layout
+    c1, c2 = runner._cyc1[1], runner._cyc2[1]
+    out = torch.empty_like(c1)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for i in range(10):
+        ops.draw(c1, c2, out, ops.VAR_FROM_MOMENTS, 1.25, ops.make_noise(seed=42, subseq=i, stream_id=2))
+    torch.cuda.synchronize()
+    ours_draw_ms = (time.perf_counter() - t0) / 10 * 1e3
+    import copy
+    mean_views, var_views = lay.views(c1), lay.views(torch.clamp(c2 - c1 ** 2, min=1e-12))
+    t0 = time.perf_counter()
+    for i in range(3):
+        with torch.no_grad():
+            net_sample = copy.deepcopy(runner.net)
+            for p_, p_mean, p_var in zip(net_sample.parameters(), mean_views, var_views):
+                p_.copy_(p_mean + p_var.sqrt() * torch.randn_like(p_))
+    torch.cuda.synchronize()
+    ref_draw_ms = (time.perf_counter() - t0) / 3 * 1e3
+    del net_sample
+    runner.flush_io()
+    return {"metric": "ensemble preds/s (ResNet-101 cSGLD 40-sample posterior-predictive ensemble + ECE/MCE/NLL)",
+            "value": rows * S / dt_max, "unit": "preds/s", "rows": rows, "samples": S, "batch": batch, "seconds": dt_max, "n_gpus": world,
+            "api": "bayesdll_b200.methods.csgld.Runner.evaluate(loader) with hparams eval_shard=1 (5-tuple incl. logits_all "
+                   f"{list(logits_all.shape)}), then row-sharded ECE/MCE/NLL",
+            "sharding": "samples dealt round-robin (cycle*nst + s); one all-gather of the local sample logits, one "
+                        "all-reduce of the 3*M+2 bin statistics",
+            "phases_rank0_ms": phases, "h2d_bytes": sum(x.numel() * 4 + y.numel() * 8 for x, y in loader),
+            "d2h_bytes": int(targets.nbytes + logits.nbytes + logits_all.nbytes),
+            "ece": float(ece), "mce": float(mce), "nll": float(nll), "loss": float(loss), "err": float(err),
+            "ece_unsharded": float(e1), "bin_sizes": [int(v) for v in sizes],
+            "draw_ms": ours_draw_ms, "reference_structure_draw_ms": ref_draw_ms,
+            "note": "per-sample cost = 1 draw kernel (12 B/param) + PyTorch fp32 forward of 64 images (CUDA-graph replay); "
+                    "samples re-drawn for every batch as the reference does (Appendix B.6)"}
 
 
 # ------------------------------------------------------------------------------------------------------------
@@ -675,9 +812,15 @@ def eager_rate(lay, cores, max_params=64 << 20):
 
 
 def eager_gpu_rate(lay, device, reps=3):
-    """The reference's own structure on the SAME B200: per-tensor eager loop + SGD.step (baseline/eager_port.py restating
-    methods/sghmc.py:482-510, :229) over all 296 ViT-L/32 tensors.  This is the number the fused kernel replaces
-    ('reference on the same B200')."""
+    """The reference's own structure on the SAME B200 ('reference on the same B200'): the unmodified
+    methods/sghmc.py Model.forward + optimizer.step() over all 296 ViT-L/32 tensors when a reference tree is present,
+    else its restatement baseline/eager_port.py.  This is the number the fused kernel replaces."""
+    from baseline import reference_arm
+    if reference_arm.available() is not None:
+        named = [(sg.name, sg.shape) for sg in lay.segments]
+        r = reference_arm.sghmc_update_rate(named, lay.readout_name, device, steps=reps, warmup=2, hp=HP)
+        r["kernel_launches_per_step"] = "~12 eager kernels x 296 tensors"
+        return r
     from baseline import eager_port
     names = [s.name for s in lay.segments]
     gen = torch.Generator(device=device).manual_seed(1)
@@ -696,33 +839,57 @@ def eager_gpu_rate(lay, device, reps=3):
     e1.record()
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / reps
-    return {"value": lay.n_dense / (ms * 1e-3), "unit": "params/s", "ms_per_step": ms, "steps": reps,
+    return {"value": lay.n_dense / (ms * 1e-3), "unit": "params/s", "ms_per_step": ms, "steps": reps, "kind": "port",
             "kernel_launches_per_step": "~12 eager kernels x 296 tensors",
             "sample": "per-tensor torch-eager SGHMC loop + SGD step on cuda:0, all 296 ViT-L/32 tensors (baseline/eager_port.py)"}
 
 
+def reference_cpu_rate(lay, seconds, steps, warmup):
+    """The reference's OWN code on the host cores (kind "reference"), or None when no reference tree exists
+    (neither /root/reference nor baseline/_ref)."""
+    from baseline import reference_arm
+    if reference_arm.available() is None:
+        return None
+    named = [(sg.name, sg.shape) for sg in lay.segments]
+    return reference_arm.sghmc_update_rate(named, lay.readout_name, "cpu", steps=steps, warmup=warmup, hp=HP, seconds=seconds)
+
+
 def run_reference(args):
-    """The reference arm: the CPU implementation of the path (fused C port; the reference itself is Python and cannot
-    travel to the GPU box).  Rank 0 only."""
+    """The reference arm: the reference's own CPU implementation of the path on the host cores -- its unmodified
+    methods/sghmc.py Model.forward + optimizer.step() (kind "reference") when a reference tree is present, the fused C port
+    (kind "port") otherwise.  Rank 0 only; every step is a bounded sample of the workload."""
     rank = env_int("RANK", 0)
     if rank != 0:
         return
     lay = build_layout()
     K, W = args.steps, max(args.warmup, 1)
-    res = cpu_port_rate(lay, seconds=args.ref_seconds, steps=K, warmup=W)
+    res = guarded("reference arm", reference_cpu_rate, lay, args.ref_seconds, K, W)
+    if not res or "error" in res:
+        res = cpu_port_rate(lay, seconds=args.ref_seconds, steps=K, warmup=W)
+    world = env_int("WORLD_SIZE", 1)
     line = {
-        "impl": "reference", "metric": METRIC, "value": res["value"], "unit": "params/s", "n_gpus": env_int("WORLD_SIZE", 1),
+        "impl": "reference", "metric": METRIC, "value": res["value"], "unit": "params/s", "n_gpus": world,
         "steps": K, "warmup": W, "ms_per_step": res["ms_per_step"], "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "sample": res["sample"]},
-        "cpu_baseline": {"value": res["value"], "unit": "params/s", "cores": res["cores"], "kind": "port", "sample": res["sample"]},
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic (random-init weights of the named shapes, g ~ N(0,1e-2^2))",
+        "config": bench_config(world, lay.n_dense),
+        "cpu_baseline": {"value": res["value"], "unit": "params/s", "cores": res["cores"], "kind": res["kind"], "sample": res["sample"]},
         "e2e": {"value": res["value"], "unit": "params/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-        "gpu_launches": 0,
+        "gpu_launches": 0, "sample_params_per_step": res["n"],
     }
+    if not args.no_cfg1:
+        line["cfg1_mlp_mnist_sgld"] = {"reference_cpu": guarded("cfg1", cfg1_line, True, "cpu")}
     print(json.dumps(line), flush=True)
 
 
+def cfg1_line(reference, device):
+    from baseline import reference_arm
+    if reference and reference_arm.available() is None:
+        return {"unavailable": "no reference tree (/root/reference or baseline/_ref)"}
+    return reference_arm.cfg1_mlp_mnist(device=device, reference=reference)
+
+
 def main():
+    os.environ.setdefault("TQDM_DISABLE", "1")              # the Runners' progress bars would flood stderr
     # NCCL prints its version banner / debug lines to stdout by default; rank 0's stdout must carry the JSON line only
     os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
     ap = argparse.ArgumentParser()
@@ -733,7 +900,8 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=10)
     ap.add_argument("--cpu-seconds", type=float, default=15.0)
     ap.add_argument("--ref-seconds", type=float, default=60.0)
-    ap.add_argument("--ensemble-rows", type=int, default=512)
+    ap.add_argument("--ensemble-rows", type=int, default=3669, help="Pets test-set size (BASELINE.json configs[4])")
+    ap.add_argument("--no-cfg1", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-train-step", action="store_true")
     ap.add_argument("--no-ensemble", action="store_true")

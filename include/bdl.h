@@ -62,8 +62,12 @@ typedef struct {
     uint64_t end;          /* one past the last element incl. padding, multiple of 4               */
     uint64_t valid_end;    /* begin + number of real elements; [valid_end, end) is padding         */
     const float* g_dev;    /* optional per-run gradient tensor (element 0 <-> flat index `begin`,   */
-                           /* 16-byte aligned, readable up to the next 16-byte boundary past its    */
-                           /* end); NULL -> read the flat gradient buffer                           */
+                           /* 16-byte aligned, READABLE up to the next 16-byte boundary past its    */
+                           /* end: the tail group is fetched as one 128-bit load and the lanes past */
+                           /* valid_end are zeroed in registers.  Any allocator with >= 16-byte      */
+                           /* granularity (cudaMalloc: 256 B, torch's caching allocator: 512 B)     */
+                           /* satisfies this; a sub-allocated view ending at the very end of a       */
+                           /* mapping with numel % 4 != 0 does not); NULL -> flat gradient buffer   */
     uint32_t cls;          /* BDL_CLS_* bits                                                       */
     uint32_t reserved;
 } bdl_run;
@@ -124,7 +128,9 @@ const char* bdl_last_error(void);
 
 /* Optional launch tuning for bdl_step (0 = library default: one tile per CTA, 64-256 threads depending on the
  * variant, 1 float4 group per thread).  ctas_per_sm > 0 caps the grid at #SM * ctas_per_sm persistent CTAs.  Used by bench sweeps and by the
- * launch-shape-independence tests; not needed for correctness. */
+ * launch-shape-independence tests; not needed for correctness.  The setting is THREAD-LOCAL: it affects the launches of the
+ * calling thread only, so the library stays re-entrant across threads / devices.  An explicit shape always runs the
+ * generic build of the kernel (never the lean kFast / run-table builds). */
 int bdl_set_launch_config(int ctas_per_sm, int unroll, int threads);
 
 /* (a1..a5) One fused sampler update over the whole flat state: prior pull, friction/momentum,
@@ -187,7 +193,7 @@ int bdl_moments_welford(const float* theta_dev, float* mean_dev, float* m2_dev, 
  * bulk copies (cp.async.bulk global->shared->global).  Replaces theta_vec.clone() into a dict
  * (methods/csgld.py:278-279). */
 int bdl_capture_ring(const float* theta_dev, float* ring_dev, uint64_t slot, uint64_t n, void* stream);
-/* Tuning: 16 KiB chunks copied by one CTA of the ring kernel (default 4). */
+/* Tuning: 16 KiB chunks copied by one CTA of the ring kernel (default 4); thread-local like bdl_set_launch_config. */
 int bdl_set_ring_config(int chunks_per_cta);
 
 /* (a9) Posterior draw theta_s = mean + sqrt(var) * eps (methods/sgld.py:292-297, csgld.py:404-413).

@@ -1,11 +1,13 @@
 """Loader + injection harness for the *real* reference (omarezz46/BayesDLL).
 
-TEST INFRASTRUCTURE ONLY.  Nothing under ``bayesdll_b200/`` may import this.
+TEST / BASELINE INFRASTRUCTURE ONLY.  Nothing under ``bayesdll_b200/`` may import this.
 It is used in the build container (where ``/root/reference`` is mounted) by
 ``oracle/make_golden.py`` to run the reference's own PyTorch code on injected
-gradients / injected noise and record golden vectors under ``tests/golden/``.
-The reference does not exist on the GPU box, so nothing in ``tests -m gpu``,
-``smoke()`` or ``bench.py`` imports this module.
+gradients / injected noise and record golden vectors under ``tests/golden/``, and by
+``baseline/reference_arm.py`` (bench.py's reference arm / cpu_baseline legs) to TIME the
+unmodified reference.  ``/root/reference`` does not exist on the GPU box: there the loader
+finds the install ``baseline/install_ref.py`` leaves in ``baseline/_ref/`` (git-ignored, travels
+with the gpurun snapshot); nothing in ``tests -m gpu`` or ``smoke()`` needs it.
 
 Two shims are needed to import the reference unmodified:
   * a stub ``matplotlib`` (imported at calibration.py:14-15, only used by the plots)
@@ -22,11 +24,16 @@ import torch
 import torch.nn as nn
 
 
+_REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
 def find_reference():
-    for cand in (os.environ.get("BDL_REF"), "/root/reference"):
+    """$BDL_REF, the mounted checkout, then the install under baseline/_ref/  -- in that order."""
+    for cand in (os.environ.get("BDL_REF"), "/root/reference", os.path.join(_REPO, "baseline", "_ref")):
         if cand and os.path.isfile(os.path.join(cand, "methods", "sghmc.py")):
             return cand
-    raise FileNotFoundError("reference checkout not found (set $BDL_REF or mount /root/reference)")
+    raise FileNotFoundError("reference not found: set $BDL_REF, mount /root/reference, or run baseline/install_ref.py "
+                            "where the checkout is mounted (it fills baseline/_ref/)")
 
 
 def _install_matplotlib_stub():
@@ -188,3 +195,28 @@ class GradInjectNet(nn.Module):
 
 def identity_criterion(out, y):
     return out
+
+
+class _HandOutGrads(torch.autograd.Function):
+    """forward: a scalar; backward: hands every parameter its prepared gradient tensor, no arithmetic at all."""
+
+    @staticmethod
+    def forward(ctx, holder, *params):
+        ctx.holder = holder
+        return params[0].new_zeros(())
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        return (None,) + tuple(ctx.holder.grads)
+
+
+class TimedInjectNet(GradInjectNet):
+    """GradInjectNet for TIMING the reference's update loop: the forward / backward pair costs
+    nothing but autograd's bookkeeping (one clone of each prepared gradient by AccumulateGrad, 8 B/param), so the time of
+    the reference's unmodified ``Model.forward`` + ``optimizer.step()`` is the time of its per-tensor update statements."""
+
+    def set_grads(self, grads):
+        self.grads = list(grads)
+
+    def forward(self, x):
+        return _HandOutGrads.apply(self, *self.parameters())
