@@ -17,6 +17,7 @@ from .flat import FlatLayout, adopt_parameters, alloc_flat
 _RUN_DTYPE = np.dtype([("begin", "<u8"), ("end", "<u8"), ("valid_end", "<u8"), ("g_dev", "<u8"), ("cls", "<u4"),
                        ("reserved", "<u4")])
 assert _RUN_DTYPE.itemsize == C.sizeof(_lib.Run)
+_PTABLE_ROWS = 512          # bdl_step.cu kPRows: tables up to this size ride in the kernel arguments
 
 
 class ChainState:
@@ -143,8 +144,11 @@ class ChainState:
             base_cls = rows["cls"] & ~np.uint32(_lib.CLS_SKIP)
             rows["cls"] = np.where(skip, base_cls | np.uint32(_lib.CLS_SKIP), base_cls)
             self._had_skip = bool(n_none)
-        # unchanged table (gradients at fixed addresses, e.g. a CUDA-graph-captured backward): the copy on the device is
-        # still valid
+        if len(rows) <= _PTABLE_ROWS and self.layout.n_padded < 2 ** 32:
+            # the table travels inside the kernel arguments (step_ptable_kernel): nothing to stage on the device
+            return None, len(rows)
+        # larger tables live in device memory.  Unchanged table (gradients at fixed addresses, e.g. a CUDA-graph-captured
+        # backward): the copy on the device is still valid
         sig = rows.tobytes()
         if sig == self._table_sig:
             return self._run_dev[self._run_slot], len(rows)
@@ -186,17 +190,21 @@ class ChainState:
     def update(self, scalars, capture=None):
         """Apply one fused update using the gradients currently held in ``p.grad``.  ``capture`` (ops.make_capture)
         folds the new theta into running moments in the same launch."""
+        runs_host = None
         if self.grad_mode == "table":
             runs_dev, nruns = self._gradient_table()
+            runs_host = self._run_np.ctypes.data            # host copy: small tables ride in the kernel arguments
             g = self.g_flat
         else:
             runs_dev, nruns = self._gradient_flat()
             g = self.g_flat
+            if runs_dev is None or not hasattr(runs_dev, "_bdl_host"):
+                runs_host = self._run_np.ctypes.data        # fell back to the per-tensor table (a gradient was None)
         scalars.div_mode = self.div_mode
         if self.buf is not None:
             scalars.first_step = int(self.sgd_steps == 0)
         ops.step(self.variant, self.theta, g, self.theta0, self.v, self.m, self.s, self.buf, runs_dev, nruns,
-                 scalars, self._noise(), capture=capture)
+                 scalars, self._noise(), capture=capture, runs_host=runs_host)
         self.step_count += 1
         self.sgd_steps += 1
 

@@ -34,6 +34,8 @@ namespace bdl {
 
 constexpr int kInlineRuns = 8;
 
+struct PTable;
+
 struct StepParams {
     float* theta;
     const float* g;
@@ -63,7 +65,25 @@ struct StepParams {
     float cap_a, cap_b, cap_inv;   // avg: cnt, cnt+1, 1/(cnt+1);  Welford: n, -, 1/n
     int cap_init, cap_kind;
     NoiseKey key;
+    const PTable* ptab;        // HOST pointer (launch plumbing only, never dereferenced on the device): table for step_ptable_kernel
 };
+
+// Run table carried INSIDE the kernel arguments (constant bank; CUDA >= 12.1 allows 32 KB of parameters on sm_70+): the
+// launch Runner.train() makes has <= 512 rows for every backbone of the reference (ViT-L/32: 296, ResNet-101: 314), so
+// rows and a coarse directory (first run of every 2^dir_shift groups) fit: the per-CTA lookup becomes a few uniform
+// constant loads instead of a 32-ary search through L1/L2, and no table has to be staged to the device at all.
+constexpr int kPRows = 512;
+constexpr int kPDir = 5120;
+struct PTable {
+    uint32_t nrows, dir_shift;
+    uint32_t end4[kPRows];         // run end, in float4 groups
+    uint32_t tail_q[kPRows];       // group holding the tensor's last real elements when numel % 4 != 0 (own gradient), else 0xFFFFFFFF
+    uint64_t gbase[kPRows];        // address A such that the gradient of flat element i is ((const float*)A)[i]
+    uint8_t cls[kPRows];
+    uint8_t tail_n[kPRows];        // real elements in the tail group (1..3)
+    uint16_t dir[kPDir];           // dir[j] = first run whose end is beyond group (j << dir_shift)
+};
+static_assert(sizeof(PTable) < 24 * 1024, "PTable + StepParams must stay well inside the 32 KB kernel-parameter space");
 
 struct RunCursor {
     uint32_t idx;
@@ -553,6 +573,95 @@ step_table_kernel(const StepParams p) {
 }
 
 // -------------------------------------------------------------------------------------------
+// The same launch with the run table in the kernel arguments (PTable): preferred whenever the host copy of the table is
+// at hand and fits (every backbone of the reference).  Control flow as step_table_kernel, lookup = directory entry +
+// forward scan over uniform constant loads; no shared memory, no barrier.
+// -------------------------------------------------------------------------------------------
+#ifndef BDL_PTABLE_TPC
+#define BDL_PTABLE_TPC 1   // profiles/r02_ab_builds_ptable.log: 1 tile per CTA 1.038 / 1.773 ms (= the flat launch), 2: 1.047 / 1.796, 4: 1.056 / 1.809 (SGHMC / Adam-cSGHMC)
+#endif
+constexpr int kPTableTpc = BDL_PTABLE_TPC;
+
+template <int kVariant, bool kHasBuf, bool kPhilox, int kDiv, int kT, int kCap = 0>
+__global__ void __launch_bounds__(kT, BDL_TABLE_BLOCKS(kVariant, kHasBuf, kPhilox, 1, kT, kCap))
+step_ptable_kernel(const __grid_constant__ StepParams p, const __grid_constant__ PTable t) {
+    constexpr uint32_t cta_groups = kT * kPTableTpc;
+    const uint32_t q_cta = blockIdx.x * cta_groups;          // < n4 for every launched CTA (whole range, q_begin == 0)
+    uint32_t q = q_cta + threadIdx.x;
+    TileRegs<kVariant, kHasBuf, kPhilox, kCap> r;
+    if (q < p.n4) tile_load(r, p, static_cast<uint64_t>(q) << 2);
+    uint32_t idx = t.dir[q_cta >> t.dir_shift];
+    while (q_cta >= t.end4[idx]) ++idx;                      // the last run ends at n4 > q_cta
+    const uint32_t end4 = t.end4[idx];
+    const uint32_t q_last = q_cta + cta_groups;
+    if (q_last <= p.n4 && (q_last < end4 || (q_last == end4 && t.tail_q[idx] == 0xFFFFFFFFu))) {
+        // ---- CTA-uniform: the whole span is real elements of ONE tensor ----
+        const uint32_t cls = t.cls[idx];
+        const bool live = (cls & BDL_CLS_SKIP) == 0;
+        const float* gbase = reinterpret_cast<const float*>(t.gbase[idx]);
+#pragma unroll
+        for (int k = 0; k < kPTableTpc; ++k, q += kT) {
+            const uint64_t i = static_cast<uint64_t>(q) << 2;
+            if (k > 0) tile_load(r, p, i);
+            if (live) {
+                r.g = ld_stream(gbase + i);
+                tile_update_store<kVariant, kHasBuf, kPhilox, kDiv, kCap>(r, p, q, i, cls);
+            }
+            if constexpr (kCap != 0) capture_fold<kCap, kDiv>(p, i, r.th, r.c1, r.c2);
+        }
+        return;
+    }
+    // ---- general: per-thread row index, advanced monotonically ----
+#pragma unroll 1
+    for (int k = 0; k < kPTableTpc; ++k, q += kT) {
+        if (q >= p.n4) break;
+        const uint64_t i = static_cast<uint64_t>(q) << 2;
+        if (k > 0) tile_load(r, p, i);
+        while (q >= t.end4[idx] && idx + 1 < t.nrows) ++idx;
+        const uint32_t cls = t.cls[idx];
+        if ((cls & BDL_CLS_SKIP) == 0) {
+            r.g = ld_stream(reinterpret_cast<const float*>(t.gbase[idx]) + i);
+            if (q == t.tail_q[idx]) {                        // tail group of a tensor: lanes past its end are padding (g = 0)
+                const uint32_t tn = t.tail_n[idx];
+                if (tn < 2) r.g.y = 0.f;
+                if (tn < 3) r.g.z = 0.f;
+                r.g.w = 0.f;
+            }
+            tile_update_store<kVariant, kHasBuf, kPhilox, kDiv, kCap>(r, p, q, i, cls);
+        }
+        if constexpr (kCap != 0) capture_fold<kCap, kDiv>(p, i, r.th, r.c1, r.c2);
+    }
+}
+
+// Host: PTable from the host copy of a run table; false when it does not fit (then the device-table kernel runs).
+static bool build_ptable(PTable& t, const bdl_run* rows, uint32_t nruns, const float* g_flat, uint64_t n) {
+    if (nruns > static_cast<uint32_t>(kPRows) || n >= 0xFFFFFFFFull) return false;
+    const uint32_t n4 = static_cast<uint32_t>(n >> 2);
+    uint32_t shift = 10;
+    while (((n4 - 1) >> shift) >= static_cast<uint32_t>(kPDir)) ++shift;
+    t.nrows = nruns;
+    t.dir_shift = shift;
+    for (uint32_t r = 0; r < nruns; ++r) {
+        t.end4[r] = static_cast<uint32_t>(rows[r].end >> 2);
+        t.cls[r] = static_cast<uint8_t>(rows[r].cls);
+        const bool own = rows[r].g_dev != nullptr;
+        const uint32_t tn = own ? static_cast<uint32_t>(rows[r].valid_end & 3u) : 0u;   // the flat buffer carries its own (zero) padding
+        t.tail_n[r] = static_cast<uint8_t>(tn);
+        t.tail_q[r] = tn ? static_cast<uint32_t>(rows[r].valid_end >> 2) : 0xFFFFFFFFu;
+        t.gbase[r] = own ? reinterpret_cast<uint64_t>(rows[r].g_dev) - 4ull * rows[r].begin : reinterpret_cast<uint64_t>(g_flat);
+    }
+    if (t.end4[nruns - 1] != n4) return false;               // rows must cover [0, n)
+    uint32_t r = 0;
+    const uint32_t ndir = ((n4 - 1) >> shift) + 1;
+    for (uint32_t j = 0; j < ndir; ++j) {
+        const uint32_t q = j << shift;
+        while (q >= t.end4[r]) ++r;
+        t.dir[j] = static_cast<uint16_t>(r);
+    }
+    return true;
+}
+
+// -------------------------------------------------------------------------------------------
 // host side
 // -------------------------------------------------------------------------------------------
 // Launch-shape overrides (bdl_set_launch_config): per calling thread, so a sweep on one thread / device never changes
@@ -582,6 +691,15 @@ static int launch_shape(const StepParams& p, cudaStream_t st) {
     }
     if (grid > 0x7FFFFFFFull) grid = 0x7FFFFFFFull;
     if (grid == 0) return BDL_OK;
+    if constexpr (kAllowFast && kU == 1) {
+        if (p.ptab != nullptr && grid == ntiles) {               // per-tensor gradient pointers, table in the kernel arguments
+            constexpr uint32_t span = kT * kPTableTpc;
+            grid = (static_cast<uint64_t>(p.n4) + span - 1) / span;
+            step_ptable_kernel<kVariant, kHasBuf, kPhilox, kDiv, kT, kCap><<<static_cast<uint32_t>(grid), kT, 0, st>>>(p, *p.ptab);
+            return check_cuda(cudaGetLastError(), "step_ptable_kernel launch");
+        }
+    }
+    BDL_REQUIRE(p.runs != nullptr || p.inl_n != 0, BDL_ERR_INVALID, "bdl_step: this launch shape needs the run table in device memory");
     if (grid == ntiles && p.inl_n == 0 && !p.flat_g && table_tiles_per_cta() > 1) {
         // run table with per-tensor gradient pointers (the training-loop launch): the gradient load depends on the table
         // lookup.  A CTA that walks a few consecutive tiles pays the search and that late first load once.  Tables
@@ -679,8 +797,7 @@ int step_range(int variant, float* theta, const float* g, const float* theta0, f
     BDL_REQUIRE(variant >= BDL_SGLD && variant <= BDL_ADAM_CSGHMC, BDL_ERR_INVALID, "bdl_step: unknown variant %d", variant);
     if (n == 0 || q_begin >= q_end) return BDL_OK;   // empty state / empty range: nothing to do (pointers may be null)
     BDL_REQUIRE(theta && (runs || runs_host) && sc && nz, BDL_ERR_INVALID, "bdl_step: null theta/runs/scalars/noise");
-    BDL_REQUIRE(runs || nruns <= static_cast<uint32_t>(kInlineRuns), BDL_ERR_INVALID,
-                "bdl_step: a device run table is required for more than %d runs", kInlineRuns);
+    BDL_REQUIRE(runs || runs_host, BDL_ERR_INVALID, "bdl_step: run table required");
     BDL_REQUIRE(n % 4 == 0, BDL_ERR_INVALID, "bdl_step: n=%llu is not a multiple of 4", (unsigned long long)n);
     BDL_REQUIRE((n >> 2) < 0xFFFFFFFFull, BDL_ERR_INVALID, "bdl_step: n too large for 32-bit group index");
     BDL_REQUIRE(q_end <= (n >> 2), BDL_ERR_INVALID, "bdl_step: range end beyond n");
@@ -721,6 +838,16 @@ int step_range(int variant, float* theta, const float* g, const float* theta0, f
             }
         }
     }
+    // per-tensor gradient pointers + host copy of the table: carry the table in the kernel arguments (step_ptable_kernel)
+    static thread_local PTable ptab_storage;
+    p.ptab = nullptr;
+#ifndef BDL_NO_PTABLE
+    if (runs_host && !p.flat_g && q_begin == 0 && q_end == (n >> 2) && table_tiles_per_cta() == static_cast<uint32_t>(kDefaultTableTpc) &&
+        build_ptable(ptab_storage, runs_host, nruns, g, n))
+        p.ptab = &ptab_storage;
+#endif
+    BDL_REQUIRE(runs || p.ptab || p.inl_n, BDL_ERR_INVALID,
+                "bdl_step: a device run table is required (more than %d runs without a host copy that fits the kernel arguments)", kInlineRuns);
     p.n4 = static_cast<uint32_t>(q_end); p.q_begin = static_cast<uint32_t>(q_begin);
     for (int h = 0; h < 2; ++h) {
         p.lr[h] = sc->lr[h];

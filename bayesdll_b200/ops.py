@@ -149,18 +149,20 @@ def make_capture(kind, first, second, cnt, init=False):
 
 
 @_on_tensor_device
-def step(variant, theta, g, theta0, v, m, s, buf, runs_dev, nruns, scalars, noise, capture=None):
+def step(variant, theta, g, theta0, v, m, s, buf, runs_dev, nruns, scalars, noise, capture=None, runs_host=None):
     """One fused sampler update (bdl_step).  Tensors are padded-flat fp32 CUDA buffers; unused state may be
     None.  ``noise`` from make_noise(); ``runs_dev`` from upload_runs().  ``capture`` (make_capture) additionally folds
-    the new theta into running moments in the same pass (bdl_step_capture)."""
+    the new theta into running moments in the same pass (bdl_step_capture).  ``runs_host``: address (or ctypes array) of a
+    HOST copy of the run table -- with it a table of <= 512 rows travels inside the kernel arguments and ``runs_dev`` may
+    be None (default: the host copy upload_runs() attached to ``runs_dev``)."""
     n = theta.numel()
     for name, t in (("g", g), ("theta0", theta0), ("v", v), ("m", m), ("s", s), ("buf", buf)):
         if t is not None and t.numel() != n:
             raise BdlError(f"{name}: length {t.numel()} != theta length {n}")
     args = (int(variant), _ptr(theta, "theta"), _ptr(g, "g", allow_none=True), _ptr(theta0, "theta0", allow_none=True),
             _ptr(v, "v", allow_none=True), _ptr(m, "m", allow_none=True), _ptr(s, "s", allow_none=True),
-            _ptr(buf, "buf", allow_none=True), n, _ptr(runs_dev, "runs", torch.uint8), nruns,
-            getattr(runs_dev, "_bdl_host", None), C.byref(scalars), C.byref(noise))
+            _ptr(buf, "buf", allow_none=True), n, _ptr(runs_dev, "runs", torch.uint8, allow_none=runs_host is not None), nruns,
+            runs_host if runs_host is not None else getattr(runs_dev, "_bdl_host", None), C.byref(scalars), C.byref(noise))
     if capture is None:
         _lib.check(_lib.load().bdl_step(*args, _stream()), "bdl_step")
         return

@@ -44,6 +44,7 @@ import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+os.environ.setdefault("TQDM_DISABLE", "1")                  # before anything imports tqdm: the Runners' progress bars would flood stderr
 
 import numpy as np  # noqa: E402
 import torch  # noqa: E402
@@ -889,7 +890,6 @@ def cfg1_line(reference, device):
 
 
 def main():
-    os.environ.setdefault("TQDM_DISABLE", "1")              # the Runners' progress bars would flood stderr
     # NCCL prints its version banner / debug lines to stdout by default; rank 0's stdout must carry the JSON line only
     os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
     ap = argparse.ArgumentParser()

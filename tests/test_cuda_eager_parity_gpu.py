@@ -100,7 +100,7 @@ def test_fused_kernel_equals_torch_cuda_eager(cuda_device, variant_name, bias):
         runs_dev, nruns = chain._gradient_table()
         sc.first_step = int(chain.sgd_steps == 0)
         ops.step(variant, chain.theta, None, chain.theta0, chain.v, chain.m, chain.s, chain.buf, runs_dev, nruns, sc,
-                 ops.make_noise(xi=xi_flat))
+                 ops.make_noise(xi=xi_flat), runs_host=chain._run_np.ctypes.data)      # the launch ChainState.update makes
         chain.sgd_steps += 1
         torch.cuda.synchronize()
         pairs = {"theta": (chain.layout.views(chain.theta), [p.data for _, p in named])}
@@ -280,7 +280,7 @@ def test_parameters_without_gradient_are_left_untouched(cuda_device, variant_nam
         runs_dev, nruns = chain._gradient_table()
         assert chain.g_flat is None                               # nothing was gathered: every live gradient is read in place
         ops.step(variant, chain.theta, None, chain.theta0, chain.v, chain.m, chain.s, None, runs_dev, nruns, sc,
-                 ops.make_noise(xi=xi_flat))
+                 ops.make_noise(xi=xi_flat), runs_host=chain._run_np.ctypes.data)
     torch.cuda.synchronize()
     for (n_, p), th, vv in zip(named, chain.layout.views(chain.theta), chain.layout.views(chain.v)):
         assert torch.equal(th, p.data), n_

@@ -102,7 +102,11 @@ def test_step_ragged_layout_vs_oracle(cuda_device, variant_name, bias_mode, own_
         tab = lay.run_table(bias_mode)
         g_arg = T["g"]
     runs_dev, nruns = ops.upload_runs(tab, dev)
-    for div_name, div in (("true", _lib.DIV_IEEE), ("recip", _lib.DIV_RECIP)):
+    runs_dev_only, _ = ops.upload_runs(tab, dev)
+    del runs_dev_only._bdl_host        # no host copy: the table is searched in device memory (step_table_kernel / generic build)
+    # with the host copy a pointer table rides in the kernel arguments (step_ptable_kernel); both must give the oracle's bits
+    for (div_name, div), runs_dev in [(d, r) for d in (("true", _lib.DIV_IEEE), ("recip", _lib.DIV_RECIP))
+                                      for r in (runs_dev, runs_dev_only)]:
         for k, a in dict(theta=theta, v=v, m=m, s=s, buf=buf).items():
             T[k].copy_(torch.from_numpy(a))
         sc = ops.make_scalars(variant, lr_body=lrb, lr_head=lrh, ND=hp.ND, Ninflate=hp.Ninflate, prior_sig=hp.prior_sig,
@@ -189,7 +193,7 @@ def test_inline_run_table_equals_device_run_table(cuda_device, bias_mode):
 
 @pytest.mark.parametrize("variant_name", ["sgld", "sghmc", "csghmc", "adam_sghmc", "adam_csghmc"])
 @pytest.mark.parametrize("kind", ["avg", "avg_nomom2", "welford"])
-@pytest.mark.parametrize("own_g", [False, True])
+@pytest.mark.parametrize("own_g", [False, True, "device-table"])
 def test_fused_capture_equals_step_then_moments(cuda_device, variant_name, kind, own_g):
     """bdl_step_capture == bdl_step followed by bdl_moments_avg / bdl_moments_welford, bit for bit: first sample (init)
     and later samples, both division modes, in-kernel Philox, ragged layout, a tensor without gradient (BDL_CLS_SKIP:
@@ -218,6 +222,8 @@ def test_fused_capture_equals_step_then_moments(cuda_device, variant_name, kind,
     skip_idx = 5
     tab[skip_idx].cls |= _lib.CLS_SKIP                                  # this tensor has p.grad None
     runs_dev, nruns = ops.upload_runs(tab, dev)
+    if own_g == "device-table":     # no host copy: step_table_kernel searches the table in device memory; with it
+        del runs_dev._bdl_host      # (own_g is True) the pointer table rides in the kernel arguments (step_ptable_kernel)
     for div in (_lib.DIV_IEEE, _lib.DIV_RECIP):
         sc = ops.make_scalars(variant, lr_body=1e-3, lr_head=1e-2, ND=1840, Ninflate=3.0, prior_sig=0.9, nd=0.7, alpha=0.18,
                               mu=mu, t=4, first_step=False, add_noise=True, div_mode=div)

@@ -1,13 +1,17 @@
 # The round-end measurement pass (run on the GPU box through gpurun): GPU test suite, default bench, reference arm,
-# launch list of the profiled command and one ncu --set full capture of the draws / gradient-pointer step.
-# Outputs land in gpurun_out/; the summaries judged are copied to profiles/.
+# launch list of the profiled command and ncu --set full captures of the step builds and the draws.
+# Outputs land in gpurun_out/; the summaries judged are copied to profiles/ (and profiles/traffic.json is regenerated
+# from the capture with tools/traffic_from_ncu.py, which ties it to the build).
+R=${R:-r02}
 mkdir -p gpurun_out
 set -x
 python -m pytest tests -m gpu -x -q 2>&1 | grep -v "batch/s" | tail -4
-( time python bench.py ) > gpurun_out/bench_final6.json 2> gpurun_out/bench_final6.err; tail -4 gpurun_out/bench_final6.err
-python bench.py --impl reference > gpurun_out/bench_ref6.json 2> gpurun_out/bench_ref6.err
-python tools/show_variants.py gpurun_out/bench_final6.json
-PROF="python bench.py --steps 20 --warmup 3 --no-train-step --no-ensemble --no-cpu-baseline --no-e2e --no-variants --no-eager-gpu --no-sample-store"
-$PROF > gpurun_out/plain7.log 2>&1 && ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/r01j_launches.csv $PROF > gpurun_out/ncu_l7.log 2>&1
-python tools/run_draws.py > gpurun_out/plain_draws.log 2>&1 && ncu --set full --clock-control none --import-source on -k regex:'dropout_mix|draw_kernel|step_kernel' -s 8 -c 8 -o gpurun_out/r01j_draws_full python tools/run_draws.py > gpurun_out/ncu_d7.log 2>&1
-tail -2 gpurun_out/ncu_d7.log
+( time python bench.py ) > gpurun_out/${R}_bench_final.json 2> gpurun_out/${R}_bench_final.err; tail -4 gpurun_out/${R}_bench_final.err
+python bench.py --impl reference --steps 20 --warmup 5 > gpurun_out/${R}_bench_ref_final.json 2> gpurun_out/${R}_bench_ref_final.err
+python tools/show_variants.py gpurun_out/${R}_bench_final.json
+PROF="python bench.py --steps 20 --warmup 3 --no-train-step --no-ensemble --no-cpu-baseline --no-e2e --no-variants --no-eager-gpu --no-sample-store --no-cfg1"
+$PROF > gpurun_out/${R}_plain.log 2>&1 && ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/${R}_launches.csv $PROF > gpurun_out/${R}_ncu_launches.log 2>&1
+python tools/run_steps.py --generic > gpurun_out/${R}_plain_steps.log 2>&1 && ncu --set full --clock-control none --import-source on -k regex:'step_kernel|step_table_kernel' -s 8 -c 12 -o gpurun_out/${R}_steps_full python tools/run_steps.py --generic > gpurun_out/${R}_ncu_steps.log 2>&1
+tail -2 gpurun_out/${R}_ncu_steps.log
+python tools/run_draws.py > gpurun_out/${R}_plain_draws.log 2>&1 && ncu --set full --clock-control none --import-source on -k regex:'dropout_mix|draw_kernel' -s 6 -c 6 -o gpurun_out/${R}_draws_full python tools/run_draws.py > gpurun_out/${R}_ncu_draws.log 2>&1
+tail -2 gpurun_out/${R}_ncu_draws.log
