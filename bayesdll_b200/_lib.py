@@ -11,7 +11,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("BDL_LIB_PATH") or os.path.join(HERE, "libbdl.so")   # BDL_LIB_PATH: A/B builds (tools/ab_builds.py)
 
 # ---- enums / constants (include/bdl.h) -------------------------------------------------------
-BDL_ABI_VERSION = 5
+BDL_ABI_VERSION = 6
 SGLD, SGHMC, CSGHMC, ADAM_SGHMC, ADAM_CSGHMC = range(5)
 VARIANT_NAMES = {SGLD: "sgld", SGHMC: "sghmc", CSGHMC: "csghmc", ADAM_SGHMC: "adam_sghmc",
                  ADAM_CSGHMC: "adam_csghmc"}
@@ -64,6 +64,9 @@ SIGNATURES = {
     "bdl_step": [_I32, _P, _P, _P, _P, _P, _P, _P, _U64, _P, _U32, _P, C.POINTER(Scalars), C.POINTER(Noise), _P],
     "bdl_step_capture": [_I32, _P, _P, _P, _P, _P, _P, _P, _U64, _P, _U32, _P, C.POINTER(Scalars), C.POINTER(Noise),
                          C.POINTER(Capture), _P],
+    "bdl_step_gradnorm": [_I32, _P, _P, _P, _P, _P, _P, _P, _U64, _P, _U32, C.POINTER(Scalars), C.POINTER(Noise), _P, _P],
+    "bdl_clip_coef": [_P, _F, _P, _P, _P],
+    "bdl_step_clipped": [_I32, _P, _P, _P, _P, _P, _P, _P, _U64, _P, _U32, C.POINTER(Scalars), C.POINTER(Noise), _P, _P],
     "bdl_philox_normal": [_P, _U64, _U64, _U32, _U64, _P],
     "bdl_moments_avg": [_P, _P, _P, _U64, _F, _F, _I32, _I32, _P],
     "bdl_moments_welford": [_P, _P, _P, _U64, _F, _I32, _I32, _P],

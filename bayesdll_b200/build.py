@@ -14,7 +14,9 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "libbdl.so")
-SOURCES = ["bdl_api.cu", "bdl_step.cu", "bdl_capture.cu", "bdl_draw.cu", "bdl_predict.cu", "bdl_host.cu", "bdl_selftest.cu"]
+STEP_INSTANCES = ["sgld", "sgld_buf", "sghmc", "csghmc", "adam_sghmc", "adam_sghmc_buf", "adam_csghmc"]
+# the slowest units first: they are compiled in parallel and the Adam kernels take longest
+SOURCES = [f"bdl_step_inst_{v}.cu" for v in reversed(STEP_INSTANCES)] + ["bdl_api.cu", "bdl_step.cu", "bdl_capture.cu", "bdl_draw.cu", "bdl_predict.cu", "bdl_host.cu", "bdl_selftest.cu"]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",

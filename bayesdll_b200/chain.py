@@ -187,9 +187,33 @@ class ChainState:
         raise ValueError(f"unknown noise mode {self.noise_mode!r} (philox | torch)")
 
     # ---- the fused update --------------------------------------------------------------------
-    def update(self, scalars, capture=None):
+    CLIPPED_VARIANTS = (_lib.SGLD, _lib.ADAM_CSGHMC)   # the runners whose clipped p.grad reaches theta (csgld, adam_csghmc)
+
+    def update(self, scalars, capture=None, clip=None):
         """Apply one fused update using the gradients currently held in ``p.grad``.  ``capture`` (ops.make_capture)
-        folds the new theta into running moments in the same launch."""
+        folds the new theta into running moments in the same launch.  ``clip`` = args.clip_grad: the reference's
+        ``clip_grad_norm_(net.parameters(), clip)`` between Model.forward and optimizer.step() (methods/csgld.py:250-251),
+        as two passes with the coefficient kept on the device (no host sync)."""
+        if clip is not None and self.variant in self.CLIPPED_VARIANTS:
+            if capture is not None:
+                raise _lib.BdlError("clipping and fused capture cannot be combined (capture after the step instead)")
+            _, nruns = self._gradient_table()                # fills the per-tensor host table (pointers, skip flags)
+            if getattr(self, "_clip_buf", None) is None:
+                self._clip_sumsq = torch.zeros(1, dtype=torch.float64, device=self.device)
+                self._clip_buf = torch.zeros(2, dtype=torch.float32, device=self.device)     # [coef, total_norm]
+            scalars.div_mode = self.div_mode
+            if self.buf is not None:
+                scalars.first_step = int(self.sgd_steps == 0)
+            nz = self._noise()                                # ONE draw for both passes
+            host = self._run_np.ctypes.data
+            state = (self.variant, self.theta, self.g_flat, self.theta0, self.v, self.m, self.s, self.buf, host, nruns, scalars, nz)
+            self._clip_sumsq.zero_()
+            ops.step_gradnorm(*state, self._clip_sumsq)
+            ops.clip_coef(self._clip_sumsq, clip, self._clip_buf[0:1], self._clip_buf[1:2])
+            ops.step_clipped(*state, self._clip_buf[0:1])
+            self.step_count += 1
+            self.sgd_steps += 1
+            return
         runs_host = None
         if self.grad_mode == "table":
             runs_dev, nruns = self._gradient_table()

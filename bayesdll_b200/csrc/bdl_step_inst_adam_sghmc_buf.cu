@@ -1,0 +1,9 @@
+// bdl_step_inst_adam_sghmc_buf.cu -- instantiates every build of the fused step for (BDL_ADAM_SGHMC, SGD momentum buffer = true); see bdl_step.cuh.
+#define BDL_STEP_INSTANTIATE
+#include "bdl_step.cuh"
+
+#ifndef BDL_AB_SLIM      // slim A/B builds (tools/ab_builds.py) instantiate the two kernels they time from bdl_step.cu
+namespace bdl {
+template int launch_nd<BDL_ADAM_SGHMC, true>(const StepParams&, bool, int, cudaStream_t);
+}  // namespace bdl
+#endif

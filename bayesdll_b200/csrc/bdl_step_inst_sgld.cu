@@ -1,0 +1,10 @@
+// bdl_step_inst_sgld.cu -- instantiates every build of the fused step for (BDL_SGLD, SGD momentum buffer = false); see bdl_step.cuh.
+#define BDL_STEP_INSTANTIATE
+#include "bdl_step.cuh"
+
+#ifndef BDL_AB_SLIM      // slim A/B builds (tools/ab_builds.py) instantiate the two kernels they time from bdl_step.cu
+namespace bdl {
+template int launch_nd<BDL_SGLD, false>(const StepParams&, bool, int, cudaStream_t);
+template int launch_clip_nd<BDL_SGLD, false>(const StepParams&, bool, int, int, double*, const float*, cudaStream_t);
+}  // namespace bdl
+#endif

@@ -146,10 +146,11 @@ class FusedModel(nn.Module):
                                 mu=self._opts["sgd_momentum"], beta1=self.beta1, beta2=self.beta2, eps=self.epsilon,
                                 temperature=self.temperature, t=max(self.t, 1), add_noise=should_sample)
 
-    def step_async(self, x, y, net, net0, criterion, lrs, Ninflate=1.0, nd=1.0, should_sample=False, capture=None):
+    def step_async(self, x, y, net, net0, criterion, lrs, Ninflate=1.0, nd=1.0, should_sample=False, capture=None, clip=None):
         """``forward`` without the host sync: returns (loss tensor, detached logits).  ``capture``: a callable returning
         an ops.make_capture spec, evaluated once the flat state exists; the sample capture that follows this step in
-        the reference's loop then rides in the same kernel."""
+        the reference's loop then rides in the same kernel.  ``clip``: args.clip_grad -- the reference's
+        ``clip_grad_norm_`` between this call and ``optimizer.step()`` (methods/csgld.py:250-251) folded into the update."""
         chain = self._ensure_chain(net, net0)
         if self.VARIANT in (_lib.ADAM_SGHMC, _lib.ADAM_CSGHMC):
             self.t += 1                                   # methods/adam_sghmc.py:494
@@ -161,7 +162,7 @@ class FusedModel(nn.Module):
             loss = criterion(out, y)
             net.zero_grad()                               # grads -> None; autograd hands us fresh tensors
             loss.backward()
-        chain.update(self._scalars(lrs, Ninflate, nd, should_sample), capture=None if capture is None else capture())
+        chain.update(self._scalars(lrs, Ninflate, nd, should_sample), capture=None if capture is None else capture(), clip=clip)
         if self._opts["release_grads"]:
             # The reference leaves the modified gradient in p.grad for the caller's optimizer.step(); here the update is
             # already applied, so a REAL torch optimizer stepping on p.grad would update theta a second time.  With the
@@ -369,17 +370,16 @@ class _RunnerCommon:
 
     MODEL_CLS = None
     SGD_MOMENTUM_FROM_ARGS = False     # SGD(momentum=args.momentum) vs SGD(momentum=0)
-    SUPPORTS_CLIP_GRAD = False         # args.clip_grad: see CyclicalRunner
+    CONSULTS_CLIP_GRAD = False         # only the cyclical runners read args.clip_grad (methods/csgld.py:250)
 
     # ---- construction (methods/sghmc.py:18-67) ------------------------------------------------------------
     def __init__(self, net, net0, args, logger):
         self.args = args
         self.logger = logger
-        self.clip_grad = getattr(args, "clip_grad", None)   # consulted by the cyclical runners only (methods/csgld.py:250)
-        if self.clip_grad is not None and not self.SUPPORTS_CLIP_GRAD:
-            raise NotImplementedError(
-                f"args.clip_grad={self.clip_grad!r}: gradient-norm clipping between Model.forward and optimizer.step() "
-                f"(methods/csgld.py:250-251) is not available for {type(self).__module__}; leave args.clip_grad unset")
+        # args.clip_grad: no driver of the reference defines it; the CYCLICAL runners consult it between Model.forward and
+        # optimizer.step() (methods/csgld.py:250, adam_csghmc.py:319; csghmc.py:301 / csghmc_fs.py:509 clip a gradient that
+        # is never used again, their Model.forward has already written p.data).  The burn-in runners never look at it.
+        self.clip_grad = getattr(args, "clip_grad", None) if self.CONSULTS_CLIP_GRAD else None
         if args.pretrained is None:                       # zero prior mean
             self.net0 = copy.deepcopy(net)
             with torch.no_grad():
@@ -801,6 +801,7 @@ class BurninRunner(_RunnerCommon):
 # cyclical runners: csgld, csghmc, adam_csghmc       (methods/csgld.py:17-594, csghmc.py, adam_csghmc.py)
 # ================================================================================================
 class CyclicalRunner(_RunnerCommon):
+    CONSULTS_CLIP_GRAD = True        # csgld.py:250, adam_csghmc.py:319 (csghmc.py:301: no effect on theta, see ChainState.update)
     CAPTURE = "avg"                  # 'avg' (csgld.py:282-290, adam_csghmc.py:349-357) | 'welford' (csghmc.py:333-345)
     LIKELIHOOD_MEAN = "theta"        # 'theta' (csgld.py:518) | 'cycle_mean' (csghmc.py:578, adam_csghmc.py:639)
     LAST_THETA_AS_VECTOR = False     # csghmc / adam_csghmc store a flat vector (csghmc.py:534)
@@ -930,7 +931,9 @@ class CyclicalRunner(_RunnerCommon):
 
                 x, y = x.to(dev, non_blocking=True), y.to(dev, non_blocking=True)
                 kw = dict(should_sample=should_sample) if self.PASS_SHOULD_SAMPLE else {}
-                fused = should_sample and self.fuse_capture
+                fused = should_sample and self.fuse_capture and self.clip_grad is None
+                if self.clip_grad is not None:
+                    kw["clip"] = self.clip_grad           # torch.nn.utils.clip_grad_norm_(self.net.parameters(), args.clip_grad)
                 if fused:
                     cyc = sched.get_cycle_number(**pos)
                     kw["capture"] = lambda: self._capture_spec(cyc)

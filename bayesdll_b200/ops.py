@@ -13,7 +13,7 @@ import torch
 from . import _lib
 from ._lib import ADAM_SGHMC, CSGHMC, DIV_RECIP, SGHMC, SGLD, STREAM_STEP, STREAM_USER, BdlError, Noise, Scalars
 
-__all__ = ["make_scalars", "upload_runs", "step", "make_capture", "philox_normal", "moments_avg", "moments_welford",
+__all__ = ["make_scalars", "upload_runs", "step", "step_gradnorm", "clip_coef", "step_clipped", "make_capture", "philox_normal", "moments_avg", "moments_welford",
            "capture_ring", "draw", "ensemble", "ce_err", "lse_accum", "lse_rescale", "lse_finalize", "calibrate", "bma_mean", "dropout_mix",
            "nll_temperature",
            "set_launch_config"]
@@ -170,6 +170,40 @@ def step(variant, theta, g, theta0, v, m, s, buf, runs_dev, nruns, scalars, nois
         if t is not None and t.numel() != n:
             raise BdlError(f"capture buffer length {t.numel()} != theta length {n}")
     _lib.check(_lib.load().bdl_step_capture(*args, C.byref(capture), _stream()), "bdl_step_capture")
+
+
+def _clip_args(variant, theta, g, theta0, v, m, s, buf, runs_host, nruns, scalars, noise):
+    n = theta.numel()
+    for name, t in (("g", g), ("theta0", theta0), ("v", v), ("m", m), ("s", s), ("buf", buf)):
+        if t is not None and t.numel() != n:
+            raise BdlError(f"{name}: length {t.numel()} != theta length {n}")
+    if runs_host is None:
+        raise BdlError("gradient-norm clipping needs the host copy of a per-tensor run table")
+    return (int(variant), _ptr(theta, "theta"), _ptr(g, "g", allow_none=True), _ptr(theta0, "theta0", allow_none=True),
+            _ptr(v, "v", allow_none=True), _ptr(m, "m", allow_none=True), _ptr(s, "s", allow_none=True),
+            _ptr(buf, "buf", allow_none=True), n, runs_host, nruns, C.byref(scalars), C.byref(noise))
+
+
+@_on_tensor_device
+def step_gradnorm(variant, theta, g, theta0, v, m, s, buf, runs_host, nruns, scalars, noise, sumsq):
+    """Pass 1 of the clipped update (bdl_step_gradnorm): ``sumsq`` (fp64[1], caller-zeroed) += sum of squares of what the
+    reference holds in p.grad between Model.forward and optimizer.step().  Nothing else is written."""
+    args = _clip_args(variant, theta, g, theta0, v, m, s, buf, runs_host, nruns, scalars, noise)
+    _lib.check(_lib.load().bdl_step_gradnorm(*args, _ptr(sumsq, "sumsq", torch.float64), _stream()), "bdl_step_gradnorm")
+
+
+@_on_tensor_device
+def clip_coef(sumsq, max_norm, coef, total_norm=None):
+    """coef[0] = min(1, max_norm / (sqrt(sumsq[0]) + 1e-6)) in fp32 (torch.nn.utils.clip_grad_norm_), on the device."""
+    _lib.check(_lib.load().bdl_clip_coef(_ptr(sumsq, "sumsq", torch.float64), float(max_norm), _ptr(coef, "coef"),
+                                         _ptr(total_norm, "total_norm", allow_none=True), _stream()), "bdl_clip_coef")
+
+
+@_on_tensor_device
+def step_clipped(variant, theta, g, theta0, v, m, s, buf, runs_host, nruns, scalars, noise, coef):
+    """Pass 2 (bdl_step_clipped): the fused update with p.grad scaled by the device scalar ``coef``."""
+    args = _clip_args(variant, theta, g, theta0, v, m, s, buf, runs_host, nruns, scalars, noise)
+    _lib.check(_lib.load().bdl_step_clipped(*args, _ptr(coef, "coef"), _stream()), "bdl_step_clipped")
 
 
 @_on_tensor_device

@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define BDL_ABI_VERSION 5
+#define BDL_ABI_VERSION 6
 
 typedef enum {
     BDL_OK = 0,
@@ -170,6 +170,27 @@ int bdl_step_capture(int variant, float* theta_dev, const float* g_dev, const fl
                      float* v_dev, float* m_dev, float* s_dev, float* buf_dev, uint64_t n,
                      const bdl_run* runs_dev, uint32_t nruns, const bdl_run* runs_host, const bdl_scalars* scalars,
                      const bdl_noise* noise, const bdl_capture* capture, void* stream);
+
+/* Gradient-norm clipping between Model.forward and optimizer.step() -- ``torch.nn.utils.clip_grad_norm_(net.parameters(),
+ * args.clip_grad)`` at methods/csgld.py:250-251 (p.grad = g + prior + noise) and methods/adam_csghmc.py:319-320 (p.grad = v):
+ * every p.grad is scaled by min(1, max_norm / (||all p.grad||_2 + 1e-6)) before the SGD step.  Fused as two passes with
+ * no host synchronisation:
+ *   bdl_step_gradnorm   recomputes what the reference holds in p.grad (same arithmetic as bdl_step, nothing stored; the
+ *                       counter-based noise makes both passes see the same draw) and ADDS the sum of its squares over the
+ *                       real elements of every tensor with a gradient to *sumsq_dev (caller zeroes it);
+ *   bdl_clip_coef       total_norm = fp32(sqrt(sumsq)); *coef_dev = min(1, max_norm / (total_norm + 1e-6)) (fp32, torch's
+ *                       statements); total_norm_dev is optional;
+ *   bdl_step_clipped    bdl_step with p.grad scaled by *coef_dev.
+ * Variants: BDL_SGLD (sgld / csgld) and BDL_ADAM_CSGHMC.  (csghmc / csghmc_fs also consult args.clip_grad, :301 / :509, but
+ * write p.data inside Model.forward, so their clipping never reaches theta: nothing to do.)  runs_host: HOST array with
+ * one row per tensor (<= 512 rows, with or without per-run gradient pointers); it travels in the kernel arguments. */
+int bdl_step_gradnorm(int variant, const float* theta_dev, const float* g_dev, const float* theta0_dev, const float* v_dev,
+                      const float* m_dev, const float* s_dev, const float* buf_dev, uint64_t n, const bdl_run* runs_host,
+                      uint32_t nruns, const bdl_scalars* scalars, const bdl_noise* noise, double* sumsq_dev, void* stream);
+int bdl_clip_coef(const double* sumsq_dev, float max_norm, float* coef_dev, float* total_norm_dev, void* stream);
+int bdl_step_clipped(int variant, float* theta_dev, const float* g_dev, const float* theta0_dev, float* v_dev, float* m_dev,
+                     float* s_dev, float* buf_dev, uint64_t n, const bdl_run* runs_host, uint32_t nruns,
+                     const bdl_scalars* scalars, const bdl_noise* noise, const float* coef_dev, void* stream);
 
 /* Fill out[0..n) with exactly the N(0,1) stream the step / draw kernels use for (seed, stream_id,
  * subseq).  Test and diagnostics entry (KS / moment tests; external-vs-in-kernel equivalence). */

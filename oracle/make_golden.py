@@ -90,7 +90,7 @@ def sgd_buf_flat(opt, net, names):
 
 
 def run_step_case(method, hparams, *, lr, lr_head, momentum, ND, T, seed, sample_pattern=None,
-                  cyc_lrs=None):
+                  cyc_lrs=None, clip_grad=None):
     """Drive the reference Model.forward (+ optimizer.step()) exactly like train_one_epoch does
     (methods/sghmc.py:220-229, methods/csghmc.py:285-304) and record the state after every step."""
     mod = refshim.load(f"methods.{method}")
@@ -106,7 +106,7 @@ def run_step_case(method, hparams, *, lr, lr_head, momentum, ND, T, seed, sample
     rec = dict(theta_init=flat(net.parameters()), theta0=flat(runner.net0.parameters()))
     G = (rng.standard_normal((T, n)) * 0.05).astype(np.float32)
     XI = rng.standard_normal((T, n)).astype(np.float32)
-    out = {k: [] for k in ("theta", "v", "m", "s", "buf", "lr_body", "lr_head")}
+    out = {k: [] for k in ("theta", "v", "m", "s", "buf", "lr_body", "lr_head", "total_norm", "pgrad")}
     for t in range(T):
         if cyc_lrs is not None:                       # cyclical runners overwrite param_group lrs each step
             cur = cyc_lrs[t]
@@ -126,6 +126,10 @@ def run_step_case(method, hparams, *, lr, lr_head, momentum, ND, T, seed, sample
             else:
                 model(None, None, runner.net, runner.net0, refshim.identity_criterion, lrs,
                       runner.Ninflate, runner.nd)
+                if clip_grad is not None:             # the statement of methods/csgld.py:250-251 / adam_csghmc.py:319-320
+                    out["pgrad"].append(flat([p.grad for p in net.parameters()]))
+                    tn = torch.nn.utils.clip_grad_norm_(runner.net.parameters(), clip_grad)
+                    out["total_norm"].append(np.float32(tn.item()))
                 opt.step()
         assert tape.calls == len(names) and tape.pos == n
         out["theta"].append(flat(net.parameters()))
@@ -195,6 +199,31 @@ def make_step_goldens():
              hp_keys=np.array(hp_keys), hp_vals=np.array([str(hp[k]) for k in hp_keys]),
              lr=lr, lr_head_arg=lr_head, ND=ND, momentum=kw["momentum"],
              sample_pattern=np.array(extra.get("sample_pattern", []), dtype=np.int64), **rec)
+
+
+def make_clip_goldens():
+    """args.clip_grad: no driver of the reference defines it, the cyclical runners consult it (csgld.py:250, adam_csghmc.py:319).
+    The clip values sit inside the range of the recorded norms, so both regimes (coef < 1, coef clamped to 1) occur."""
+    T = 6
+    base = dict(prior_sig=0.7, Ninflate=10.0, nd=0.5, burnin=1, thin=2, nst=3)
+    cases = [("csgld", "clip_inf_mu0.5", dict(base, bias="informative"), dict(momentum=0.5), 4.6),
+             ("csgld", "clip_uni_mu0.0", dict(base, bias="uninformative"), dict(momentum=0.0), 4.6),
+             ("adam_csghmc", "clip_inf", dict(base, bias="informative", momentum_decay=0.05, beta1=0.8, beta2=0.99, epsilon=1e-6,
+                                              temperature=1.7), dict(momentum=0.9), 1.3)]
+    cyc = refshim.load("methods.cyclical")
+    for i, (method, tag, hp, kw, clip) in enumerate(cases):
+        lr, lr_head, ND = 1e-2, 3e-2, 500
+        sched = cyc.CyclicalSGMCMC(base_lr=lr, nbr_of_cycles=2, epochs=2, proportion_exploration=0.5)
+        cyc_lrs = [sched.calculate_lr(epoch=0, batch=b, batches_per_epoch=6) for b in range(T)]
+        rec, names = run_step_case(method, hp, lr=lr, lr_head=lr_head, ND=ND, T=T, seed=300 + i, cyc_lrs=cyc_lrs,
+                                   clip_grad=clip, **kw)
+        sizes, is_head, is_bias = meta_arrays(names)
+        hp_keys = sorted(hp)
+        print(method, tag, "total norms", rec["total_norm"], "clip", clip)
+        save(f"step_{method}_{tag}", names=np.array(names), sizes=sizes, is_head=is_head, is_bias=is_bias,
+             hp_keys=np.array(hp_keys), hp_vals=np.array([str(hp[k]) for k in hp_keys]),
+             lr=lr, lr_head_arg=lr_head, ND=ND, momentum=kw["momentum"], clip_grad=clip,
+             sample_pattern=np.array([], dtype=np.int64), **rec)
 
 
 def make_cyclical_golden():
@@ -347,6 +376,8 @@ if __name__ == "__main__":
     which = sys.argv[1:] or ["step", "cyclical", "calibration", "runner"]
     if "step" in which:
         make_step_goldens()
+    if "clip" in which:                       # args.clip_grad cases only (added in round 2; "step" leaves them alone)
+        make_clip_goldens()
     if "cyclical" in which:
         make_cyclical_golden()
     if "calibration" in which:

@@ -105,8 +105,24 @@ def _sgd_apply(theta, gprime, buf, lr_e, mu, first_step):
 # ----------------------------------------------------------------------------------------------
 # (a1) SGLD / cSGLD      methods/sgld.py:469-484 + SGD.step :226 ; methods/csgld.py:665-680 + :253
 # ----------------------------------------------------------------------------------------------
+def clip_coef(pgrad, valid, max_norm):
+    """torch.nn.utils.clip_grad_norm_(parameters, max_norm) (methods/csgld.py:250-251, methods/adam_csghmc.py:319-320):
+    total_norm = || stack(||g_t||_2) ||_2 over the tensors that have a gradient, clip_coef = max_norm / (total_norm + 1e-6)
+    -- evaluated by torch as ``(total_norm + 1e-6).reciprocal() * max_norm`` (Tensor.__rtruediv__: two roundings) --,
+    clamped to <= 1, all in fp32.  ``pgrad``: what the reference holds in p.grad at that point (flat, padded layout);
+    ``valid``: boolean mask of the real elements of tensors with a gradient.  The sum of squares is formed in fp64 here
+    (torch: fp32, per tensor, vectorised), so total_norm agrees with torch's to ~1e-7 relative, not bit for bit.
+    -> (coef fp32, total_norm fp32)."""
+    q = np.asarray(pgrad, f64)[np.asarray(valid, bool)]
+    total = f32(np.sqrt(np.sum(q * q)))
+    coef = (f32(1.0) / (total + f32(1e-6))) * f32(max_norm)      # float / Tensor is Tensor.__rtruediv__: reciprocal() * other
+    return f32(min(coef, f32(1.0))), total
+
+
 def step_sgld(theta, g, theta0, buf, xi, *, is_head, P, lr_body, lr_head, hp, first_step,
-              div_mode="true"):
+              div_mode="true", clip=None, valid=None, coef=None):
+    """``clip`` = args.clip_grad: the modified gradient is scaled by clip_coef(g', valid, clip) before the SGD step
+    (methods/csgld.py:250-253); ``coef`` overrides the coefficient (replaying a recorded one)."""
     N = hp.N
     lr_e = _per_class(is_head, lr_body, lr_head)
     c_body = hp.nd * np.sqrt(2 / (N * lr_body))      # host fp64, methods/sgld.py:478/483
@@ -115,6 +131,10 @@ def step_sgld(theta, g, theta0, buf, xi, *, is_head, P, lr_body, lr_head, hp, fi
     with_prior = _prior_term(theta, theta0, hp, div_mode) + noise
     add = np.where(P.astype(bool), with_prior, noise)
     gprime = g + add                                  # p.grad = p.grad + ( ... )
+    if clip is not None or coef is not None:
+        if coef is None:
+            coef, _ = clip_coef(gprime, valid, clip)
+        gprime = gprime * f32(coef)                   # g.mul_(clip_coef_clamped)
     return _sgd_apply(theta, gprime, buf, lr_e, hp.mu, first_step)
 
 
@@ -184,10 +204,17 @@ def step_adam_sghmc(theta, g, theta0, v, m, s, buf, xi, *, is_head, P, lr_body, 
 
 
 def step_adam_csghmc(theta, g, theta0, v, m, s, xi, *, is_head, P, lr_body, lr_head, hp, t,
-                     div_mode="true"):
+                     div_mode="true", clip=None, valid=None, coef=None):
+    """``clip`` / ``coef`` as in step_sgld: p.grad = v is scaled before the SGD step (adam_csghmc.py:319-322); the
+    momentum buffer itself keeps the unclipped v."""
     lr_e, v, m, s = _adam_core(theta, g, theta0, v, m, s, xi, is_head=is_head, P=P, lr_body=lr_body,
                                lr_head=lr_head, hp=hp, t=t, cyc=True, div_mode=div_mode)
-    theta = _fma(v, -lr_e, theta)                                                    # p.grad = v (:861); SGD mu=0
+    pgrad = v
+    if clip is not None or coef is not None:
+        if coef is None:
+            coef, _ = clip_coef(v, valid, clip)
+        pgrad = v * f32(coef)
+    theta = _fma(pgrad, -lr_e, theta)                                                # p.grad = v (:861); SGD mu=0
     return theta, v, m, s
 
 

@@ -55,6 +55,19 @@ def max_rel(a, b):
     return float(np.max(np.abs(a - b)) / max(np.max(np.abs(b)), 1e-30))
 
 
+def recorded_clip_coef(z, t):
+    """clip_coef_clamped of step t as torch.nn.utils.clip_grad_norm_ forms it from the RECORDED total norm (fp32):
+    max_norm / (total_norm + 1e-6) = (total_norm + 1e-6).reciprocal() * max_norm (Tensor.__rtruediv__), clamped to <= 1."""
+    f32 = np.float32
+    coef = (f32(1.0) / (f32(z["total_norm"][t]) + f32(1e-6))) * f32(float(z["clip_grad"]))
+    return f32(min(coef, f32(1.0)))
+
+
+def valid_mask(z):
+    """Real elements of tensors with a gradient: everything, in the dense layout of the goldens."""
+    return np.ones(z["G"].shape[1], bool)
+
+
 def replay_step_case(name, impl, chained=True, div_mode="true"):
     """Replay one step golden through ``impl`` (module/object exposing the oracle's step_* API).
 
@@ -82,9 +95,12 @@ def replay_step_case(name, impl, chained=True, div_mode="true"):
         g, xi = z["G"][t], z["XI"][t]
         lrb, lrh = float(z["lr_body"][t]), float(z["lr_head"][t])
         kw = dict(is_head=is_head, lr_body=lrb, lr_head=lrh, hp=H)
+        # args.clip_grad goldens: replay the reference's own coefficient so that the update itself is compared bit for
+        # bit; the norm (a reduction: order-dependent) has its own tolerance test
+        ck = dict(coef=recorded_clip_coef(z, t)) if "clip_grad" in z.files else {}
         if method in ("sgld", "csgld"):
             st["theta"], st["buf"] = impl.step_sgld(st["theta"], g, theta0, st["buf"], xi, P=P,
-                                                    first_step=(t == 0), div_mode=div_mode, **kw)
+                                                    first_step=(t == 0), div_mode=div_mode, **kw, **ck)
         elif method == "sghmc":
             st["theta"], st["v"] = impl.step_sghmc(st["theta"], g, theta0, st["v"], xi, P=P,
                                                    div_mode=div_mode, **kw)
@@ -100,7 +116,7 @@ def replay_step_case(name, impl, chained=True, div_mode="true"):
             t_adam += 1
             st["theta"], st["v"], st["m"], st["s"] = impl.step_adam_csghmc(
                 st["theta"], g, theta0, st["v"], st["m"], st["s"], xi, P=P, t=t_adam,
-                div_mode=div_mode, **kw)
+                div_mode=div_mode, **kw, **ck)
         else:
             raise ValueError(method)
         for k in pairs:

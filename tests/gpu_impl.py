@@ -25,9 +25,15 @@ class GpuStepper:
     def down(self, t):
         return self.layout.dense_numpy(t.cpu().numpy())
 
-    def _run(self, variant, sc, theta, g, theta0, v, m, s, buf, xi):
+    def _run(self, variant, sc, theta, g, theta0, v, m, s, buf, xi, coef=None):
         T = {k: (None if a is None else self.up(a)) for k, a in
              dict(theta=theta, g=g, theta0=theta0, v=v, m=m, s=s, buf=buf, xi=xi).items()}
+        if coef is not None:        # args.clip_grad: pass 2 of the clipped update with a given coefficient (device scalar)
+            tab = self.layout.run_table(self.bias_mode, grad_ptrs=[0] * len(self.layout.segments))
+            ops.step_clipped(variant, T["theta"], T["g"], T["theta0"], T["v"], T["m"], T["s"], T["buf"], tab, len(tab), sc,
+                             ops.make_noise(xi=T["xi"]), torch.tensor([coef], dtype=torch.float32, device=self.dev))
+            torch.cuda.synchronize()
+            return {k: (None if t is None else self.down(t)) for k, t in T.items()}
         ops.step(variant, T["theta"], T["g"], T["theta0"], T["v"], T["m"], T["s"], T["buf"], self.runs_dev,
                  self.nruns, sc, ops.make_noise(xi=T["xi"]))
         torch.cuda.synchronize()
@@ -39,9 +45,9 @@ class GpuStepper:
                                 prior_sig=hp.prior_sig, nd=hp.nd, alpha=hp.alpha, mu=hp.mu, beta1=hp.beta1,
                                 beta2=hp.beta2, eps=hp.eps, temperature=hp.temperature, div_mode=DIV[div_mode], **kw)
 
-    def step_sgld(self, theta, g, theta0, buf, xi, *, is_head, P, lr_body, lr_head, hp, first_step, div_mode="true"):
+    def step_sgld(self, theta, g, theta0, buf, xi, *, is_head, P, lr_body, lr_head, hp, first_step, div_mode="true", coef=None):
         sc = self._sc(_lib.SGLD, hp, lr_body, lr_head, div_mode, first_step=first_step)
-        o = self._run(_lib.SGLD, sc, theta, g, theta0, None, None, None, buf if hp.mu != 0 else None, xi)
+        o = self._run(_lib.SGLD, sc, theta, g, theta0, None, None, None, buf if hp.mu != 0 else None, xi, coef=coef)
         return o["theta"], (o["buf"] if hp.mu != 0 else buf)
 
     def step_sghmc(self, theta, g, theta0, v, xi, *, is_head, P, lr_body, lr_head, hp, div_mode="true"):
@@ -60,7 +66,7 @@ class GpuStepper:
         o = self._run(_lib.ADAM_SGHMC, sc, theta, g, theta0, v, m, s, buf if hp.mu != 0 else None, xi)
         return o["theta"], o["v"], o["m"], o["s"], (o["buf"] if hp.mu != 0 else buf)
 
-    def step_adam_csghmc(self, theta, g, theta0, v, m, s, xi, *, is_head, P, lr_body, lr_head, hp, t, div_mode="true"):
+    def step_adam_csghmc(self, theta, g, theta0, v, m, s, xi, *, is_head, P, lr_body, lr_head, hp, t, div_mode="true", coef=None):
         sc = self._sc(_lib.ADAM_CSGHMC, hp, lr_body, lr_head, div_mode, t=t)
-        o = self._run(_lib.ADAM_CSGHMC, sc, theta, g, theta0, v, m, s, None, xi)
+        o = self._run(_lib.ADAM_CSGHMC, sc, theta, g, theta0, v, m, s, None, xi, coef=coef)
         return o["theta"], o["v"], o["m"], o["s"]

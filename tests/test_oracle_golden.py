@@ -39,6 +39,41 @@ def test_recip_mode_is_within_tolerance_of_reference():
                 assert gu.max_rel(got, want) <= 1e-6
 
 
+CLIP_CASES = [n for n in gu.step_cases() if "_clip_" in n]
+
+
+@pytest.mark.parametrize("name", CLIP_CASES)
+def test_clip_norm_and_coefficient_match_reference(name):
+    """args.clip_grad (methods/csgld.py:250-251, adam_csghmc.py:319-320): the oracle's total norm of the recorded p.grad
+    agrees with torch.nn.utils.clip_grad_norm_'s return value to fp32 rel 1e-6 (only the summation order differs), both
+    regimes occur (coef < 1 and coef clamped to 1), and the oracle recomputes that p.grad itself bit for bit."""
+    z, hp, method = gu.load_step_case(name)
+    assert len(CLIP_CASES) >= 3
+    clip = float(z["clip_grad"])
+    coefs = []
+    for t in range(z["G"].shape[0]):
+        coef, total = so.clip_coef(z["pgrad"][t], gu.valid_mask(z), clip)
+        assert abs(float(total) - float(z["total_norm"][t])) <= 1e-6 * float(z["total_norm"][t])
+        want = gu.recorded_clip_coef(z, t)
+        assert abs(float(coef) - float(want)) <= 1e-6 * float(want)
+        coefs.append(float(want))
+    assert min(coefs) < 1.0 and max(coefs) == 1.0, coefs
+    # with its OWN coefficient (not the recorded one) the oracle stays within the per-step tolerance of the reference
+    H = gu.hparams_from(hp, z, method)
+    P = gu.prior_mask(hp, z)
+    zeros = np.zeros(z["G"].shape[1], np.float32)
+    for t in range(1, z["G"].shape[0]):
+        kw = dict(is_head=z["is_head"], lr_body=float(z["lr_body"][t]), lr_head=float(z["lr_head"][t]), hp=H, clip=clip,
+                  valid=gu.valid_mask(z))
+        if method == "csgld":
+            th, _ = so.step_sgld(z["theta"][t - 1], z["G"][t], z["theta0"], z["buf"][t - 1] if H.mu else zeros, z["XI"][t], P=P,
+                                 first_step=False, **kw)
+        else:
+            th, _, _, _ = so.step_adam_csghmc(z["theta"][t - 1], z["G"][t], z["theta0"], z["v"][t - 1], z["m"][t - 1], z["s"][t - 1],
+                                              z["XI"][t], P=P, t=t + 1, **kw)
+        assert gu.max_rel(th, z["theta"][t]) <= 1e-6
+
+
 def test_cyclical_schedule():
     z = np.load(gu.golden_path("cyclical"))
     rows = z["rows"]

@@ -44,6 +44,11 @@ def build(specs):
 
 def run(argv):
     rounds = 2
+    script = os.path.join(ROOT, "tools", "ab_block.py")
+    if "--script" in argv:                                 # e.g. --script tools/ab_draw.py (takes no further arguments)
+        i = argv.index("--script")
+        script = os.path.join(ROOT, argv[i + 1])
+        del argv[i:i + 2]
     if "--rounds" in argv:
         i = argv.index("--rounds")
         rounds = int(argv[i + 1])
@@ -54,7 +59,8 @@ def run(argv):
             flags = open(os.path.join(AB, name, "flags.txt")).read().strip()
             print(f"=== round {r} build {name} [{flags}]", flush=True)
             env = dict(os.environ, BDL_LIB_PATH=os.path.join(AB, name, "libbdl.so"))
-            subprocess.call([sys.executable, os.path.join(ROOT, "tools", "ab_block.py"), "--rounds", "1", *argv], env=env)
+            extra = ["--rounds", "1", *argv] if script.endswith("ab_block.py") else argv
+            subprocess.call([sys.executable, script, *extra], env=env)
 
 
 if __name__ == "__main__":
