@@ -97,6 +97,8 @@ typedef struct {
     float lr[2], c[2];
     float oma, sig2, inv_sig2, N, inv_N, mu, b1, omb1, b2, omb2, bc1, inv_bc1, bc2, inv_bc2, eps, two_alpha, nd, T, inv_T;
     int first_step, add_noise, div;
+    int clip;      /* 0 none; 1 norm pass (clipq receives p.grad, caller stores nothing); 2 p.grad scaled by coef */
+    float coef;
 } sc_t;
 
 static inline float prior_term(const sc_t* p, float th, float th0) {
@@ -115,15 +117,19 @@ static inline float sgd_apply(const sc_t* p, int has_buf, float th, float gp, fl
     return fmaf(d, -lr, th);
 }
 
+/* clipq: torch.nn.utils.clip_grad_norm_ between Model.forward and optimizer.step() (methods/csgld.py:250-251,
+ * methods/adam_csghmc.py:319-320) acts on p.grad = g' (SGLD family) / v (Adam-cSGHMC). */
 static inline void update_one(int variant, int has_buf, const sc_t* p, uint32_t cls, float* th, float g, float th0,
-                              float* v, float* m, float* s, float* b, float xi) {
+                              float* v, float* m, float* s, float* b, float xi, float* clipq) {
     const int h = cls & BDL_CLS_HEAD;
     const int prior = (cls & BDL_CLS_PRIOR) != 0;
     const float lr = p->lr[h];
     if (variant == BDL_SGLD) {
         const float noise = p->c[h] * xi;
         const float add = prior ? prior_term(p, *th, th0) + noise : noise;
-        const float gp = g + add;
+        float gp = g + add;
+        if (p->clip == 1) *clipq = gp;
+        if (p->clip == 2) gp = gp * p->coef;
         *th = sgd_apply(p, has_buf, *th, gp, lr, b);
     } else if (variant == BDL_SGHMC) {
         const float gU = prior ? g + prior_term(p, *th, th0) : g;
@@ -152,7 +158,8 @@ static inline void update_one(int variant, int has_buf, const sc_t* p, uint32_t 
         const float noise = ns * xi;
         *v = ((*v * p->oma) + (lr * pg)) + noise;
         if (cyc) {
-            *th = fmaf(*v, -lr, *th);
+            if (p->clip == 1) *clipq = *v;
+            *th = fmaf(p->clip == 2 ? *v * p->coef : *v, -lr, *th);
         } else {
             const float gp = g + *v;
             *th = sgd_apply(p, has_buf, *th, gp, lr, b);
@@ -160,12 +167,17 @@ static inline void update_one(int variant, int has_buf, const sc_t* p, uint32_t 
     }
 }
 
-/* Same contract as bdl_step() in include/bdl.h with HOST pointers (stream ignored). */
-int bdl_oracle_step(int variant, float* theta, const float* g, const float* theta0, float* v, float* m, float* s,
-                    float* buf, uint64_t n, const bdl_run* runs, uint32_t nruns, const bdl_scalars* sc,
-                    const bdl_noise* nz) {
+/* Same contract as bdl_step() / bdl_step_gradnorm() / bdl_step_clipped() in include/bdl.h with HOST pointers (stream
+ * ignored).  clip 0: plain step; 1: *sumsq += sum of squares of p.grad over the real elements of tensors with a gradient,
+ * state untouched; 2: p.grad scaled by coef. */
+static int step_impl(int variant, float* theta, const float* g, const float* theta0, float* v, float* m, float* s,
+                     float* buf, uint64_t n, const bdl_run* runs, uint32_t nruns, const bdl_scalars* sc,
+                     const bdl_noise* nz, int clip, float coef, double* sumsq) {
     if (variant < BDL_SGLD || variant > BDL_ADAM_CSGHMC || !theta || !runs || !sc || !nz || n % 4) return BDL_ERR_INVALID;
+    if (clip && variant != BDL_SGLD && variant != BDL_ADAM_CSGHMC) return BDL_ERR_UNSUPPORTED;
     sc_t p;
+    p.clip = clip; p.coef = coef;
+    double total = 0.0;
     for (int h = 0; h < 2; ++h) { p.lr[h] = sc->lr[h]; p.c[h] = sc->noise_scale[h]; }
     /* reciprocal mode multiplies by the host-supplied fp32(1.0 / s_double) (what torch CUDA uses); 0 = not supplied */
 #define INV_OF(s_f, host_inv) ((sc->div_mode == BDL_DIV_RECIP && (host_inv) != 0.0f) ? (host_inv) : 1.0f / (s_f))
@@ -183,7 +195,7 @@ int bdl_oracle_step(int variant, float* theta, const float* g, const float* thet
         const bdl_run run = runs[r];
         if (run.cls & BDL_CLS_SKIP) continue;
         const int64_t q0 = (int64_t)(run.begin / 4), q1 = (int64_t)(run.end / 4);
-#pragma omp parallel for schedule(static)
+#pragma omp parallel for schedule(static) reduction(+ : total)
         for (int64_t q = q0; q < q1; ++q) {
             float z[4];
             if (xi) memcpy(z, xi + 4 * q, sizeof z);
@@ -193,13 +205,48 @@ int bdl_oracle_step(int variant, float* theta, const float* g, const float* thet
                 float gi;
                 if (run.g_dev) gi = i < run.valid_end ? run.g_dev[i - run.begin] : 0.0f;
                 else gi = g[i];
-                float dv = 0, dm = 0, ds = 0, db = 0;
+                float dv = 0, dm = 0, ds = 0, db = 0, cq = 0;
+                if (clip == 1) {                         /* norm pass: work on copies, store nothing */
+                    float th = theta[i], vv = v ? v[i] : 0, mm = m ? m[i] : 0, ss = s ? s[i] : 0, bb = buf ? buf[i] : 0;
+                    update_one(variant, has_buf, &p, run.cls, &th, gi, theta0 ? theta0[i] : 0.0f, &vv, &mm, &ss, &bb, z[k], &cq);
+                    if (i < run.valid_end) total += (double)cq * (double)cq;
+                    continue;
+                }
                 update_one(variant, has_buf, &p, run.cls, &theta[i], gi, theta0 ? theta0[i] : 0.0f, v ? &v[i] : &dv,
-                           m ? &m[i] : &dm, s ? &s[i] : &ds, buf ? &buf[i] : &db, z[k]);
+                           m ? &m[i] : &dm, s ? &s[i] : &ds, buf ? &buf[i] : &db, z[k], &cq);
             }
         }
     }
+    if (clip == 1 && sumsq) *sumsq += total;
     return BDL_OK;
+}
+
+int bdl_oracle_step(int variant, float* theta, const float* g, const float* theta0, float* v, float* m, float* s,
+                    float* buf, uint64_t n, const bdl_run* runs, uint32_t nruns, const bdl_scalars* sc,
+                    const bdl_noise* nz) {
+    return step_impl(variant, theta, g, theta0, v, m, s, buf, n, runs, nruns, sc, nz, 0, 1.0f, NULL);
+}
+
+/* per-tensor runs required (valid_end delimits the real elements) */
+int bdl_oracle_step_gradnorm(int variant, const float* theta, const float* g, const float* theta0, const float* v,
+                             const float* m, const float* s, const float* buf, uint64_t n, const bdl_run* runs,
+                             uint32_t nruns, const bdl_scalars* sc, const bdl_noise* nz, double* sumsq) {
+    return step_impl(variant, (float*)theta, g, theta0, (float*)v, (float*)m, (float*)s, (float*)buf, n, runs, nruns, sc, nz,
+                     1, 1.0f, sumsq);
+}
+
+/* total_norm = fp32(sqrt(sumsq)); coef = min(1, (total_norm + 1e-6).reciprocal() * max_norm) -- clip_grad_norm_'s statements */
+float bdl_oracle_clip_coef(double sumsq, float max_norm, float* total_norm) {
+    const float tn = (float)sqrt(sumsq);
+    const float c = (1.0f / (tn + 1e-6f)) * max_norm;
+    if (total_norm) *total_norm = tn;
+    return c < 1.0f ? c : 1.0f;
+}
+
+int bdl_oracle_step_clipped(int variant, float* theta, const float* g, const float* theta0, float* v, float* m, float* s,
+                            float* buf, uint64_t n, const bdl_run* runs, uint32_t nruns, const bdl_scalars* sc,
+                            const bdl_noise* nz, float coef) {
+    return step_impl(variant, theta, g, theta0, v, m, s, buf, n, runs, nruns, sc, nz, 2, coef, NULL);
 }
 
 /* posterior draw, same contract as bdl_draw() */

@@ -65,6 +65,31 @@ def step(variant, theta, g, theta0, v, m, s, buf, runs, scalars, noise):
     assert rc == 0, rc
 
 
+def step_clipped(variant, theta, g, theta0, v, m, s, buf, runs, scalars, noise, coef):
+    """bdl_step_clipped on the host: the step with p.grad scaled by ``coef`` (args.clip_grad)."""
+    rc = lib().bdl_oracle_step_clipped(C.c_int(variant), _fp(theta), _fp(g), _fp(theta0), _fp(v), _fp(m), _fp(s), _fp(buf),
+                                       C.c_uint64(theta.size), runs, C.c_uint32(len(runs)), C.byref(scalars), C.byref(noise),
+                                       C.c_float(coef))
+    assert rc == 0, rc
+
+
+def step_gradnorm(variant, theta, g, theta0, v, m, s, buf, runs, scalars, noise):
+    """bdl_step_gradnorm on the host -> sum of squares (float) of what the reference holds in p.grad; ``runs``: per tensor."""
+    out = C.c_double(0.0)
+    rc = lib().bdl_oracle_step_gradnorm(C.c_int(variant), _fp(theta), _fp(g), _fp(theta0), _fp(v), _fp(m), _fp(s), _fp(buf),
+                                        C.c_uint64(theta.size), runs, C.c_uint32(len(runs)), C.byref(scalars), C.byref(noise),
+                                        C.byref(out))
+    assert rc == 0, rc
+    return out.value
+
+
+def clip_coef(sumsq, max_norm):
+    lib().bdl_oracle_clip_coef.restype = C.c_float
+    tn = C.c_float(0)
+    coef = lib().bdl_oracle_clip_coef(C.c_double(sumsq), C.c_float(max_norm), C.byref(tn))
+    return coef, tn.value
+
+
 def draw(mean, second, out, var_mode, scale, div_mode, noise, center=None):
     rc = lib().bdl_oracle_draw(_fp(mean), _fp(second), _fp(center), _fp(out), C.c_uint64(mean.size), C.c_int(var_mode),
                                C.c_float(scale), C.c_int(div_mode), C.byref(noise))

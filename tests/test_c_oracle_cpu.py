@@ -37,12 +37,15 @@ class COracleStepper:
         self.layout = FlatLayout([(n, (int(s),)) for n, s in zip(names, sizes)], readout)
         self.runs = self.layout.run_table(bias_mode)
 
-    def _run(self, variant, sc, **arrs):
+    def _run(self, variant, sc, coef=None, **arrs):
         T = {k: (None if a is None else np.ascontiguousarray(self.layout.padded_numpy(np.asarray(a, np.float32))))
              for k, a in arrs.items()}
         nz = L.Noise()
         nz.xi_dev = T["xi"].ctypes.data
-        co.step(variant, T["theta"], T["g"], T["theta0"], T["v"], T["m"], T["s"], T["buf"], self.runs, sc, nz)
+        if coef is not None:      # args.clip_grad goldens: the step with the recorded coefficient
+            co.step_clipped(variant, T["theta"], T["g"], T["theta0"], T["v"], T["m"], T["s"], T["buf"], self.runs, sc, nz, coef)
+        else:
+            co.step(variant, T["theta"], T["g"], T["theta0"], T["v"], T["m"], T["s"], T["buf"], self.runs, sc, nz)
         return {k: (None if t is None else self.layout.dense_numpy(t)) for k, t in T.items()}
 
     @staticmethod
@@ -52,9 +55,9 @@ class COracleStepper:
                                 nd=hp.nd, alpha=hp.alpha, mu=hp.mu, beta1=hp.beta1, beta2=hp.beta2, eps=hp.eps,
                                 temperature=hp.temperature, div_mode={"true": 0, "recip": 1}[div_mode], **kw)
 
-    def step_sgld(self, theta, g, theta0, buf, xi, *, is_head, P, lr_body, lr_head, hp, first_step, div_mode="true"):
+    def step_sgld(self, theta, g, theta0, buf, xi, *, is_head, P, lr_body, lr_head, hp, first_step, div_mode="true", coef=None):
         sc = self._sc(L.SGLD, hp, lr_body, lr_head, div_mode, first_step=first_step)
-        o = self._run(L.SGLD, sc, theta=theta, g=g, theta0=theta0, v=None, m=None, s=None,
+        o = self._run(L.SGLD, sc, coef=coef, theta=theta, g=g, theta0=theta0, v=None, m=None, s=None,
                       buf=buf if hp.mu != 0 else None, xi=xi)
         return o["theta"], (o["buf"] if hp.mu != 0 else buf)
 
@@ -75,9 +78,9 @@ class COracleStepper:
                       buf=buf if hp.mu != 0 else None, xi=xi)
         return o["theta"], o["v"], o["m"], o["s"], (o["buf"] if hp.mu != 0 else buf)
 
-    def step_adam_csghmc(self, theta, g, theta0, v, m, s, xi, *, is_head, P, lr_body, lr_head, hp, t, div_mode="true"):
+    def step_adam_csghmc(self, theta, g, theta0, v, m, s, xi, *, is_head, P, lr_body, lr_head, hp, t, div_mode="true", coef=None):
         sc = self._sc(L.ADAM_CSGHMC, hp, lr_body, lr_head, div_mode, t=t)
-        o = self._run(L.ADAM_CSGHMC, sc, theta=theta, g=g, theta0=theta0, v=v, m=m, s=s, buf=None, xi=xi)
+        o = self._run(L.ADAM_CSGHMC, sc, coef=coef, theta=theta, g=g, theta0=theta0, v=v, m=m, s=s, buf=None, xi=xi)
         return o["theta"], o["v"], o["m"], o["s"]
 
 
@@ -91,6 +94,32 @@ def test_c_oracle_bit_exact_vs_numpy_oracle(name, div_mode):
     for key in a:
         for (got, _), (want, _) in zip(a[key], b[key]):
             assert np.array_equal(got.view(np.uint32), np.asarray(want, np.float32).view(np.uint32)), (name, key)
+
+
+@pytest.mark.parametrize("name", [n for n in gu.step_cases() if "_clip_" in n])
+def test_c_oracle_gradnorm_matches_reference_norm(name):
+    """The C restatement's norm pass (bdl_oracle_step_gradnorm, per-tensor runs) reproduces the total norm the reference's
+    clip_grad_norm_ returned at every recorded step to fp32 rel 1e-6, and its coefficient is the recorded one."""
+    z, hp, method = gu.load_step_case(name)
+    H = gu.hparams_from(hp, z, method)
+    lay = FlatLayout([(n, (int(s),)) for n, s in zip(z["names"].tolist(), z["sizes"].tolist())], "classifier")
+    tab = lay.run_table(hp["bias"], grad_ptrs=[0] * len(lay.segments))
+    variant = L.SGLD if method == "csgld" else L.ADAM_CSGHMC
+    pad = lambda a: np.ascontiguousarray(lay.padded_numpy(np.asarray(a, np.float32)))
+    zeros = np.zeros(z["G"].shape[1], np.float32)
+    for t in range(z["G"].shape[0]):
+        prev = (lambda k: z[k][t - 1] if t > 0 and k in z.files else (z["theta_init"] if k == "theta" else zeros))
+        sc = COracleStepper._sc(variant, H, float(z["lr_body"][t]), float(z["lr_head"][t]), "true", t=t + 1, first_step=(t == 0))
+        nz = L.Noise()
+        xi = pad(z["XI"][t])
+        nz.xi_dev = xi.ctypes.data
+        adam = variant == L.ADAM_CSGHMC
+        sumsq = co.step_gradnorm(variant, pad(prev("theta")), pad(z["G"][t]), pad(z["theta0"]), pad(prev("v")) if adam else None,
+                                 pad(prev("m")) if adam else None, pad(prev("s")) if adam else None,
+                                 pad(prev("buf")) if H.mu else None, tab, sc, nz)
+        coef, total = co.clip_coef(sumsq, float(z["clip_grad"]))
+        assert abs(total - float(z["total_norm"][t])) <= 1e-6 * float(z["total_norm"][t]), (t, total, float(z["total_norm"][t]))
+        assert abs(coef - float(gu.recorded_clip_coef(z, t))) <= 1e-6
 
 
 def test_c_oracle_moments_and_draw_vs_numpy():
