@@ -702,8 +702,13 @@ class BurninRunner(_RunnerCommon):
             bdist.agree_across_ranks(torch.cat(ys), "the evaluation targets")
             la = self._gather_eval(local, rows, S, rank, world, ph)
             with ph("reduce"):
-                for la_b, y in zip(torch.split(la, rows), ys):     # same batch boundaries as one rank: same summation order
-                    self._reduce_batch(la_b.contiguous(), y, acc)
+                # the ensemble kernel is row-wise (one warp per row), so ONE launch over all N rows gives the bits the
+                # per-batch launches of one rank give; the CE accumulation keeps the batch boundaries (fp64 summation order)
+                logits_full = torch.empty(la.shape[:2], dtype=torch.float32, device=dev)
+                ops.ensemble(la, logits_full, self.nst)
+                for la_b, lg_b, y in zip(torch.split(la, rows), torch.split(logits_full, rows), ys):
+                    ops.ce_err(lg_b, y, acc.loss_sum, acc.err_cnt)
+                    acc.add(y, lg_b, la_b)
         return self._finish_eval(acc, ph)
 
     def _reduce_batch(self, logits_all_, y, acc):
@@ -1089,13 +1094,19 @@ class CyclicalRunner(_RunnerCommon):
             bdist.agree_across_ranks(torch.cat(ys), "the evaluation targets")
             la = self._gather_eval(local, rows, S, rank, world, ph)
             with ph("reduce"):
-                for la_b, y in zip(torch.split(la, rows), ys):
-                    self._reduce_batch(la_b, y, acc, weights, per)
+                # row-wise kernels: reduce all N rows at once (2 launches per cycle instead of 2 per cycle per batch); only
+                # the CE accumulation keeps the batch boundaries, so every number equals the single-rank one bit for bit
+                wide = _EvalAccumulator(dev)
+                self._reduce_batch(la, torch.cat(ys), wide, weights, per, with_ce=False)
+                for la_b, lg_b, y in zip(torch.split(wide.lgalls[0], rows), torch.split(wide.lgs[0], rows), ys):
+                    ops.ce_err(lg_b.contiguous(), y, acc.loss_sum, acc.err_cnt)
+                    acc.add(y, lg_b, la_b)
         return self._finish_eval(acc, ph)
 
-    def _reduce_batch(self, flat, y, acc, weights, per):
+    def _reduce_batch(self, flat, y, acc, weights, per, with_ce=True):
         """One batch: ``flat`` [B,K,C*per] (sample index cycle * per + s) -> ``logits_all`` [B,K,per,C], per-cycle
-        log-mean-softmax, weighted sum of log-probabilities (Appendix B.5; methods/csgld.py:416-439), CE / errors."""
+        log-mean-softmax, weighted sum of log-probabilities (Appendix B.5; methods/csgld.py:416-439), CE / errors
+        (``with_ce=False``: the caller accumulates them)."""
         B, K, C = flat.shape[0], flat.shape[1], len(weights)
         dev = flat.device
         if C == 0:
@@ -1111,7 +1122,8 @@ class CyclicalRunner(_RunnerCommon):
                 batch_logits = wt * comp.squeeze(2) if ci == 0 else batch_logits + wt * comp.squeeze(2)
             else:
                 ops.ensemble(comp, batch_logits, self.nst, weight=w, mode=1 if ci == 0 else 2)
-        ops.ce_err(batch_logits.contiguous(), y, acc.loss_sum, acc.err_cnt)
+        if with_ce:
+            ops.ce_err(batch_logits.contiguous(), y, acc.loss_sum, acc.err_cnt)
         acc.add(y, batch_logits, logits_all)
 
     # ---- cycle likelihoods and GMM weights (methods/csgld.py:508-594) ----------------------------------------

@@ -67,11 +67,11 @@ def make_runner(method, device, log_dir, nst, eval_shard, cycles=3):
     return runner
 
 
-def run_case(method, device, log_dir, nst, eval_shard):
+def run_case(method, device, log_dir, nst, eval_shard, cycles=3):
     """evaluate() twice (the second call uses the captured CUDA graphs and another Philox sub-sequence), the calibration
     bins of the result, and -- cyclical runners -- full_batch_likelihoods()."""
     from bayesdll_b200 import calibration
-    runner = make_runner(method, device, log_dir, nst, eval_shard)
+    runner = make_runner(method, device, log_dir, nst, eval_shard, cycles=cycles)
     loader = make_loader()
     out = {}
     for i in range(2):

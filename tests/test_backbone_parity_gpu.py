@@ -10,6 +10,7 @@ division semantics would show up and be amplified by the network."""
 import copy
 import logging
 
+import numpy as np
 import pytest
 import torch
 
@@ -172,3 +173,50 @@ def test_cfg5_resnet101_csgld_ensemble_and_calibration(cuda_device, deterministi
     a = calibration.analyze(targets, logits, 15, None)
     b = calibration.analyze(ref_targets.cpu().numpy(), ref_logits.float().cpu().numpy(), 15, None)
     assert all(abs(x - y) <= 1e-5 for x, y in zip(a, b))
+
+
+def test_cfg5_full_sample_count_8_cycles_x_5_draws(cuda_device, deterministic_fp32, tmp_path):
+    """configs[4] at its stated ensemble size: 8 cycles x nst 5 = 40 posterior samples on ResNet-101 (K = 37).  The cycle
+    statistics are injected through the reference's attribute names (checkpoint layout), ``evaluate()`` (noise=torch,
+    seeded) runs over two batches (16 + a ragged 5) and is compared with the reference's evaluate statements
+    (methods/csgld.py:333-456) on the same GPU: all 40 sampled networks' logits bit-identical in the reference's
+    [N, K, nst, C] layout, mixture within 1e-5, same error count, same calibration bins."""
+    from oracle import make_golden_runner as mgr
+    from bayesdll_b200 import calibration
+    from bayesdll_b200.methods import csgld
+    dev = cuda_device
+    net, net0 = mgr.cfg2_networks()
+    C, nst = 8, 5
+    hp = dict(prior_sig=1.0, Ninflate=1.0, nd=0.01, thin=1, bias="informative", nst=nst, noise="torch")
+    args = mgr.make_args(hp, str(tmp_path), dev, momentum=0.5, epochs=8, num_cycles=C, lr=1e-4, lr_head=1e-2, ND=1840)
+    args.num_classes = 37
+    runner = csgld.Runner(net, net0, args, _logger())
+    gen = torch.Generator(device=dev).manual_seed(4)
+    with torch.no_grad():
+        theta = torch.nn.utils.parameters_to_vector(runner.net.parameters())
+    m1, m2 = {}, {}
+    for c in range(1, C + 1):
+        mean = theta + 1e-3 * torch.randn(theta.numel(), device=dev, generator=gen)
+        m1[c], m2[c] = mean, mean * mean + 1e-6 * torch.rand(theta.numel(), device=dev, generator=gen)
+    runner.cycle_theta_mom1, runner.cycle_theta_mom2 = m1, m2
+    runner.samples_per_cycle = {c: 3 + c for c in m1}
+    runner.cycle_likelihoods = {c: [0.1 + 0.02 * c, 0.12 + 0.01 * c] for c in m1}
+    runner.current_cycle = C
+    g2 = torch.Generator().manual_seed(9)
+    test = [(torch.randn(b, 3, 224, 224, generator=g2), torch.randint(0, 37, (b,), generator=g2)) for b in (16, 5)]
+    torch.manual_seed(321)
+    loss, err, targets, logits, logits_all = runner.evaluate(test)
+    weights = runner.calculate_gmm_weights()
+    assert len(weights) == C and abs(sum(weights.values()) - 1) < 1e-12
+    torch.manual_seed(321)
+    ref_logits, ref_all, ref_targets = er.evaluate_cyclical_avg(runner.net, runner.cycle_theta_mom1, runner.cycle_theta_mom2,
+                                                                runner.samples_per_cycle, weights, nst, test, dev)
+    assert logits_all.shape == tuple(ref_all.shape) == (21, 37, nst, C)
+    assert torch.equal(torch.from_numpy(logits_all), ref_all.cpu()), "a sampled network's logits differ"
+    assert torch.equal(torch.from_numpy(targets), ref_targets.cpu())
+    torch.testing.assert_close(torch.from_numpy(logits), ref_logits.float().cpu(), atol=1e-5, rtol=1e-5)
+    assert round(err * 21) == int(ref_logits.argmax(1).ne(ref_targets).sum().item()) and abs(err * 21 - round(err * 21)) < 1e-9
+    _, _, _, _, sizes_a = calibration.calc_bins(targets, logits, 15)
+    a = calibration.analyze(targets, logits, 15, None)
+    b = calibration.analyze(ref_targets.cpu().numpy(), ref_logits.float().cpu().numpy(), 15, None)
+    assert int(np.asarray(sizes_a).sum()) == 21 * 37 and all(abs(x - y) <= 1e-5 for x, y in zip(a, b))

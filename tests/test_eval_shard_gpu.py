@@ -18,10 +18,12 @@ import shard_util
 
 pytestmark = pytest.mark.gpu
 
-CASES = [("csgld", 2), ("csghmc", 3), ("adam_csghmc", 2), ("csgld", 0), ("sghmc", 5), ("sgld", 1), ("adam_sghmc", 0)]
+# (method, nst, cycles); the last one is BASELINE.json configs[4]'s ensemble size: 8 cycles x nst 5 = 40 samples, 20 per rank
+CASES = [("csgld", 2, 3), ("csghmc", 3, 3), ("adam_csghmc", 2, 3), ("csgld", 0, 3), ("sghmc", 5, 3), ("sgld", 1, 3),
+         ("adam_sghmc", 0, 3), ("csgld", 5, 8)]
 
 
-def _worker(rank, world, port, method, nst, multi_gpu, log_dir, q):
+def _worker(rank, world, port, method, nst, cycles, multi_gpu, log_dir, q):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     import torch.distributed as dist
     dev = torch.device("cuda", rank if multi_gpu else 0)
@@ -30,7 +32,7 @@ def _worker(rank, world, port, method, nst, multi_gpu, log_dir, q):
         dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
     else:
         dist.init_process_group("gloo", rank=rank, world_size=world)
-    out = shard_util.run_case(method, dev, os.path.join(log_dir, f"r{rank}"), nst, eval_shard=True)
+    out = shard_util.run_case(method, dev, os.path.join(log_dir, f"r{rank}"), nst, eval_shard=True, cycles=cycles)
     q.put((rank, out))
     dist.barrier()
     dist.destroy_process_group()
@@ -52,17 +54,17 @@ def _same(a, b, what):
         assert a == b, f"{what}: {a!r} != {b!r}"
 
 
-@pytest.mark.parametrize("method,nst", CASES, ids=[f"{m}-nst{n}" for m, n in CASES])
-def test_two_rank_evaluate_is_bit_identical_to_one_rank(cuda_device, tmp_path, method, nst):
+@pytest.mark.parametrize("method,nst,cycles", CASES, ids=[f"{m}-nst{n}-c{c}" for m, n, c in CASES])
+def test_two_rank_evaluate_is_bit_identical_to_one_rank(cuda_device, tmp_path, method, nst, cycles):
     os.makedirs(tmp_path / "one", exist_ok=True)
-    one = shard_util.run_case(method, cuda_device, tmp_path / "one", nst, eval_shard=False)
+    one = shard_util.run_case(method, cuda_device, tmp_path / "one", nst, eval_shard=False, cycles=cycles)
     # the reference's output contract
     e = one["eval0"]
     n_rows = sum(len(y) for _, y in shard_util.make_loader())
     cyclical = "likelihoods" in one
     assert e["targets"].dtype == np.int64 and e["targets"].shape == (n_rows,)
     assert e["logits"].shape == (n_rows, shard_util.K) and e["logits"].dtype == np.float32
-    assert e["logits_all"].shape == ((n_rows, shard_util.K, max(1, nst), 3) if cyclical else (n_rows, shard_util.K, max(1, nst)))
+    assert e["logits_all"].shape == ((n_rows, shard_util.K, max(1, nst), cycles) if cyclical else (n_rows, shard_util.K, max(1, nst)))
     assert not np.array_equal(one["eval0"]["logits_all"], one["eval1"]["logits_all"]) or nst == 0    # fresh draws per call
     assert int(e["sizes"].sum()) == n_rows * shard_util.K
 
@@ -74,7 +76,7 @@ def test_two_rank_evaluate_is_bit_identical_to_one_rank(cuda_device, tmp_path, m
         os.makedirs(tmp_path / f"r{r}", exist_ok=True)
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
-    procs = [ctx.Process(target=_worker, args=(r, 2, port, method, nst, multi_gpu, str(tmp_path), q)) for r in range(2)]
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, method, nst, cycles, multi_gpu, str(tmp_path), q)) for r in range(2)]
     for p in procs:
         p.start()
     res = sorted((q.get(timeout=300) for _ in range(2)), key=lambda t: t[0])

@@ -11,7 +11,12 @@ python bench.py --impl reference --steps 20 --warmup 5 > gpurun_out/${R}_bench_r
 python tools/show_variants.py gpurun_out/${R}_bench_final.json
 PROF="python bench.py --steps 20 --warmup 3 --no-train-step --no-ensemble --no-cpu-baseline --no-e2e --no-variants --no-eager-gpu --no-sample-store --no-cfg1"
 $PROF > gpurun_out/${R}_plain.log 2>&1 && ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/${R}_launches.csv $PROF > gpurun_out/${R}_ncu_launches.log 2>&1
-python tools/run_steps.py --generic > gpurun_out/${R}_plain_steps.log 2>&1 && ncu --set full --clock-control none --import-source on -k regex:'step_kernel|step_table_kernel' -s 8 -c 12 -o gpurun_out/${R}_steps_full python tools/run_steps.py --generic > gpurun_out/${R}_ncu_steps.log 2>&1
+# the .ncu-rep files exceed what gpurun copies back (64 MiB): export the raw pages here, keep the reports in /tmp
+python tools/run_steps.py --generic > gpurun_out/${R}_plain_steps.log 2>&1 && ncu --set full --clock-control none -k regex:'step_' -s 12 -c 16 -o /tmp/${R}_steps_full python tools/run_steps.py --generic > gpurun_out/${R}_ncu_steps.log 2>&1
 tail -2 gpurun_out/${R}_ncu_steps.log
-python tools/run_draws.py > gpurun_out/${R}_plain_draws.log 2>&1 && ncu --set full --clock-control none --import-source on -k regex:'dropout_mix|draw_kernel' -s 6 -c 6 -o gpurun_out/${R}_draws_full python tools/run_draws.py > gpurun_out/${R}_ncu_draws.log 2>&1
+ncu -i /tmp/${R}_steps_full.ncu-rep --page raw --csv > gpurun_out/${R}_steps_full_raw.csv
+python -c "from bayesdll_b200 import build; print(build.source_hash())" > gpurun_out/${R}_steps_build_hash.txt
+python tools/run_draws.py > gpurun_out/${R}_plain_draws.log 2>&1 && ncu --set full --clock-control none -k regex:'dropout_mix|draw_kernel' -s 6 -c 6 -o /tmp/${R}_draws_full python tools/run_draws.py > gpurun_out/${R}_ncu_draws.log 2>&1
 tail -2 gpurun_out/${R}_ncu_draws.log
+ncu -i /tmp/${R}_draws_full.ncu-rep --page raw --csv > gpurun_out/${R}_draws_full_raw.csv
+# then, back in the build container:  cp gpurun_out/${R}_steps_full_raw.csv profiles/ && python tools/traffic_from_ncu.py profiles/${R}_steps_full_raw.csv --build-hash $(cat gpurun_out/${R}_steps_build_hash.txt)
