@@ -256,6 +256,17 @@ class _EvalNet:
         # every pointer of the forward pass is stable (the draw overwrites ``flat`` in place): replay it as a CUDA graph
         self.forward = GraphedForward(self.net, enabled=graph)
 
+    def refresh(self, net):
+        """Re-inherit the live network's buffers (BatchNorm running statistics, Appendix B.12) IN PLACE: the captured
+        graphs keep reading the same addresses.  False when the live network no longer matches this copy."""
+        src, dst = list(net.buffers()), list(self.net.buffers())
+        if len(src) != len(dst) or any(a.shape != b.shape or a.dtype != b.dtype for a, b in zip(src, dst)):
+            return False
+        with torch.no_grad():
+            if src:
+                torch._foreach_copy_(dst, src)
+        return True
+
     def load(self, flat_values):
         self.flat.copy_(flat_values)
 
@@ -287,12 +298,15 @@ class _Phases:
             yield
             return
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0 = time.perf_counter()
         e0.record()
         try:
             yield
         finally:
             e1.record()
             self.spans.setdefault(name, []).append((e0, e1))
+            # host time spent issuing the phase: a phase whose host time is close to its device time is host-bound
+            self.host[f"{name}_host_ms"] = self.host.get(f"{name}_host_ms", 0.0) + (time.perf_counter() - t0) * 1e3
 
     def summary(self):
         """{phase: milliseconds}; synchronises."""
@@ -416,6 +430,8 @@ class _RunnerCommon:
         # are bit-identical to one rank and identical on every rank.  Off by default: independent chains (one per
         # rank) must not pool their samples.
         self.eval_shard = bool(int(float(hp.get("eval_shard", 0))))
+        self.eval_cache = bool(int(float(hp.get("eval_cache", 1))))   # keep the evaluation copy + its graphs across calls
+        self._eval_cached = None
         self.profile_eval = False        # True: evaluate() leaves a per-phase device-time split in self.eval_phases
         self.eval_phases = {}
         # fuse=1 (default): the moment capture that follows a sampler step runs inside the step kernel; fuse=0: separate
@@ -441,6 +457,26 @@ class _RunnerCommon:
 
     def _dense(self, flat):
         return self._chain().layout.to_dense(flat)
+
+    def _eval_net(self):
+        """The evaluation copy of the live network (parameters = views of one flat buffer the draws overwrite).  Built
+        once and kept across evaluate() / full_batch_likelihoods() calls -- the reference makes a fresh deepcopy(net) per
+        sample per batch (methods/csgld.py:404-406); here even one copy per call would re-capture the forward's CUDA
+        graphs every epoch -- and refreshed in place with the live network's buffers at every call, so each evaluation
+        inherits the current BatchNorm statistics exactly like a fresh copy (Appendix B.12).  ``hparams eval_cache=0``
+        restores one copy per call; ``release_eval_cache()`` frees the copy's memory."""
+        layout = self._chain().layout
+        ev = self._eval_cached
+        if (ev is not None and self.eval_cache and ev.src is self.net and ev.layout is layout
+                and ev.graph == self.use_graph and ev.refresh(self.net)):
+            return ev
+        ev = _EvalNet(self.net, layout, graph=self.use_graph)
+        ev.src, ev.graph = self.net, self.use_graph
+        self._eval_cached = ev if self.eval_cache else None
+        return ev
+
+    def release_eval_cache(self):
+        self._eval_cached = None
 
     def _shard(self):
         """(rank, world) of the sample-sharded evaluation: the default process group when hparams ``eval_shard=1``,
@@ -670,7 +706,7 @@ class BurninRunner(_RunnerCommon):
         args = self.args
         dev = args.device
         ch = self._chain()
-        ev = _EvalNet(self.net, ch.layout, graph=self.use_graph)
+        ev = self._eval_net()
         self._eval_calls += 1
         ratio = self._variance_ratio()
         rank, world = self._shard()
@@ -1056,7 +1092,7 @@ class CyclicalRunner(_RunnerCommon):
         ch = self._chain()
         gmm_weights = self.calculate_gmm_weights()
         self.logger.info(f"GMM component weights: {gmm_weights}")
-        ev = _EvalNet(self.net, ch.layout, graph=self.use_graph)
+        ev = self._eval_net()
         self._eval_calls += 1
         cycles = [c for c in self._cyc1 if not gmm_weights.get(c, 0.0) < 1e-10]
         specs = {c: self._cycle_variance_spec(c) for c in cycles} if self.nst > 0 else {}
@@ -1148,7 +1184,7 @@ class CyclicalRunner(_RunnerCommon):
                 spec = self._cycle_variance_spec(c)
             else:
                 raise TypeError("cycle variance is None (reference: vector_to_parameters(None, ...), Appendix B.8)")
-        ev = _EvalNet(self.net, ch.layout, graph=self.use_graph)
+        ev = self._eval_net()
         self._eval_calls += 1
         n_draws = max(1, self.nst)
         rank, world = self._shard()

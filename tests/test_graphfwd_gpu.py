@@ -21,3 +21,47 @@ def test_replay_follows_in_place_refill_of_one_input_tensor(cuda_device):
     with torch.no_grad():
         x.data.fill_(0.25)
         assert torch.equal(fwd(x), net(x))
+
+
+@pytest.mark.parametrize("method", ["sghmc", "csgld"])
+def test_cached_evaluation_copy_equals_a_fresh_copy_per_call(cuda_device, tmp_path, method):
+    """The evaluation copy of the network (and its captured graphs) is kept across evaluate() calls and refreshed in place
+    with the live network's buffers; hparams eval_cache=0 builds a fresh deepcopy per call like round 1 did.  Three calls
+    with the BatchNorm statistics of the LIVE network changed in between (Appendix B.12: every evaluation inherits the
+    current statistics): all outputs bit-identical, and the cached runner captures each input shape once."""
+    import numpy as np
+    import shard_util as su
+    from bayesdll_b200.graphfwd import GraphedForward
+    loader = su.make_loader()
+    outs, captures = {}, {}
+    for cache in (1, 0):
+        d = tmp_path / f"c{cache}"
+        d.mkdir()
+        runner = su.make_runner(method, cuda_device, d, nst=3, eval_shard=0)
+        runner.eval_cache = bool(cache)
+        before = GraphedForward.total_captures
+        res = []
+        for call in range(3):
+            with torch.no_grad():
+                bn = runner.net.features[1]
+                bn.running_mean.add_(0.05 * call)
+                bn.running_var.mul_(1.0 + 0.1 * call)
+            res.append(runner.evaluate(loader))
+        if hasattr(runner, "full_batch_likelihoods"):
+            res.append((0.0, 0.0) + tuple(np.asarray(runner.full_batch_likelihoods(su.make_loader(seed=9)))[None] for _ in range(3)))
+        outs[cache], captures[cache] = res, GraphedForward.total_captures - before
+        if cache:
+            assert runner._eval_cached is not None and runner._eval_cached.src is runner.net
+            runner.release_eval_cache()
+            assert runner._eval_cached is None
+        else:
+            assert runner._eval_cached is None
+        runner.flush_io()
+    n_shapes = len({tuple(x.shape) for x, _ in loader})
+    assert captures[1] <= n_shapes + 1 < captures[0], captures    # cached: one capture per shape (+1: the likelihood loader)
+    for a, b in zip(outs[1], outs[0]):
+        assert a[0] == b[0] and a[1] == b[1]
+        for u, v in zip(a[2:], b[2:]):
+            assert np.array_equal(np.asarray(u), np.asarray(v))
+    # the calls differ from each other (the statistics really changed): the refresh is not a no-op
+    assert not np.array_equal(outs[1][0][3], outs[1][1][3])
