@@ -112,6 +112,51 @@ def sghmc_update_rate(named_shapes, readout_name, device, *, steps, warmup, hp, 
                       f"(no backbone cost)"}
 
 
+def train_step_ms(backbone, device, *, batch, steps, hp, method="sghmc", num_classes=37, seed=42):
+    """ms per training step of the UNMODIFIED reference on ``device``: its own ``networks.create_backbone`` (torchvision
+    ResNet-101 / ViT-L/32, random init), its ``methods/<method>.Runner`` and the statements of its ``train_one_epoch``
+    (methods/sghmc.py:220-236: batch to the device, ``Model.forward`` = forward + backward + per-tensor update loop,
+    ``optimizer.step()``, prediction error) on synthetic 224x224 batches from pinned host memory -- the whole user-visible
+    step the drop-in's ``Model.forward`` replaces."""
+    import importlib
+    import tempfile
+    from oracle import refshim
+    device = torch.device(device)
+    torch.manual_seed(seed)
+    with refshim.reference_imports():
+        networks = importlib.import_module("networks")
+        mod = importlib.import_module(f"methods.{method}")
+    a = argparse.Namespace(device=device, ND=hp["ND"], lr=hp["lr_body"], lr_head=hp["lr_head"], momentum=0.5, epochs=1,
+                           pretrained="synthetic", num_classes=num_classes, backbone=backbone, ece_num_bins=15, test_eval_freq=1,
+                           log_dir=tempfile.mkdtemp(prefix="bdl_refstep_"), seed=seed, num_cycles=1, proportion_exploration=0.5,
+                           full_sample=False,
+                           hparams=dict(prior_sig=str(hp["prior_sig"]), Ninflate=str(hp["Ninflate"]), nd=str(hp["nd"]),
+                                        momentum_decay=str(hp["alpha"]), burnin="5", thin="1", bias="informative", nst="5"))
+    net, net0 = networks.create_backbone(a), networks.create_backbone(a)
+    runner = mod.Runner(net, net0, a, _quiet_logger())
+    runner.net.train()
+    x_host = torch.randn(batch, 3, 224, 224)
+    y_host = torch.randint(0, num_classes, (batch,))
+    if device.type == "cuda":
+        x_host, y_host = x_host.pin_memory(), y_host.pin_memory()
+
+    def one():
+        x, y = x_host.to(device), y_host.to(device)
+        loss_, out = runner.model(x, y, runner.net, runner.net0, runner.criterion,
+                                  [pg["lr"] for pg in runner.optimizer.param_groups], runner.Ninflate, runner.nd)
+        runner.optimizer.step()
+        pred = out.data.max(dim=1)[1]
+        return loss_, pred.ne(y.data).sum().item()
+    for _ in range(2):
+        one()
+    _sync(device)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        one()
+    _sync(device)
+    return (time.perf_counter() - t0) / steps * 1e3
+
+
 def cfg1_mlp_mnist(device="cpu", batches=20, batch_size=128, test_batches=8, reference=True, seed=42):
     """BASELINE.json configs[0] (README.md:83): mlp_mnist SGLD, prior_sig=1, Ninflate=1e3, nd=1, burnin=5, thin=10, nst=5,
     lr 1e-2, momentum 0.5, synthetic 28x28 batches of 128, ND = 30 000.  ``reference=True``: the unmodified reference Runner

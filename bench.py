@@ -619,6 +619,23 @@ def train_step_extra(device, rank, world, steps=6, batch=64, backbone="vit_l_32"
            "d2h_bytes_per_step": 4, "last_loss": loss,
            "api": f"bayesdll_b200.methods.sghmc.Model.forward on torchvision {backbone}, batch {batch}, fp32 fwd/bwd in PyTorch"}
     del runner, net, net0
+    torch.cuda.empty_cache()
+    # ... and the UNMODIFIED reference itself (baseline/_ref): its own backbone factory, Runner, Model.forward +
+    # optimizer.step() on this GPU -- the user-visible step the drop-in replaces; rank 0 only
+    if rank == 0:
+        try:
+            from baseline import reference_arm
+            if reference_arm.available():
+                hp_ref = dict(lr_body=HP["lr_body"], lr_head=HP["lr_head"], ND=HP["ND"], Ninflate=HP["Ninflate"],
+                              prior_sig=HP["prior_sig"], nd=HP["nd"], alpha=HP["alpha"])
+                res["reference_ms_per_step"] = reference_arm.train_step_ms(backbone, device, batch=batch, steps=steps, hp=hp_ref)
+                res["reference_kind"] = "reference (unmodified methods/sghmc.py Runner from baseline/_ref on this GPU)"
+            else:
+                res["reference_ms_per_step"] = None
+                res["reference_kind"] = "no reference tree found (baseline/install_ref.py)"
+        except Exception as e:                                   # context figure only
+            res["reference_ms_per_step"] = f"failed: {type(e).__name__}: {e}"
+        torch.cuda.empty_cache()
     return res
 
 

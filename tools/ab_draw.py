@@ -41,6 +41,11 @@ def main():
             e1.record()
             torch.cuda.synchronize()
             res[name].append(e0.elapsed_time(e1) / 200)
+    sums = []
+    for name, fn in cases:                               # same bits from every build: checksum of one fixed draw per case
+        fn(12345)
+        sums.append(f"{int(out.view(torch.int32).sum(dtype=torch.int64)):x}")
+    print("checksums " + " ".join(sums), flush=True)
     print("  ".join(f"{k}: " + "/".join(f"{x:.4f}" for x in v) + f" ms ({12 * lay.n_dense / min(v) / 1e6:.0f} GB/s)" for k, v in res.items()), flush=True)
 
 
