@@ -11,7 +11,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("BDL_LIB_PATH") or os.path.join(HERE, "libbdl.so")   # BDL_LIB_PATH: A/B builds (tools/ab_builds.py)
 
 # ---- enums / constants (include/bdl.h) -------------------------------------------------------
-BDL_ABI_VERSION = 6
+BDL_ABI_VERSION = 7
 SGLD, SGHMC, CSGHMC, ADAM_SGHMC, ADAM_CSGHMC = range(5)
 VARIANT_NAMES = {SGLD: "sgld", SGHMC: "sghmc", CSGHMC: "csghmc", ADAM_SGHMC: "adam_sghmc",
                  ADAM_CSGHMC: "adam_csghmc"}
@@ -83,6 +83,7 @@ SIGNATURES = {
     "bdl_bma_mean": [_P, _U32, _U32, _U32, _P, _P],
     "bdl_nll_temperature": [_P, _P, _U64, _U32, _D, _P, _P, _P],
     "bdl_selftest_math": [_P, _P],
+    "bdl_probe_stream": [_P, _P, _P, _P, _U64, _I32, _I32, _I32, _P],
     "bdl_chain_create": [_U64, _I32, _I32, _U64, C.POINTER(_P)],
     "bdl_chain_destroy": [_P],
     "bdl_chain_upload": [_P, _I32, _P],

@@ -44,7 +44,43 @@ __global__ void __launch_bounds__(256) selftest_math_kernel(unsigned long long* 
     }
 }
 
+// Bare-traffic yardstick (bdl_probe_stream): the memory traffic of a sampler kernel with next to no arithmetic, in the
+// product kernels' launch shape (one tile per CTA, CTAs dispatched in address order, one 128-bit group per thread and
+// stream, evict-first stores).  kReads / kWrites streams: 4/2 = SGHMC step, 2/1 = posterior draw, 1/1 = copy.
+template <int kReads, int kWrites>
+__global__ void __launch_bounds__(256) probe_stream_kernel(float* __restrict__ a, float* __restrict__ b, const float* __restrict__ c,
+                                                           const float* __restrict__ d, uint32_t n4) {
+    const uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= n4) return;
+    const uint64_t i = static_cast<uint64_t>(q) << 2;
+    float4 x = *reinterpret_cast<const float4*>(c + i);
+    if constexpr (kReads >= 2) { const float4 y = *reinterpret_cast<const float4*>(d + i); x.x += y.x; x.y += y.y; x.z += y.z; x.w += y.w; }
+    if constexpr (kReads >= 3) { const float4 y = *reinterpret_cast<const float4*>(a + i); x.x = 0.5f * (x.x + y.x); x.y = 0.5f * (x.y + y.y); x.z = 0.5f * (x.z + y.z); x.w = 0.5f * (x.w + y.w); }
+    float4 z = x;
+    if constexpr (kReads >= 4) { const float4 y = *reinterpret_cast<const float4*>(b + i); z.x = 0.5f * (x.x - y.x); z.y = 0.5f * (x.y - y.y); z.z = 0.5f * (x.z - y.z); z.w = 0.5f * (x.w - y.w); }
+    st_stream(a + i, x);
+    if constexpr (kWrites >= 2) st_stream(b + i, z);
+}
+
 }  // namespace bdl
+
+extern "C" int bdl_probe_stream(float* a, float* b, const float* c, const float* d, uint64_t n, int reads, int writes,
+                                int threads, void* stream) {
+    using namespace bdl;
+    if (n == 0) return BDL_OK;
+    BDL_REQUIRE(a && c && (reads < 2 || d) && ((reads < 4 && writes < 2) || b), BDL_ERR_INVALID, "bdl_probe_stream: null pointer");
+    BDL_REQUIRE(n % 4 == 0 && (n >> 2) < 0xFFFFFFFFull, BDL_ERR_INVALID, "bdl_probe_stream: bad n");
+    BDL_REQUIRE(aligned16(a) && aligned16(b) && aligned16(c) && aligned16(d), BDL_ERR_ALIGN, "bdl_probe_stream: unaligned pointer");
+    BDL_REQUIRE(threads == 64 || threads == 128 || threads == 256, BDL_ERR_INVALID, "bdl_probe_stream: threads must be 64, 128 or 256");
+    const uint32_t n4 = static_cast<uint32_t>(n >> 2);
+    const uint32_t grid = (n4 + threads - 1) / threads;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (reads == 4 && writes == 2) probe_stream_kernel<4, 2><<<grid, threads, 0, st>>>(a, b, c, d, n4);
+    else if (reads == 2 && writes == 1) probe_stream_kernel<2, 1><<<grid, threads, 0, st>>>(a, b, c, d, n4);
+    else if (reads == 1 && writes == 1) probe_stream_kernel<1, 1><<<grid, threads, 0, st>>>(a, b, c, d, n4);
+    else BDL_REQUIRE(false, BDL_ERR_INVALID, "bdl_probe_stream: (reads, writes) must be (4,2), (2,1) or (1,1)");
+    return check_cuda(cudaGetLastError(), "probe_stream_kernel launch");
+}
 
 extern "C" int bdl_selftest_math(unsigned long long* out6_dev, void* stream) {
     using namespace bdl;

@@ -362,6 +362,16 @@ def selftest_math(device):
     return {"mismatch": h[:3], "fast": h[3:]}
 
 
+@_on_tensor_device
+def probe_stream(a, b, c, d, reads, writes, threads=64):
+    """Bare-traffic yardstick (bdl_probe_stream): (reads, writes) = (4, 2) / (2, 1) / (1, 1) streams over flat fp32 buffers,
+    next to no arithmetic, the product kernels' launch shape.  Overwrites ``a`` (and ``b`` for two writes)."""
+    rc = _lib.load().bdl_probe_stream(_ptr(a, "a"), _ptr(b, "b") if b is not None else None, _ptr(c, "c"),
+                                      _ptr(d, "d") if d is not None else None, a.numel(), int(reads), int(writes), int(threads),
+                                      _stream())
+    _lib.check(rc, "bdl_probe_stream")
+
+
 class HostChain:
     """Python handle of the host-buffer chain API (bdl_chain_*): sampler state resident in HBM, gradient in / theta
     out through pinned host tensors.  See include/bdl.h."""

@@ -255,6 +255,14 @@ def run_ours(args):
                 "frac_of_nominal_8TBps": round(achieved / 8000.0, 4), "kernel": "bdl::step_kernel<SGHMC,philox,recip,U=1,T=64>, one tile per CTA",
                 "algorithmic_bytes_per_launch": BYTES_PER_PARAM * n_dense, "kernel_ms": round(kernel_ms, 4)}
 
+    # the bare-traffic yardstick: a kernel that only MOVES the step's bytes (4 reads + 2 writes per element, next to no
+    # arithmetic, same launch shape; bdl_probe_stream) on scratch copies of the same size, timed right after the step
+    bare = guarded("bare traffic", bare_traffic_ms, theta, g, theta0, device, reps=min(K, 50))
+    if isinstance(bare, dict) and "ms" in bare:
+        roofline["bare_traffic_kernel"] = {"ms": round(bare["ms"], 4), "gbs": round(BYTES_PER_PARAM * n_dense / (bare["ms"] * 1e-3) / 1e9, 1),
+                                           "step_over_bare": round(kernel_ms / bare["ms"], 4),
+                                           "note": "bdl_probe_stream(4 reads, 2 writes): the step's traffic without its arithmetic"}
+
     # ---- the other update rules on the same state (extra; BASELINE.json configs[1], [3], [4] kernels) ----------
     variants = {} if args.no_variants else guarded("variants", variant_rates, lay, theta, g, theta0, v, runs_dev, nruns, device,
                                                    world, peak, seed)
@@ -323,6 +331,23 @@ def run_ours(args):
 
 
 # ------------------------------------------------------------------------------------------------------------
+def bare_traffic_ms(theta, g, theta0, device, reps=50):
+    """Average duration of bdl_probe_stream(4 reads, 2 writes) over buffers of the state's size (two scratch buffers stand
+    in for theta and v so the chain's state is left alone)."""
+    from bayesdll_b200 import ops
+    a, b = torch.zeros_like(theta), torch.zeros_like(theta)
+    for _ in range(3):
+        ops.probe_stream(a, b, g, theta0, 4, 2, threads=64)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        ops.probe_stream(a, b, g, theta0, 4, 2, threads=64)
+    e1.record()
+    torch.cuda.synchronize()
+    return {"ms": e0.elapsed_time(e1) / reps}
+
+
 def e2e_host_chain(lay, theta, theta0, g, sc, seed, K, args, world, device):
     """The same update through the host-buffer C ABI: pinned host gradient in, pinned host theta out, every step."""
     from bayesdll_b200 import _lib, ops
@@ -438,6 +463,11 @@ def variant_rates(lay, theta, g, theta0, v, runs_dev, nruns, device, world, peak
         out[name] = {"params_per_s": world * n_dense / (ms * 1e-3), "ms_per_launch": ms, "bytes_per_param": 12,
                      "achieved_gbs_per_gpu": gbs, "frac_of_measured_peak": gbs / peak}
     out["mc_dropout_mix_bias_gaussian"]["runs"] = dr_n
+    # the draws' yardstick: 2 reads + 1 write per element with next to no arithmetic (bdl_probe_stream), same buffers
+    ms = timed(lambda i: ops.probe_stream(buf, None, mom1, mom2, 2, 1, threads=128))
+    out["bare_traffic_2r1w"] = {"ms_per_launch": ms, "bytes_per_param": 12, "achieved_gbs_per_gpu": 12 * n_dense / (ms * 1e-3) / 1e9,
+                                "frac_of_measured_peak": 12 * n_dense / (ms * 1e-3) / 1e9 / peak,
+                                "note": "bdl_probe_stream(2 reads, 1 write): what the draws' traffic costs without Philox / Box-Muller / sqrt"}
     # the shape Runner.train() actually launches: one run per tensor, each row pointing at that tensor's own
     # (separately allocated) autograd gradient -- no flat gradient buffer, no gather pass (step_table_kernel)
     del buf
@@ -461,7 +491,7 @@ def variant_rates(lay, theta, g, theta0, v, runs_dev, nruns, device, world, peak
         gbs = bpp * n_dense / (ms * 1e-3) / 1e9
         out[name] = {"params_per_s": world * n_dense / (ms * 1e-3), "ms_per_step": ms, "bytes_per_param": bpp,
                      "achieved_gbs_per_gpu": gbs, "frac_of_measured_peak": gbs / peak, "frac_of_nominal_8TBps": gbs / 8000.0,
-                     "runs": nr, "aligned": ok, "kernel": "bdl::step_table_kernel",
+                     "runs": nr, "aligned": ok, "kernel": "bdl::step_ptable_kernel (run table in the kernel arguments)",
                      "note": "run table with one row per tensor carrying that tensor's p.grad address (the training-loop launch)"}
     return out
 

@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define BDL_ABI_VERSION 6
+#define BDL_ABI_VERSION 7
 
 typedef enum {
     BDL_OK = 0,
@@ -295,6 +295,15 @@ int bdl_nll_temperature(const float* logits_dev, const int64_t* labels_dev, uint
  * the CUDA intrinsics over all 2^32 bit patterns.  out6_dev: 6 x uint64 = mismatches {sqrt, rcp, div}, then the number
  * of inputs that took the fast path {sqrt, rcp, div}.  ~0.1 s on B200. */
 int bdl_selftest_math(unsigned long long* out6_dev, void* stream);
+
+/* Diagnostics entry: the bare-traffic yardstick of the streaming kernels.  Moves the bytes of a sampler kernel with next
+ * to no arithmetic, in the product kernels' launch shape (one tile per CTA in address order, one 128-bit group per thread
+ * and stream, evict-first stores):  (reads, writes) = (4, 2): a, b read and written, c, d read -- the SGHMC step's
+ * 24 B/element (methods/sghmc.py:482-510 + :229);  (2, 1): c, d read, a written -- the posterior draw's 12 B/element
+ * (methods/sgld.py:292-297);  (1, 1): c read, a written -- a copy.  bench.py times it next to the real kernels
+ * (`roofline.bare_traffic_kernel`); no reference counterpart.  a and b are overwritten with finite averages. */
+int bdl_probe_stream(float* a_dev, float* b_dev, const float* c_dev, const float* d_dev, uint64_t n, int reads, int writes,
+                     int threads, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Host-buffer form: a chain whose state is resident in HBM, stepped from HOST memory.

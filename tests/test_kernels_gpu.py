@@ -395,3 +395,29 @@ def test_mc_dropout_in_kernel_philox_uniforms_equal_the_c_oracle(cuda_device, n)
         want, wz = np.empty(n, np.float32), np.empty(n, np.float32)
         co.dropout_mix(m, th0, want, p_drop, nz, z_out=wz)
         assert np.array_equal(mask.cpu().numpy(), wz) and bits_equal(out.cpu().numpy(), want)
+
+
+@pytest.mark.parametrize("threads", [64, 128, 256])
+def test_probe_stream_moves_what_it_says(cuda_device, threads):
+    """bdl_probe_stream (the bare-traffic yardstick bench.py times next to the real kernels): every element is read and
+    written exactly once per stream, for a length that is not a multiple of the CTA size; neighbours stay untouched."""
+    from bayesdll_b200 import ops
+    n = 4 * (3 * 256 + 37)
+    gen = torch.Generator(device=cuda_device).manual_seed(5)
+    pad = 64
+    def buf():
+        return torch.randn(n + 2 * pad, device=cuda_device, generator=gen)
+    A, B, Cc, D = buf(), buf(), buf(), buf()
+    a, b, c, d = (t[pad:pad + n] for t in (A, B, Cc, D))
+    A0, B0 = A.clone(), B.clone()
+    ops.probe_stream(a, None, c, None, 1, 1, threads=threads)
+    assert torch.equal(a, c) and torch.equal(A[:pad], A0[:pad]) and torch.equal(A[pad + n:], A0[pad + n:])
+    ops.probe_stream(a, None, c, d, 2, 1, threads=threads)
+    assert torch.equal(a, c + d)
+    a_old, b_old = a.clone(), b.clone()
+    ops.probe_stream(a, b, c, d, 4, 2, threads=threads)
+    want_a = 0.5 * ((c + d) + a_old)
+    assert torch.equal(a, want_a) and torch.equal(b, 0.5 * (want_a - b_old))
+    assert torch.equal(B[:pad], B0[:pad]) and torch.equal(B[pad + n:], B0[pad + n:])
+    with pytest.raises(Exception, match="reads, writes"):
+        ops.probe_stream(a, b, c, d, 3, 1, threads=threads)
