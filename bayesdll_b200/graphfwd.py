@@ -11,9 +11,29 @@ Policy: the first call for an input shape runs eagerly (it is also the warm-up),
 replay.  A network whose forward cannot be captured (host-side control flow on tensor values, ...) is run eagerly from
 then on, with one warning; ``hparams graph=0`` turns the mechanism off.
 """
+import contextlib
+import gc
 import warnings
 
 import torch
+
+
+@contextlib.contextmanager
+def capture_gc_guard():
+    """Around every CUDA-graph capture of this package.  A ``torch.cuda.CUDAGraph`` that Python's CYCLIC collector happens to
+    finalise while a stream is capturing calls ``cudaGraphExecDestroy`` in the middle of the capture, which CUDA answers with
+    "operation not permitted when stream is capturing" and an INVALIDATED capture (seen in the test suite: runners of
+    earlier tests, kept alive by reference cycles, own cached evaluation graphs; torch 2.11's ``torch.cuda.graph`` no
+    longer runs ``gc.collect()`` on entry).  So: collect what is collectable BEFORE the capture begins, and keep the
+    cyclic collector off until it has ended (reference-counted frees are unaffected)."""
+    gc.collect()
+    was = gc.isenabled()
+    gc.disable()
+    try:
+        yield
+    finally:
+        if was:
+            gc.enable()
 
 
 class GraphedForward:
@@ -38,7 +58,7 @@ class GraphedForward:
             self._pool = torch.cuda.graph_pool_handle()
         graph = torch.cuda.CUDAGraph()
         # thread_local: the asynchronous checkpoint writer may allocate pinned memory on its own thread meanwhile
-        with torch.cuda.graph(graph, pool=self._pool, capture_error_mode="thread_local"):
+        with capture_gc_guard(), torch.cuda.graph(graph, pool=self._pool, capture_error_mode="thread_local"):
             out = self.net(static_x)
         if not isinstance(out, torch.Tensor) or out.device != dev:
             raise TypeError("forward did not return a tensor on the input's device")

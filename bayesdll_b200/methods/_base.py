@@ -29,7 +29,7 @@ from .. import _lib, calibration, ops
 from .. import dist as bdist
 from ..chain import ChainState, SampleRing
 from ..flat import adopt_parameters, alloc_flat
-from ..graphfwd import GraphedForward
+from ..graphfwd import GraphedForward, capture_gc_guard
 from ..writer import AsyncWriter, FlatBackedStateDict
 from .cyclical import CyclicalSGMCMC
 
@@ -203,7 +203,7 @@ class FusedModel(nn.Module):
                 quiet = getattr(torch.autograd.graph, "set_warn_on_accumulate_grad_stream_mismatch", None)
                 if quiet is not None:
                     quiet(False)
-                with torch.cuda.graph(graph, capture_error_mode="thread_local"):
+                with capture_gc_guard(), torch.cuda.graph(graph, capture_error_mode="thread_local"):
                     out = net(sx)
                     loss = criterion(out, sy)
                     loss.backward()

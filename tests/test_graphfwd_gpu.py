@@ -65,3 +65,57 @@ def test_cached_evaluation_copy_equals_a_fresh_copy_per_call(cuda_device, tmp_pa
             assert np.array_equal(np.asarray(u), np.asarray(v))
     # the calls differ from each other (the statistics really changed): the refresh is not a no-op
     assert not np.array_equal(outs[1][0][3], outs[1][1][3])
+
+
+def test_capture_keeps_the_cyclic_collector_out(cuda_device):
+    """A CUDAGraph finalised by Python's cyclic collector WHILE another graph is being captured invalidates that capture
+    (cudaGraphExecDestroy is not permitted while a stream captures) -- and a Runner's cached evaluation graphs live until
+    the collector finds the runner.  graphfwd.capture_gc_guard: collectable garbage is finalised BEFORE the capture starts
+    and the collector stays off until it has ended."""
+    import gc
+    import warnings
+    from bayesdll_b200.graphfwd import GraphedForward
+    seen = {}
+
+    class Owner:                                          # cyclic garbage that owns captured graphs, like a dropped Runner
+        def __init__(self, fwd):
+            self.me, self.fwd = self, fwd
+
+        def __del__(self):
+            seen["finalised_while_capturing"] = torch.cuda.is_current_stream_capturing()
+
+    class Net(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.lin = torch.nn.Linear(16, 4)
+
+        def forward(self, x):
+            if torch.cuda.is_current_stream_capturing():
+                seen["collector_enabled_during_capture"] = gc.isenabled()
+                [[i] for i in range(5000)]               # enough container allocations to trigger generation-0 collections
+            return self.lin(x)
+
+    x = torch.randn(8, 16, device=cuda_device)
+    was = gc.isenabled()
+    gc.disable()                                          # the garbage survives until the guard collects it
+    try:
+        old = GraphedForward(Net().to(cuda_device).eval())
+        with torch.no_grad():
+            for _ in range(3):
+                old(x)
+        assert old.captures == 1
+        Owner(old)
+        del old
+        fwd = GraphedForward(Net().to(cuda_device).eval())
+        with torch.no_grad():
+            fwd(x)                                        # eager
+            gc.enable()
+            with warnings.catch_warnings():
+                warnings.simplefilter("error")            # a failed capture warns and falls back to eager
+                out = fwd(x)                              # captures
+            assert torch.equal(out, fwd.net(x))
+        assert fwd.captures == 1
+        assert seen == {"finalised_while_capturing": False, "collector_enabled_during_capture": False}
+        assert gc.isenabled()                             # restored
+    finally:
+        gc.enable() if was else gc.disable()
