@@ -142,9 +142,13 @@ def train_step_ms(backbone, device, *, batch, steps, hp, method="sghmc", num_cla
 
     def one():
         x, y = x_host.to(device), y_host.to(device)
-        loss_, out = runner.model(x, y, runner.net, runner.net0, runner.criterion,
-                                  [pg["lr"] for pg in runner.optimizer.param_groups], runner.Ninflate, runner.nd)
-        runner.optimizer.step()
+        lrs = [pg["lr"] for pg in runner.optimizer.param_groups]
+        if method == "csghmc":                            # methods/csghmc.py:296-304: p.data updated inside, no optimizer.step()
+            loss_, out = runner.model(x, y, runner.net, runner.net0, runner.criterion, lrs, runner.Ninflate, runner.nd,
+                                      should_sample=True)
+        else:                                             # methods/sghmc.py:220-229
+            loss_, out = runner.model(x, y, runner.net, runner.net0, runner.criterion, lrs, runner.Ninflate, runner.nd)
+            runner.optimizer.step()
         pred = out.data.max(dim=1)[1]
         return loss_, pred.ne(y.data).sum().item()
     for _ in range(2):

@@ -225,6 +225,64 @@ def agree_across_ranks(t, what, group=None):
                            f"order (no shuffling, no DistributedSampler) and hold the same chain state")
 
 
+def broadcast_posterior(runner, src=0, group=None):
+    """Hand every rank of the process group rank ``src``'s chain state and posterior statistics -- what a sample-sharded
+    ``evaluate()`` / ``full_batch_likelihoods()`` (hparams ``eval_shard=1``) needs the ranks to agree on ("every
+    rank holds the per-cycle mom1/mom2, loaded from the ckpt or broadcast once"): theta, the network's buffers (BatchNorm
+    running statistics), the running moments with their counts (burn-in runners: ``post_theta_mom1/2``, ``post_theta_cnt``;
+    cyclical runners: ``cycle_theta_mom1/2``, ``samples_per_cycle``, ``cycle_likelihoods``, ``current_cycle``) and the seed
+    of the draws.  One object broadcast of the small metadata, then one tensor broadcast per flat vector (padded layout,
+    1.22 GB each at ViT-L/32 size: NCCL over NVLink).  Sampler state that only training uses (momentum, Adam moments,
+    SGD buffers) stays local -- the ranks may go on as independent chains afterwards."""
+    import torch.distributed as dist
+    rank = dist.get_rank(group)
+    gsrc = dist.get_global_rank(group, src) if group is not None else src
+    ch = runner._chain()
+    dev, n = ch.device, ch.layout.n_padded
+    cyclical = hasattr(runner, "_cyc1")
+    if rank == src:
+        if cyclical:
+            meta = dict(kind="cyclical", cyc1=sorted(runner._cyc1), cyc2=sorted(runner._cyc2),
+                        samples_per_cycle=dict(runner.samples_per_cycle), cycle_likelihoods=dict(runner.cycle_likelihoods),
+                        current_cycle=runner.current_cycle)
+        else:
+            meta = dict(kind="burnin", has=runner._mom1 is not None, post_theta_cnt=getattr(runner, "post_theta_cnt", 0))
+        meta.update(seed=runner.seed, n=n, eval_calls=runner._eval_calls)
+    else:
+        meta = None
+    box = [meta]
+    dist.broadcast_object_list(box, src=gsrc, group=group)
+    meta = box[0]
+    if meta["kind"] != ("cyclical" if cyclical else "burnin") or meta["n"] != n:
+        raise RuntimeError("broadcast_posterior: the ranks hold different runner families / layouts")
+
+    def bc(t):
+        dist.broadcast(t, src=gsrc, group=group)
+        return t
+
+    def recv(t):                                             # receivers reuse a buffer of the right size, else allocate one
+        if t is None or t.numel() != n:
+            t = alloc_flat(n, dev)
+        return bc(t)
+
+    bc(ch.theta)
+    for b in runner.net.buffers():
+        bc(b.data)
+    if cyclical:
+        for attr, cycles in (("_cyc1", meta["cyc1"]), ("_cyc2", meta["cyc2"])):
+            have = getattr(runner, attr)
+            setattr(runner, attr, {c: recv(have.get(c)) for c in cycles})
+        runner.samples_per_cycle = dict(meta["samples_per_cycle"])
+        runner.cycle_likelihoods = dict(meta["cycle_likelihoods"])
+        runner.current_cycle = meta["current_cycle"]
+    elif meta["has"]:
+        runner._mom1, runner._mom2 = recv(runner._mom1), recv(runner._mom2)
+        runner.post_theta_cnt = meta["post_theta_cnt"]
+    runner.seed = meta["seed"]
+    runner._eval_calls = meta["eval_calls"]                  # the Philox sub-sequence of the next evaluation: same on every rank
+    return runner
+
+
 # ------------------------------------------------------------------------------------------------------------
 # Model-sharded Bayesian model average (csghmc_fs, SURVEY 8f row 2)
 # ------------------------------------------------------------------------------------------------------------

@@ -287,6 +287,9 @@ def run_ours(args):
         torch.cuda.empty_cache()
         extras["train_step_resnet101"] = guarded("train_step_resnet101", train_step_extra, device, rank, world, steps=10,
                                                  batch=16, backbone="resnet101")
+        torch.cuda.empty_cache()
+        extras["train_step_resnet101_csghmc"] = guarded("train_step_resnet101_csghmc", train_step_extra, device, rank, world,
+                                                        steps=10, batch=16, backbone="resnet101", method="csghmc")   # configs[1]
     if not args.no_ensemble:
         torch.cuda.empty_cache()
         extras["ensemble"] = guarded("ensemble", ensemble_extra, device, rank, world, args)
@@ -556,12 +559,14 @@ def sample_store_extra(lay, theta, step, device, peak, reps=20):
             "file_identical": bool(same)}
 
 
-def train_step_extra(device, rank, world, steps=6, batch=64, backbone="vit_l_32"):
-    """The call a user of the drop-in makes: Model.forward(x, y, net, net0, criterion, lrs, Ninflate, nd)."""
+def train_step_extra(device, rank, world, steps=6, batch=64, backbone="vit_l_32", method="sghmc"):
+    """The call a user of the drop-in makes: Model.forward(x, y, net, net0, criterion, lrs, Ninflate, nd[, should_sample]).
+    ``method``: "sghmc" (BASELINE.json configs[2], ViT-L/32) or "csghmc" (configs[1], ResNet-101, sampling phase)."""
     import argparse as ap
+    import importlib
     import logging
     from bayesdll_b200 import shapes
-    from bayesdll_b200.methods import sghmc
+    mod = importlib.import_module(f"bayesdll_b200.methods.{method}")
     torch.manual_seed(42 + rank)
     with torch.device(device):
         net = shapes.create_backbone(backbone, 37)
@@ -569,11 +574,13 @@ def train_step_extra(device, rank, world, steps=6, batch=64, backbone="vit_l_32"
     a = ap.Namespace(device=device, ND=HP["ND"], lr=HP["lr_body"], lr_head=HP["lr_head"], momentum=0.5, epochs=1,
                      pretrained="synthetic", num_classes=37, ece_num_bins=15, test_eval_freq=1, log_dir=tempfile.gettempdir(),
                      seed=42 + rank,
+                     num_cycles=1, proportion_exploration=0.5, full_sample=False,
                      hparams=dict(prior_sig="1.0", Ninflate="1e3", nd="1.0", momentum_decay="0.18", burnin="5", thin="1",
                                   bias="informative", nst="5"))
     lg = logging.getLogger("bench")
     lg.addHandler(logging.NullHandler())
-    runner = sghmc.Runner(net, net0, a, lg)
+    runner = mod.Runner(net, net0, a, lg)
+    extra = dict(should_sample=True) if method == "csghmc" else {}
     runner.net.train()
     x_host = torch.randn(batch, 3, 224, 224).pin_memory()
     y_host = torch.randint(0, 37, (batch,)).pin_memory()
@@ -581,7 +588,7 @@ def train_step_extra(device, rank, world, steps=6, batch=64, backbone="vit_l_32"
 
     def one():
         x, y = x_host.to(device, non_blocking=True), y_host.to(device, non_blocking=True)
-        loss, _ = runner.model(x, y, runner.net, runner.net0, runner.criterion, lrs, runner.Ninflate, runner.nd)
+        loss, _ = runner.model(x, y, runner.net, runner.net0, runner.criterion, lrs, runner.Ninflate, runner.nd, **extra)
         return loss
     for _ in range(3):
         one()
@@ -615,6 +622,8 @@ def train_step_extra(device, rank, world, steps=6, batch=64, backbone="vit_l_32"
     # (baseline/eager_port.py restating methods/sghmc.py:482-510, :229) on the same network and GPU
     ref_ms = None
     try:
+        if method != "sghmc":
+            raise LookupError("the restatement covers SGHMC only; see reference_ms_per_step")
         from baseline import eager_port
         names = [nm for nm, _ in runner.net.named_parameters()]
         params = [p for _, p in runner.net.named_parameters()]
@@ -641,13 +650,15 @@ def train_step_extra(device, rank, world, steps=6, batch=64, backbone="vit_l_32"
         torch.cuda.synchronize()
         ref_ms = allmax(time.perf_counter() - t0, world, device) / steps * 1e3
         del mom
+    except LookupError as e:
+        ref_ms = str(e)
     except Exception as e:                                   # context figure only
         ref_ms = f"failed: {type(e).__name__}: {e}"
     res = {"value": world * n * steps / dt, "unit": "params/s", "ms_per_step": dt / steps * 1e3, "steps": steps,
            "graph_train_ms_per_step": graph_ms, "reference_structure_ms_per_step": ref_ms,
            "images_per_s": world * batch * steps / dt, "h2d_bytes_per_step": x_host.numel() * 4 + y_host.numel() * 8,
            "d2h_bytes_per_step": 4, "last_loss": loss,
-           "api": f"bayesdll_b200.methods.sghmc.Model.forward on torchvision {backbone}, batch {batch}, fp32 fwd/bwd in PyTorch"}
+           "api": f"bayesdll_b200.methods.{method}.Model.forward on torchvision {backbone}, batch {batch}, fp32 fwd/bwd in PyTorch"}
     del runner, net, net0
     torch.cuda.empty_cache()
     # ... and the UNMODIFIED reference itself (baseline/_ref): its own backbone factory, Runner, Model.forward +
@@ -658,8 +669,8 @@ def train_step_extra(device, rank, world, steps=6, batch=64, backbone="vit_l_32"
             if reference_arm.available():
                 hp_ref = dict(lr_body=HP["lr_body"], lr_head=HP["lr_head"], ND=HP["ND"], Ninflate=HP["Ninflate"],
                               prior_sig=HP["prior_sig"], nd=HP["nd"], alpha=HP["alpha"])
-                res["reference_ms_per_step"] = reference_arm.train_step_ms(backbone, device, batch=batch, steps=steps, hp=hp_ref)
-                res["reference_kind"] = "reference (unmodified methods/sghmc.py Runner from baseline/_ref on this GPU)"
+                res["reference_ms_per_step"] = reference_arm.train_step_ms(backbone, device, batch=batch, steps=steps, hp=hp_ref, method=method)
+                res["reference_kind"] = f"reference (unmodified methods/{method}.py Runner from baseline/_ref on this GPU)"
             else:
                 res["reference_ms_per_step"] = None
                 res["reference_kind"] = "no reference tree found (baseline/install_ref.py)"

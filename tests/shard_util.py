@@ -30,8 +30,8 @@ def make_loader(batches=(16, 16, 5), seed=3):
     return [(torch.randn(b, 3, 8, 8, generator=gen), torch.randint(0, K, (b,), generator=gen)) for b in batches]
 
 
-def make_runner(method, device, log_dir, nst, eval_shard, cycles=3):
-    torch.manual_seed(11)
+def make_runner(method, device, log_dir, nst, eval_shard, cycles=3, stat_seed=5, init_seed=11):
+    torch.manual_seed(init_seed)
     net, net0 = ConvNet(), ConvNet()
     with torch.no_grad():                                 # non-trivial BatchNorm statistics
         bn = net.features[1]
@@ -47,7 +47,7 @@ def make_runner(method, device, log_dir, nst, eval_shard, cycles=3):
     lg.propagate = False
     runner = importlib.import_module(f"bayesdll_b200.methods.{method}").Runner(net, net0, a, lg)
     n = sum(p.numel() for p in runner.net.parameters())
-    gen = torch.Generator().manual_seed(5)
+    gen = torch.Generator().manual_seed(stat_seed)
     theta = torch.cat([p.detach().reshape(-1).cpu() for p in runner.net.parameters()])
     if hasattr(runner, "cycle_theta_mom1"):
         m1, m2 = {}, {}
@@ -67,11 +67,12 @@ def make_runner(method, device, log_dir, nst, eval_shard, cycles=3):
     return runner
 
 
-def run_case(method, device, log_dir, nst, eval_shard, cycles=3):
+def run_case(method, device, log_dir, nst, eval_shard, cycles=3, runner=None):
     """evaluate() twice (the second call uses the captured CUDA graphs and another Philox sub-sequence), the calibration
     bins of the result, and -- cyclical runners -- full_batch_likelihoods()."""
     from bayesdll_b200 import calibration
-    runner = make_runner(method, device, log_dir, nst, eval_shard, cycles=cycles)
+    if runner is None:
+        runner = make_runner(method, device, log_dir, nst, eval_shard, cycles=cycles)
     loader = make_loader()
     out = {}
     for i in range(2):

@@ -23,7 +23,7 @@ CASES = [("csgld", 2, 3), ("csghmc", 3, 3), ("adam_csghmc", 2, 3), ("csgld", 0, 
          ("adam_sghmc", 0, 3), ("csgld", 5, 8)]
 
 
-def _worker(rank, world, port, method, nst, cycles, multi_gpu, log_dir, q):
+def _worker(rank, world, port, method, nst, cycles, multi_gpu, log_dir, q, broadcast=False):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     import torch.distributed as dist
     dev = torch.device("cuda", rank if multi_gpu else 0)
@@ -32,7 +32,24 @@ def _worker(rank, world, port, method, nst, cycles, multi_gpu, log_dir, q):
         dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
     else:
         dist.init_process_group("gloo", rank=rank, world_size=world)
-    out = shard_util.run_case(method, dev, os.path.join(log_dir, f"r{rank}"), nst, eval_shard=True, cycles=cycles)
+    runner = None
+    if broadcast:
+        # rank 1 starts from ANOTHER chain (other weights, BatchNorm statistics, moments, counts, likelihoods, seed, even
+        # another number of cycles); dist.broadcast_posterior must leave it with rank 0's posterior
+        from bayesdll_b200 import dist as bdist
+        if rank == 0:
+            runner = shard_util.make_runner(method, dev, os.path.join(log_dir, f"r{rank}"), nst, True, cycles=cycles)
+        else:
+            runner = shard_util.make_runner(method, dev, os.path.join(log_dir, f"r{rank}"), nst, True, cycles=cycles + 1,
+                                            stat_seed=99, init_seed=12)
+            runner.seed = 4242
+            runner._eval_calls = 7
+            with torch.no_grad():
+                runner.net.features[1].running_mean.add_(1.0)
+            if hasattr(runner, "post_theta_cnt"):
+                runner.post_theta_cnt = 3
+        bdist.broadcast_posterior(runner, src=0)
+    out = shard_util.run_case(method, dev, os.path.join(log_dir, f"r{rank}"), nst, eval_shard=True, cycles=cycles, runner=runner)
     q.put((rank, out))
     dist.barrier()
     dist.destroy_process_group()
@@ -77,6 +94,32 @@ def test_two_rank_evaluate_is_bit_identical_to_one_rank(cuda_device, tmp_path, m
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     procs = [ctx.Process(target=_worker, args=(r, 2, port, method, nst, cycles, multi_gpu, str(tmp_path), q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted((q.get(timeout=300) for _ in range(2)), key=lambda t: t[0])
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for rank, out in res:
+        _same(out, one, f"rank{rank}")
+
+
+@pytest.mark.parametrize("method,nst,cycles", [("csgld", 2, 3), ("csghmc", 3, 2), ("sghmc", 4, 3)])
+def test_broadcast_posterior_then_sharded_evaluate(cuda_device, tmp_path, method, nst, cycles):
+    """"every rank holds the per-cycle mom1/mom2 (loaded from the ckpt or broadcast once)".  Rank 1 starts from a
+    different chain; after dist.broadcast_posterior(runner, src=0) the sample-sharded evaluation of both ranks equals the
+    single-rank evaluation of rank 0's posterior bit for bit."""
+    os.makedirs(tmp_path / "one", exist_ok=True)
+    one = shard_util.run_case(method, cuda_device, tmp_path / "one", nst, eval_shard=False, cycles=cycles)
+    multi_gpu = torch.cuda.device_count() >= 2
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    for r in range(2):
+        os.makedirs(tmp_path / f"r{r}", exist_ok=True)
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, method, nst, cycles, multi_gpu, str(tmp_path), q, True)) for r in range(2)]
     for p in procs:
         p.start()
     res = sorted((q.get(timeout=300) for _ in range(2)), key=lambda t: t[0])
