@@ -1,17 +1,21 @@
-"""Multi-GPU paths.  The reference is single-device; both paths are new surface.
+"""Multi-GPU paths.  The reference is single-device; everything here is new surface.
 
 * Independent chains: one process per GPU (``torchrun``), distinct seeds, **no communication** -- nothing to do
   here beyond ``chain_seed``.
-* Sample-sharded posterior-predictive ensemble: the S = cycles x nst posterior samples are dealt round-robin to the
-  ranks; every rank draws its samples with the counter-based Philox stream keyed by (evaluation, batch, cycle,
-  sample) -- so the draws do not depend on the rank count --, runs the backbone forward and accumulates
-  a running logsumexp_s log_softmax(logits_s) per cycle as (max, scaled sum).  One exchange step (NCCL over NVLink:
-  all-reduce MAX then SUM of ``[C, N, K]`` fp32, 4.3 MB each at Pets size) combines the ranks; the log / GMM mixture /
-  CE / calibration reductions follow, the calibration bins being
-  sharded by row with a second tiny all-reduce of the 3*M+2 bin statistics.
+* Sample-sharded evaluation behind the unchanged Runner API (hparams ``eval_shard=1``; methods/_base.py): the
+  S = cycles x nst posterior samples are dealt round-robin to the ranks (``my_samples``); every rank draws its samples
+  with the counter-based Philox stream keyed by (evaluation, batch, cycle, sample) -- so the draws do not depend on the
+  rank count --, runs the backbone forward, and ONE all-gather of the local sample logits (``gather_samples``) rebuilds
+  the reference's ``logits_all`` on every rank; all later reductions run on the full stack with the kernels one rank
+  runs: results bit-identical to one rank.  ``agree_across_ranks`` makes ranks that walked different data fail loudly,
+  ``broadcast_posterior`` hands every rank one rank's chain state and posterior statistics ("broadcast once").
+* ``ShardedEnsemble``: the variant for callers that do not need ``logits_all`` -- a running logsumexp_s
+  log_softmax(logits_s) per cycle as (max, scaled sum), ONE exchange step (all-reduce MAX then SUM of ``[C, N, K]`` fp32,
+  4.3 MB each at Pets size), then log / GMM mixture / CE.
+* ``calibrate_sharded``: calibration bins with the rows dealt to the ranks and one all-reduce of the 3*M+2 bin statistics.
+* ``bma_evaluate``: model-sharded Bayesian model average of csghmc_fs (one all-gather).
 """
 import copy
-import time
 
 import numpy as np
 import torch
