@@ -257,7 +257,10 @@ def broadcast_posterior(runner, src=0, group=None):
     box = [meta]
     dist.broadcast_object_list(box, src=gsrc, group=group)
     meta = box[0]
-    if meta["kind"] != ("cyclical" if cyclical else "burnin") or meta["n"] != n:
+    # every rank must take the same decision, or the ranks that go on would wait forever for the one that raised
+    ok = torch.tensor([int(meta["kind"] == ("cyclical" if cyclical else "burnin") and meta["n"] == n)], dtype=torch.int32, device=dev)
+    dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=group)
+    if not int(ok.item()):
         raise RuntimeError("broadcast_posterior: the ranks hold different runner families / layouts")
 
     def bc(t):

@@ -262,3 +262,93 @@ def test_gather_samples_restores_sample_order(world, S):
         assert ok, f"rank {rank}: gathered stack differs"
         assert mine == [j for j in range(S) if j % world == rank]
         assert disagree is not None and "disagree" in disagree
+
+
+class _StubChain:
+    def __init__(self, n, fill):
+        self.device = torch.device("cpu")
+        self.theta = torch.full((n,), float(fill))
+        self.layout = type("L", (), {"n_padded": n})()
+
+
+class _StubRunner:
+    """The attributes dist.broadcast_posterior touches on a drop-in Runner (methods/_base.py), on CPU tensors."""
+
+    def __init__(self, rank, cyclical, n=24):
+        self._ch = _StubChain(n, 1 + rank)
+        self.net = torch.nn.BatchNorm1d(3)
+        with torch.no_grad():
+            self.net.running_mean.fill_(0.5 + rank)
+            self.net.num_batches_tracked.fill_(7 + rank)
+        self.seed, self._eval_calls = 100 + rank, 3 + 4 * rank
+        if cyclical:
+            cycles = [1, 2] if rank == 0 else [1, 2, 3]                   # the receiver even holds another number of cycles
+            self._cyc1 = {c: torch.full((n,), 10.0 * c + rank) for c in cycles}
+            self._cyc2 = {c: torch.full((n,), 20.0 * c + rank) for c in cycles if rank or c != 2}   # src: cycle 2 has no 2nd moment yet
+            self.samples_per_cycle = {c: 4 + c + rank for c in cycles}
+            self.cycle_likelihoods = {c: [0.1 * c + rank] for c in cycles}
+            self.current_cycle = cycles[-1]
+        else:
+            self._mom1 = torch.full((n,), 3.0) if rank == 0 else None     # the receiver has not started collecting
+            self._mom2 = torch.full((n,), 9.0) if rank == 0 else None
+            self.post_theta_cnt = 5 if rank == 0 else 1
+
+    def _chain(self):
+        return self._ch
+
+
+def _bcast_worker(rank, world, port, cyclical, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    import torch.distributed as dist
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    r = _StubRunner(rank, cyclical)
+    bdist.broadcast_posterior(r, src=0)
+    state = dict(theta=r._ch.theta.clone(), rm=r.net.running_mean.clone(), nbt=int(r.net.num_batches_tracked), seed=r.seed,
+                 calls=r._eval_calls)
+    if cyclical:
+        state.update(c1={c: t.clone() for c, t in r._cyc1.items()}, c2={c: t.clone() for c, t in r._cyc2.items()},
+                     spc=r.samples_per_cycle, lik=r.cycle_likelihoods, cur=r.current_cycle)
+    else:
+        state.update(m1=r._mom1.clone(), m2=r._mom2.clone(), cnt=r.post_theta_cnt)
+    mismatch = None
+    if not cyclical:                                                      # a rank holding the other runner family is refused
+        other = _StubRunner(rank, cyclical=(rank == 1))
+        try:
+            bdist.broadcast_posterior(other, src=0)
+        except RuntimeError as e:
+            mismatch = str(e)
+    q.put((rank, state, mismatch))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("cyclical", [True, False])
+def test_broadcast_posterior_world2(cyclical):
+    """SURVEY 8e "broadcast once": after dist.broadcast_posterior(runner, src=0) rank 1 holds rank 0's theta, buffers,
+    moments (exactly rank 0's cycles), counts, likelihoods, draw seed and evaluation counter."""
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_bcast_worker, args=(r, 2, port, cyclical, q), daemon=True) for r in range(2)]
+    for p in procs:
+        p.start()
+    try:
+        res = sorted((q.get(timeout=120) for _ in range(2)), key=lambda t: t[0])
+        for p in procs:
+            p.join(timeout=60)
+            assert p.exitcode == 0
+    finally:
+        for p in procs:                                   # a rank stuck in a collective must not outlive the test
+            if p.is_alive():
+                p.terminate()
+    want = _StubRunner(0, cyclical)
+    for rank, st, mismatch in res:
+        assert torch.equal(st["theta"], want._ch.theta) and torch.equal(st["rm"], want.net.running_mean)
+        assert st["nbt"] == 7 and st["seed"] == 100 and st["calls"] == 3
+        if cyclical:
+            assert sorted(st["c1"]) == [1, 2] and sorted(st["c2"]) == [1]
+            assert all(torch.equal(st["c1"][c], want._cyc1[c]) for c in st["c1"]) and torch.equal(st["c2"][1], want._cyc2[1])
+            assert st["spc"] == want.samples_per_cycle and st["lik"] == want.cycle_likelihoods and st["cur"] == 2
+        else:
+            assert torch.equal(st["m1"], want._mom1) and torch.equal(st["m2"], want._mom2) and st["cnt"] == 5
+            assert mismatch is not None and "different runner families" in mismatch, f"rank {rank}: {mismatch}"
