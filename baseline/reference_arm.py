@@ -161,7 +161,7 @@ def train_step_ms(backbone, device, *, batch, steps, hp, method="sghmc", num_cla
     return (time.perf_counter() - t0) / steps * 1e3
 
 
-def cfg1_mlp_mnist(device="cpu", batches=20, batch_size=128, test_batches=8, reference=True, seed=42):
+def cfg1_mlp_mnist(device="cpu", batches=20, batch_size=128, test_batches=8, reference=True, seed=42, graph_train=False):
     """BASELINE.json configs[0] (README.md:83): mlp_mnist SGLD, prior_sig=1, Ninflate=1e3, nd=1, burnin=5, thin=10, nst=5,
     lr 1e-2, momentum 0.5, synthetic 28x28 batches of 128, ND = 30 000.  ``reference=True``: the unmodified reference Runner
     (CPU by contract); False: the drop-in Runner on ``device``.  -> ms/step, param updates/s, ensemble preds/s, analyze ms."""
@@ -172,6 +172,8 @@ def cfg1_mlp_mnist(device="cpu", batches=20, batch_size=128, test_batches=8, ref
     if device.type == "cpu":
         torch.set_num_threads(host_cores())
     hp = dict(prior_sig="1.0", Ninflate="1e3", nd="1.0", burnin="5", thin="10", bias="informative", nst="5")
+    if graph_train and not reference:
+        hp["graph_train"] = "1"                           # drop-in only: forward + loss + backward as one CUDA-graph replay
     a = argparse.Namespace(device=device, ND=30000, lr=1e-2, lr_head=1e-2, momentum=0.5, epochs=1, pretrained=None,
                            hparams=hp, test_eval_freq=1, ece_num_bins=15, num_classes=10, backbone="mlp_mnist",
                            log_dir=tempfile.mkdtemp(prefix="bdl_cfg1_"), seed=seed)
@@ -195,7 +197,7 @@ def cfg1_mlp_mnist(device="cpu", batches=20, batch_size=128, test_batches=8, ref
         net = shapes.create_backbone("mlp_mnist", 10)      # same architecture as networks/small_nets.MLP(784, 10, 1000, 3)
     runner = sgld.Runner(net, None, a, _quiet_logger())
     # warm-up epoch fragment, then the timed epoch (collect=True: moments every `thin` steps, as after burn-in)
-    runner.train_one_epoch(train[:3], collect=False, bi=0)
+    runner.train_one_epoch(train[:4] if graph_train else train[:3], collect=False, bi=0)   # graph_train: 2 eager + capture + replay
     n_params = sum(p.numel() for p in runner.net.parameters())
     with torch.no_grad():
         theta = torch.nn.utils.parameters_to_vector(runner.net.parameters())
@@ -223,7 +225,8 @@ def cfg1_mlp_mnist(device="cpu", batches=20, batch_size=128, test_batches=8, ref
         ece, mce, nll = calibration.analyze(targets, logits, 15, None)
     analyze_ms = (time.perf_counter() - t0) * 1e3
     rows = len(targets)
-    return {"impl": "reference (unmodified methods/sgld.py Runner)" if reference else "bayesdll_b200.methods.sgld.Runner",
+    return {"impl": "reference (unmodified methods/sgld.py Runner)" if reference else
+            ("bayesdll_b200.methods.sgld.Runner, hparams graph_train=1" if graph_train else "bayesdll_b200.methods.sgld.Runner"),
             "device": str(device), "cores": host_cores() if device.type == "cpu" else None, "params": n_params,
             "ms_per_step": step_ms, "param_updates_per_s": n_params / (step_ms * 1e-3), "batch": batch_size,
             "ensemble_preds_per_s": rows * 5 / eval_s, "eval_rows": rows, "nst": 5, "analyze_ms": analyze_ms,

@@ -306,7 +306,8 @@ def run_ours(args):
             cpu_baseline = dict(port, reference_error=ref)
     if rank == 0 and world == 1 and not args.no_cfg1:
         extras["cfg1_mlp_mnist_sgld"] = {"reference_cpu": guarded("cfg1 reference", cfg1_line, True, "cpu"),
-                                         "ours_b200": guarded("cfg1 ours", cfg1_line, False, device)}
+                                         "ours_b200": guarded("cfg1 ours", cfg1_line, False, device),
+                                         "ours_b200_graph_train": guarded("cfg1 ours (graph_train=1)", cfg1_line, False, device, True)}
 
     ens = extras.get("ensemble")
     if isinstance(e2e, dict) and isinstance(ens, dict) and "value" in ens:
@@ -940,11 +941,11 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
-def cfg1_line(reference, device):
+def cfg1_line(reference, device, graph_train=False):
     from baseline import reference_arm
     if reference and reference_arm.available() is None:
         return {"unavailable": "no reference tree (/root/reference or baseline/_ref)"}
-    return reference_arm.cfg1_mlp_mnist(device=device, reference=reference)
+    return reference_arm.cfg1_mlp_mnist(device=device, reference=reference, graph_train=graph_train)
 
 
 def main():
