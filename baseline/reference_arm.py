@@ -172,8 +172,8 @@ def cfg1_mlp_mnist(device="cpu", batches=20, batch_size=128, test_batches=8, ref
     if device.type == "cpu":
         torch.set_num_threads(host_cores())
     hp = dict(prior_sig="1.0", Ninflate="1e3", nd="1.0", burnin="5", thin="10", bias="informative", nst="5")
-    if graph_train and not reference:
-        hp["graph_train"] = "1"                           # drop-in only: forward + loss + backward as one CUDA-graph replay
+    if not reference:                                     # drop-in only: the default (auto = CUDA-graph replay for this MLP) or eager
+        hp["graph_train"] = "auto" if graph_train else "0"
     a = argparse.Namespace(device=device, ND=30000, lr=1e-2, lr_head=1e-2, momentum=0.5, epochs=1, pretrained=None,
                            hparams=hp, test_eval_freq=1, ece_num_bins=15, num_classes=10, backbone="mlp_mnist",
                            log_dir=tempfile.mkdtemp(prefix="bdl_cfg1_"), seed=seed)
@@ -226,7 +226,7 @@ def cfg1_mlp_mnist(device="cpu", batches=20, batch_size=128, test_batches=8, ref
     analyze_ms = (time.perf_counter() - t0) * 1e3
     rows = len(targets)
     return {"impl": "reference (unmodified methods/sgld.py Runner)" if reference else
-            ("bayesdll_b200.methods.sgld.Runner, hparams graph_train=1" if graph_train else "bayesdll_b200.methods.sgld.Runner"),
+            ("bayesdll_b200.methods.sgld.Runner (default: graph_train=auto)" if graph_train else "bayesdll_b200.methods.sgld.Runner, hparams graph_train=0"),
             "device": str(device), "cores": host_cores() if device.type == "cpu" else None, "params": n_params,
             "ms_per_step": step_ms, "param_updates_per_s": n_params / (step_ms * 1e-3), "batch": batch_size,
             "ensemble_preds_per_s": rows * 5 / eval_s, "eval_rows": rows, "nst": 5, "analyze_ms": analyze_ms,

@@ -97,6 +97,7 @@ class FusedModel(nn.Module):
         self._opts = dict(sgd_momentum=0.0, seed=None, noise="philox", grad_mode="table", div_mode=_lib.DIV_RECIP,
                           optimizer=None, graph_train=False, release_grads=True)
         self._train_graphs = {}        # (net, shapes, criterion) -> eager-call count | captured graph | "eager"
+        self._auto_graph = {}          # (id(net), id(criterion)) -> (weakref(net), eligible for graph_train=auto)
 
     def configure(self, **opts):
         unknown = set(opts) - set(self._opts)
@@ -154,7 +155,7 @@ class FusedModel(nn.Module):
         chain = self._ensure_chain(net, net0)
         if self.VARIANT in (_lib.ADAM_SGHMC, _lib.ADAM_CSGHMC):
             self.t += 1                                   # methods/adam_sghmc.py:494
-        replayed = self._graphed_fwd_bwd(x, y, net, criterion) if self._opts["graph_train"] else None
+        replayed = self._graphed_fwd_bwd(x, y, net, criterion) if self._graph_train_wanted(net, criterion) else None
         if replayed is not None:
             loss, out = replayed
         else:
@@ -172,13 +173,34 @@ class FusedModel(nn.Module):
                 p.grad = None
         return loss.detach(), out.detach()
 
-    # ---- optional: forward + backward as ONE CUDA-graph replay (hparams graph_train=1) -----------------------------
+    # ---- forward + backward as ONE CUDA-graph replay (hparams graph_train=auto|1|0) ----------------------------------
+    # Module classes whose forward is known to have no host-side control flow on tensor VALUES: torch's own layers, the
+    # torchvision model zoo (the reference's resnet101 / vit_l_32, networks/__init__.py:20-54), the reference's MLP
+    # (networks/small_nets.py) and this package's copy of it.  ``graph_train=auto`` (the Runner default) captures only
+    # networks AND criteria built from these alone; anything user-defined runs eagerly unless ``graph_train=1`` says so.
+    _STATIC_MODULE_PREFIXES = ("torch.nn.", "torchvision.models.", "networks.small_nets", "bayesdll_b200.shapes")
+    _MAX_TRAIN_GRAPHS = 4              # captured (network, batch shape) combinations per Model; further shapes run eagerly
+
+    def _graph_train_wanted(self, net, criterion):
+        want = self._opts["graph_train"]
+        if want != "auto":
+            return bool(want)
+        key = (id(net), id(criterion))
+        hit = self._auto_graph.get(key)
+        if hit is None or hit[0]() is not net:            # the weak reference guards against a recycled id()
+            import weakref
+            ok = isinstance(criterion, nn.Module) and all(
+                type(m).__module__.startswith(self._STATIC_MODULE_PREFIXES) for m in list(net.modules()) + list(criterion.modules()))
+            hit = self._auto_graph[key] = (weakref.ref(net), ok)
+        return hit[1]
+
     def _graphed_fwd_bwd(self, x, y, net, criterion):
         """The backbone's forward + loss + backward replayed as a CUDA graph (the fused sampler step stays a separate
         launch: its scalars and Philox counter change every step).  Same kernels as eager, so gradients, BatchNorm
         buffers and the loss are bit-identical; what disappears is the host's launch cost (ResNet-101, batch 16: ~1000
         launches per step), and the gradients live at fixed addresses, so the per-tensor run table stops changing.
-        Opt-in because a capture freezes host-side control flow of ``net.forward`` / ``criterion``.  Per key the first two
+        A capture freezes host-side control flow of ``net.forward`` / ``criterion``: ``graph_train=auto`` therefore captures
+        only framework-provided modules (``_graph_train_wanted``), ``graph_train=1`` anything.  Per key the first two
         calls run eagerly (warm-up), the third captures; a failed capture falls back to eager with one warning.
         Returns (loss, out) clones with ``p.grad`` populated, or None when this call has to run eagerly."""
         if not (x.is_cuda and net.training):
@@ -192,6 +214,11 @@ class FusedModel(nn.Module):
         if isinstance(ent, int):
             if ent < 2:
                 self._train_graphs[key] = ent + 1
+                return None
+            if sum(isinstance(v, dict) for v in self._train_graphs.values()) >= self._MAX_TRAIN_GRAPHS:
+                # a loader that keeps producing new batch shapes must not keep producing graphs (each owns a private pool
+                # with a full set of activations): the first few shapes are replayed, the rest runs eagerly
+                self._train_graphs[key] = "eager"
                 return None
             try:
                 net.zero_grad()                           # gradients must be allocated inside the graph's private pool
@@ -423,7 +450,7 @@ class _RunnerCommon:
         self.seed = int(seed) if seed is not None else torch.initial_seed()
         self.model.configure(sgd_momentum=mu, seed=self.seed, noise=self.noise_mode,
                              grad_mode=str(hp.get("grad", "table")), div_mode=self.div_mode, optimizer=self.optimizer,
-                             graph_train=bool(int(float(hp.get("graph_train", 0)))))
+                             graph_train=self._parse_graph_train(hp.get("graph_train", "auto")))
         self._eval_calls = 0
         # eval_shard=1: inside an initialised torch.distributed process group whose ranks hold the SAME chain state,
         # evaluate() / full_batch_likelihoods() deal the posterior samples round-robin to the ranks; results
@@ -440,6 +467,14 @@ class _RunnerCommon:
         # checkpoint / sample writers: 'async' (default) overlaps D2H + serialisation with training, 'sync' behaves like
         # the reference's in-line torch.save (file complete when save_ckpt returns)
         self._writer = AsyncWriter(args.device, mode=str(hp.get("io", "async")))
+
+    @staticmethod
+    def _parse_graph_train(value):
+        """hparams graph_train: 'auto' (default: CUDA-graph replay of forward + loss + backward for networks and criteria
+        made of framework-provided modules only, eager otherwise), 1 (always try), 0 (never)."""
+        if str(value).strip().lower() == "auto":
+            return "auto"
+        return bool(int(float(value)))
 
     def flush_io(self):
         """Block until every checkpoint / sample file submitted so far is on disk."""

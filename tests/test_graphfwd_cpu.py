@@ -44,3 +44,31 @@ def test_training_capture_declines_cpu_tensors_and_eval_mode():
         assert "no_such_option" in str(e)
     else:
         raise AssertionError("unknown option accepted")
+
+
+def test_graph_train_auto_only_trusts_framework_modules():
+    """hparams graph_train=auto (the Runner default): forward + loss + backward are captured only when the network AND the
+    criterion consist of framework-provided modules (torch.nn, the torchvision model zoo, the reference's MLP), whose
+    forward has no host-side control flow on tensor values; anything user-defined stays eager unless graph_train=1."""
+    import torchvision
+    from bayesdll_b200 import shapes
+    from bayesdll_b200.methods import sghmc
+    from bayesdll_b200.methods._base import _RunnerCommon
+    assert _RunnerCommon._parse_graph_train("auto") == "auto" and _RunnerCommon._parse_graph_train("AUTO ") == "auto"
+    assert _RunnerCommon._parse_graph_train("1") is True and _RunnerCommon._parse_graph_train("0.0") is False
+    model = sghmc.Model(ND=10)
+    assert model._opts["graph_train"] is False            # a bare Model keeps the explicit opt-in; the Runner configures "auto"
+    model.configure(graph_train="auto")
+    ce = torch.nn.CrossEntropyLoss()
+    seq = torch.nn.Sequential(torch.nn.Conv2d(3, 4, 3), torch.nn.BatchNorm2d(4), torch.nn.ReLU(), torch.nn.Flatten(), torch.nn.LazyLinear(5))
+    assert model._graph_train_wanted(torchvision.models.resnet18(), ce)
+    assert model._graph_train_wanted(torchvision.models.vit_b_32(), ce)
+    assert model._graph_train_wanted(shapes.create_backbone("mlp_mnist", 10), ce)
+    assert model._graph_train_wanted(seq, ce)
+    assert not model._graph_train_wanted(_Net(), ce)                                  # user-defined forward
+    assert not model._graph_train_wanted(torch.nn.Sequential(torch.nn.Linear(4, 4), _Net()), ce)   # ... anywhere inside
+    assert not model._graph_train_wanted(seq, lambda out, y: out.sum())                # user-defined criterion
+    model.configure(graph_train=True)
+    assert model._graph_train_wanted(_Net(), ce)
+    model.configure(graph_train=False)
+    assert not model._graph_train_wanted(seq, ce)

@@ -119,3 +119,79 @@ def test_capture_keeps_the_cyclic_collector_out(cuda_device):
         assert gc.isenabled()                             # restored
     finally:
         gc.enable() if was else gc.disable()
+
+
+def test_runner_default_captures_framework_networks_and_only_those(cuda_device, tmp_path):
+    """hparams graph_train defaults to 'auto': a Runner training a network built from torch.nn modules replays forward +
+    backward as a CUDA graph from its third step on, bit-identical to graph_train=0; a user-defined module class stays
+    eager under the default."""
+    import argparse
+    import logging
+    from bayesdll_b200.methods import sghmc
+    import shard_util as su
+    monkey = torch.backends.cudnn.deterministic
+    torch.backends.cudnn.deterministic = True
+    try:
+        def make_net(seed, custom):
+            torch.manual_seed(seed)
+            if custom:
+                return su.ConvNet()
+            net = torch.nn.Sequential(torch.nn.Conv2d(3, 6, 3, padding=1), torch.nn.BatchNorm2d(6), torch.nn.ReLU(),
+                                      torch.nn.AdaptiveAvgPool2d(4), torch.nn.Flatten(), torch.nn.Linear(96, su.K))
+            net.readout_name = "5"
+            return net
+
+        def run(hp_extra, custom=False):
+            hp = dict(prior_sig=1.0, Ninflate=10.0, nd=1.0, burnin=0, thin=1, nst=2, bias="informative", momentum_decay=0.18, seed=5,
+                      **hp_extra)
+            a = argparse.Namespace(device=cuda_device, ND=64, lr=1e-3, lr_head=1e-2, momentum=0.5, epochs=1, pretrained="synthetic",
+                                   hparams={k: str(v) for k, v in hp.items()}, test_eval_freq=1, ece_num_bins=15, num_classes=su.K,
+                                   log_dir=str(tmp_path), seed=5)
+            lg = logging.getLogger("auto")
+            lg.addHandler(logging.NullHandler())
+            lg.propagate = False
+            runner = sghmc.Runner(make_net(1, custom), make_net(2, custom), a, lg)
+            runner.net.train()
+            gen = torch.Generator().manual_seed(9)
+            outs = []
+            for _ in range(6):
+                x, y = torch.randn(8, 3, 8, 8, generator=gen).to(cuda_device), torch.randint(0, su.K, (8,), generator=gen).to(cuda_device)
+                loss, out = runner.model(x, y, runner.net, runner.net0, runner.criterion, [1e-3, 1e-2], runner.Ninflate, runner.nd)
+                outs.append((loss, out.clone(), runner.model.chain.theta.clone(), [b.clone() for b in runner.net.buffers()]))
+            captured = sum(isinstance(v, dict) for v in runner.model._train_graphs.values())
+            runner.flush_io()
+            return outs, captured, runner.model._opts["graph_train"]
+
+        auto, n_auto, mode = run({})
+        eager, n_eager, _ = run(dict(graph_train=0))
+        assert mode == "auto" and n_auto == 1 and n_eager == 0
+        for (l1, o1, t1, b1), (l0, o0, t0, b0) in zip(auto, eager):
+            assert l1 == l0 and torch.equal(o1, o0) and torch.equal(t1, t0) and all(torch.equal(a, b) for a, b in zip(b1, b0))
+        _, n_custom, _ = run({}, custom=True)
+        assert n_custom == 0                                # su.ConvNet is a user-defined class: not captured by default
+        _, n_forced, _ = run(dict(graph_train=1), custom=True)
+        assert n_forced == 1
+    finally:
+        torch.backends.cudnn.deterministic = monkey
+
+
+def test_training_graphs_are_capped_per_model(cuda_device):
+    """A loader that keeps producing new batch shapes must not keep producing CUDA graphs (each owns a private pool with a
+    full set of activations): FusedModel._MAX_TRAIN_GRAPHS shapes are replayed, later ones run eagerly -- same results."""
+    from bayesdll_b200.methods import sgld
+    torch.manual_seed(0)
+    net = torch.nn.Sequential(torch.nn.Linear(6, 8), torch.nn.Tanh(), torch.nn.Linear(8, 3)).to(cuda_device).train()
+    net.readout_name = "2"
+    net0 = torch.nn.Sequential(torch.nn.Linear(6, 8), torch.nn.Tanh(), torch.nn.Linear(8, 3)).to(cuda_device)
+    model = sgld.Model(ND=100, prior_sig=1.0, bias="informative")
+    model.configure(seed=3, graph_train="auto")
+    crit = torch.nn.CrossEntropyLoss()
+    gen = torch.Generator().manual_seed(1)
+    for rep in range(4):
+        for b in range(2, 9):                                # 7 batch shapes, each seen 4 times
+            x, y = torch.randn(b, 6, generator=gen).to(cuda_device), torch.randint(0, 3, (b,), generator=gen).to(cuda_device)
+            loss, out = model.forward(x, y, net, net0, crit, [1e-2, 1e-2], Ninflate=1.0, nd=1.0)
+            assert out.shape == (b, 3) and loss == loss
+    kinds = list(model._train_graphs.values())
+    assert sum(isinstance(v, dict) for v in kinds) == model._MAX_TRAIN_GRAPHS == 4
+    assert kinds.count("eager") == 3
