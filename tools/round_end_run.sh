@@ -19,4 +19,6 @@ python -c "from bayesdll_b200 import build; print(build.source_hash())" > gpurun
 python tools/run_draws.py > gpurun_out/${R}_plain_draws.log 2>&1 && ncu --set full --clock-control none -k regex:'dropout_mix|draw_kernel' -s 6 -c 6 -o /tmp/${R}_draws_full python tools/run_draws.py > gpurun_out/${R}_ncu_draws.log 2>&1
 tail -2 gpurun_out/${R}_ncu_draws.log
 ncu -i /tmp/${R}_draws_full.ncu-rep --page raw --csv > gpurun_out/${R}_draws_full_raw.csv
+python tools/run_probe.py > gpurun_out/${R}_plain_probe.log 2>&1 && ncu --set full --clock-control none -k regex:probe_stream -c 9 -o /tmp/${R}_probe python tools/run_probe.py > gpurun_out/${R}_ncu_probe.log 2>&1
+ncu -i /tmp/${R}_probe.ncu-rep --page raw --csv > gpurun_out/${R}_probe_stream_raw.csv
 # then, back in the build container:  cp gpurun_out/${R}_steps_full_raw.csv profiles/ && python tools/traffic_from_ncu.py profiles/${R}_steps_full_raw.csv --build-hash $(cat gpurun_out/${R}_steps_build_hash.txt)
