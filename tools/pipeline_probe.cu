@@ -112,14 +112,17 @@ static double now() { return std::chrono::duration<double>(std::chrono::steady_c
 
 int main(int argc, char** argv) {
     size_t n = 305548328;
-    bool timeline = false;
+    bool timeline = false, wc = false, quick = false;
     for (int i = 1; i < argc; ++i) {
         if (!strcmp(argv[i], "--timeline")) timeline = true;
+        else if (!strcmp(argv[i], "--wc")) wc = true;          // gradient buffer in WRITE-COMBINED pinned memory (the host only writes it)
+        else if (!strcmp(argv[i], "--quick")) quick = true;    // ceilings + chain / nokernel only
         else n = strtoull(argv[i], nullptr, 10) / 4 * 4;
     }
     Ctx c{};
     c.n = n;
-    CK(cudaHostAlloc(&c.g_h, n * 4, cudaHostAllocDefault));
+    CK(cudaHostAlloc(&c.g_h, n * 4, wc ? cudaHostAllocWriteCombined : cudaHostAllocDefault));
+    printf("gradient host buffer: %s pinned memory\n", wc ? "write-combined" : "default");
     CK(cudaHostAlloc(&c.out_h, n * 4, cudaHostAllocMapped));
     for (size_t i = 0; i < n; ++i) c.g_h[i] = 1e-2f * float((i * 2654435761u) >> 8 & 0xffff) / 65536.f;
     memset(c.out_h, 0, n * 4);
@@ -161,14 +164,14 @@ int main(int argc, char** argv) {
     }
     const char* names[4] = {"chain", "nokernel", "alt2", "mapped"};
     const size_t chunks[] = {1u << 20, 2u << 20, 4u << 20, 8u << 20, 16u << 20};
-    for (int mode = 0; mode < 4; ++mode)
+    for (int mode = 0; mode < (quick ? 2 : 4); ++mode)
         for (size_t chunk : chunks) {
             const double ms = timeit([&] { step(c, mode, chunk, eh, ec, nullptr); });
             printf("%-9s chunk %3zu Mi elems (%4zu chunks): %7.2f ms  %5.1f GB/s each way\n", names[mode], chunk >> 20,
                    (n + chunk - 1) / chunk, ms, n * 4 / ms / 1e6);
             fflush(stdout);
         }
-    for (int cap : {8, 16, 32, 64, 148, 592})
+    if (!quick) for (int cap : {8, 16, 32, 64, 148, 592})
         for (size_t chunk : {size_t(1) << 20, size_t(2) << 20, size_t(4) << 20, size_t(8) << 20}) {
             c.cap = cap;
             const double k1 = timeit([&] { step_like_capped<<<cap, 256, 0, c.s_cmp[0]>>>(c.theta, c.g, c.theta0, c.v, 0, chunk / 4); CK(cudaStreamSynchronize(c.s_cmp[0])); });
