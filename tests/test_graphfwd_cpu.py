@@ -72,3 +72,31 @@ def test_graph_train_auto_only_trusts_framework_modules():
     assert model._graph_train_wanted(_Net(), ce)
     model.configure(graph_train=False)
     assert not model._graph_train_wanted(seq, ce)
+
+
+def test_eval_copy_refresh_inherits_live_buffers_in_place():
+    """_EvalNet.refresh (the cached evaluation copy, methods/_base.py): the live network's buffers are copied IN PLACE -- the
+    addresses a captured graph reads stay valid --, parameters stay views of the copy's own flat buffer, and a network whose
+    buffers no longer match is refused (the caller then builds a fresh copy)."""
+    from bayesdll_b200.flat import FlatLayout
+    from bayesdll_b200.methods._base import _EvalNet
+    torch.manual_seed(0)
+    net = torch.nn.Sequential(torch.nn.Linear(4, 6), torch.nn.BatchNorm1d(6), torch.nn.Linear(6, 3))
+    net.readout_name = "2"
+    lay = FlatLayout([(n, tuple(p.shape)) for n, p in net.named_parameters()], "2")
+    ev = _EvalNet(net, lay, graph=True)
+    bn_live, bn_copy = net[1], ev.net[1]
+    ptrs = [b.data_ptr() for b in ev.net.buffers()]
+    with torch.no_grad():
+        bn_live.running_mean.add_(1.5)
+        bn_live.running_var.mul_(2.0)
+        bn_live.num_batches_tracked.add_(3)
+    assert not torch.equal(bn_copy.running_mean, bn_live.running_mean)
+    assert ev.refresh(net) is True
+    assert torch.equal(bn_copy.running_mean, bn_live.running_mean) and torch.equal(bn_copy.running_var, bn_live.running_var)
+    assert int(bn_copy.num_batches_tracked) == int(bn_live.num_batches_tracked)
+    assert [b.data_ptr() for b in ev.net.buffers()] == ptrs                  # in place
+    assert all(p.data_ptr() != q.data_ptr() for p, q in zip(ev.net.parameters(), net.parameters()))
+    assert not ev.net.training and ev.net[0].weight.untyped_storage().data_ptr() == ev.flat.untyped_storage().data_ptr()
+    other = torch.nn.Sequential(torch.nn.Linear(4, 6), torch.nn.BatchNorm1d(7), torch.nn.Linear(7, 3))
+    assert ev.refresh(other) is False
